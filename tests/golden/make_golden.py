@@ -1,0 +1,199 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE SOURCES in /root/reference.
+
+Run from the repo root in the build container:  python tests/golden/make_golden.py
+(the GPU box has no /root/reference; it only reads the committed .npz files).
+
+``rank_pes.py`` runs as shipped (NumPy/SciPy).  ``fourier_features.py``, ``pes.py`` and ``dts.py`` run
+under ``oracle/tf_shim.py`` (NumPy stand-in for the TF/TFP/GPflow symbols they call; TF 2.1 is not
+installable offline).  Each file stores the exact inputs the reference function saw and the output
+it returned, so both the oracle restatement (CPU tests) and the CUDA path (GPU tests) can be checked
+against reference-produced numbers.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader, tf_shim  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def se_kernel(X, ls):
+    d2 = ((X[:, None, :] - X[None, :, :]) / ls) ** 2
+    return np.exp(-0.5 * d2.sum(-1))
+
+
+def make_model(rng, n, d, lo, hi, ls):
+    """Synthetic SVGP-like posterior: q_mu = L z, q_sqrt = 0.3 L, L = chol(K_SE + 1e-6 I)."""
+    Xtr = rng.uniform(lo, hi, size=(n, d))
+    L = np.linalg.cholesky(se_kernel(Xtr, ls) + 1e-6 * np.eye(n))
+    q_mu = L @ rng.standard_normal((n, 1))
+    q_sqrt = (0.3 * L)[None]
+    return Xtr, q_mu, q_sqrt
+
+
+def golden_fourier_features(ref):
+    """ff.py:7-21, 56-87 on explicit inputs; both branches of ff.py:80-82."""
+    rng = np.random.default_rng(101)
+    out = {}
+    for tag, (count, n, d, D) in {"under": (3, 7, 2, 48), "over": (2, 40, 3, 16)}.items():
+        X = rng.uniform(-1.5, 1.5, size=(count, n, d))
+        W = rng.standard_normal((count, D, d)) / 0.6
+        b = rng.uniform(0, 2 * np.pi, size=(count, D, 1))
+        phi = ref.fourier_features.fourier_features(tf_shim._t(X), tf_shim._t(W), tf_shim._t(b)).numpy()
+        Xtr, q_mu, q_sqrt = make_model(rng, n, d, -1.5, 1.5, 0.6)
+        tf_shim.seed(7)
+        z = tf_shim._rng.standard_normal((count, n))          # the draw ff.py:71 will make next
+        tf_shim.seed(7)
+        theta = ref.fourier_features.sample_theta_variational(
+            tf_shim._t(phi), tf_shim._t(q_mu), tf_shim._t(q_sqrt)).numpy()
+        out.update({f"{tag}_X": X, f"{tag}_W": W, f"{tag}_b": b, f"{tag}_phi": phi,
+                    f"{tag}_q_mu": q_mu, f"{tag}_q_sqrt": q_sqrt, f"{tag}_z": z, f"{tag}_theta": theta})
+    np.savez_compressed(os.path.join(OUT, "ff_features_theta.npz"), **out)
+
+
+def golden_sample_maximizers(ref):
+    """ff.py:110-169 end to end with num_steps=0 (no autodiff in the shim): basis + theta sampling
+    through sample_features_weights, x_star init, final eval / argmax / gather.  c1-like sizes
+    (MPES_Forr.py:70-79: count=20, n_init=50, D=1000, d=1) and a 2-D case."""
+    out = {}
+    ffm = ref.fourier_features
+    for tag, (count, n_init, D, n, d, lo, hi, ls) in {
+            "forr": (20, 50, 1000, 12, 1, 0.0, 1.0, 0.2),
+            "shc": (8, 64, 256, 20, 2, -1.5, 1.5, 0.6)}.items():
+        rng = np.random.default_rng(202 + d)
+        Xtr, q_mu, q_sqrt = make_model(rng, n, d, lo, hi, ls)
+        model = tf_shim.StubModel(kernel=tf_shim.RBFKernel(np.full(d, ls)), q_mu=q_mu, q_sqrt=q_sqrt)
+        captured = {}
+        orig = ffm.sample_features_weights
+
+        def spy(X, model, D, _orig=orig, _cap=captured):
+            r = _orig(X, model, D)
+            _cap["phi"], _cap["W"], _cap["b"], _cap["theta"] = [np.asarray(a) for a in r]
+            return r
+
+        ffm.sample_features_weights = spy
+        tf_shim.seed(31 + d)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                maxi = ffm.sample_maximizers(X=tf_shim._t(Xtr), count=count, n_init=n_init, D=D, model=model,
+                                             min_val=lo, max_val=hi, num_steps=0).numpy()
+        finally:
+            ffm.sample_features_weights = orig
+        x_star = np.asarray(tf_shim.created_variables()[-1])
+        out.update({f"{tag}_Xtr": Xtr, f"{tag}_q_mu": q_mu, f"{tag}_q_sqrt": q_sqrt,
+                    f"{tag}_W": captured["W"], f"{tag}_b": captured["b"], f"{tag}_theta": captured["theta"],
+                    f"{tag}_x_star": x_star, f"{tag}_maximizers": maxi})
+    np.savez_compressed(os.path.join(OUT, "ff_sample_maximizers.npz"), **out)
+
+
+def golden_rank_pes(ref):
+    """rank_pes.I_batch as shipped (rank_pes.py:10-108) on fixed fp32-representable samples."""
+    out = {}
+    for tag, (S, Q, C, k, M) in {"c5k3": (512, 24, 5, 3, 20), "c4k4": (256, 10, 4, 4, 6),
+                                 "c3k1": (300, 12, 3, 1, 5), "c5k2_sparse": (200, 8, 5, 2, 40)}.items():
+        rng = np.random.default_rng({"c5k3": 1, "c4k4": 2, "c3k1": 3, "c5k2_sparse": 4}[tag])
+        d = 6
+        chi = rng.uniform(0, 1, size=(Q, C, d))
+        x_star = rng.uniform(0, 1, size=(M, d))
+        # correlated samples so that MI is non-trivial: low-rank function draws + noise
+        basis = rng.standard_normal((Q * C + M, 6))
+        fs = (rng.standard_normal((S, 6)) @ basis.T + 0.3 * rng.standard_normal((S, Q * C + M)))
+        # rank_pes.py:40 calls np.bincount without minlength, so the reference raises IndexError at
+        # rank_pes.py:75 whenever the LAST maximiser wins no sample; keep the fixtures inside the
+        # domain where the reference runs by letting x*_{M-1} win sample 0 (empty groups stay interior).
+        fs[0, Q * C + M - 1] = fs[0, Q * C:].max() + 1.0
+        fs = fs.astype(np.float32).astype(np.float64)          # exactly what the fp32 GPU kernel consumes
+        model = tf_shim.StubModel(fixed_samples=fs)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mi = ref.rank_pes.I_batch(chi, x_star, model, topk=k, num_samples=S)
+        out.update({f"{tag}_fsample_all": fs.astype(np.float32), f"{tag}_mi": mi,
+                    f"{tag}_meta": np.array([S, Q, C, k, M])})
+    out["perms_5_3"] = ref.rank_pes.get_all_permutation_k_in_n(5, 3)
+    out["nperm_5_3"] = ref.rank_pes.precompute_n_permutations(5, 3)
+    out["perms_4_2"] = ref.rank_pes.get_all_permutation_k_in_n(4, 2)
+    np.savez_compressed(os.path.join(OUT, "rank_pes.npz"), **out)
+
+
+def golden_pes(ref):
+    """pes.I / pes.I_batch (pes.py:92-132) with one fixed sample matrix per query. c1 sizes:
+    S=1000, M=20, C=2 (MPES_Forr.py:70-79) plus a C=3 case."""
+    out = {}
+    for tag, (S, M, C, Qn) in {"c1": (1000, 20, 2, 6), "c3": (400, 7, 3, 4)}.items():
+        rng = np.random.default_rng({"c1": 11, "c3": 12}[tag])
+        basis = rng.standard_normal((Qn, M + C, 5))
+        per_query = (rng.standard_normal((Qn, S, 5)) @ np.swapaxes(basis, 1, 2)
+                     + 0.2 * rng.standard_normal((Qn, S, M + C)))
+        per_query = per_query.astype(np.float32).astype(np.float64)
+        model = tf_shim.StubModel(fixed_samples=lambda x, n, call, pq=per_query: pq[call])
+        chi_batch = rng.uniform(0, 1, size=(Qn, C, 1))
+        x_star = rng.uniform(0, 1, size=(M, 1))
+        if S != 1000:
+            vals = np.array([float(ref.pes.I(tf_shim._t(c), tf_shim._t(x_star), model, num_samples=S))
+                             for c in chi_batch])
+        else:
+            vals = ref.pes.I_batch(tf_shim._t(chi_batch), tf_shim._t(x_star), model)
+        out.update({f"{tag}_samples": per_query.astype(np.float32), f"{tag}_I": np.asarray(vals, dtype=np.float64),
+                    f"{tag}_meta": np.array([S, M, C, Qn])})
+    np.savez_compressed(os.path.join(OUT, "pes.npz"), **out)
+
+
+def golden_dts(ref):
+    """dts.sample_f (dts.py:71-85) with a Product kernel, and soft_copeland_maximizer (dts.py:88-97)."""
+    import gpflow
+    rng = np.random.default_rng(77)
+    d_obj, n_disc, D, n = 2, 12, 64, 9
+    grid = ref.dts.uniform_grid(d_obj, n_disc, 0, 1)                      # (144, 2)
+    combs = ref.dts.combinations(grid)                                    # (144^2, 4)
+    ls = np.array([0.25, 0.4])
+    kernel = gpflow.kernels.Product([tf_shim.RBFKernel(ls[0]), tf_shim.RBFKernel(ls[1])])
+    kernel.__class__ = gpflow.kernels.base.Product
+    Xq, q_mu, q_sqrt = make_model(rng, n, 2 * d_obj, 0, 1, 0.4)
+    model = tf_shim.StubModel(kernel=kernel, q_mu=q_mu, q_sqrt=q_sqrt)
+    ffm = ref.fourier_features
+    captured = {}
+    orig = ffm.sample_fourier_features
+
+    def spy(X, kernel, D=100):
+        r = orig(X, kernel, D)
+        captured["W"], captured["b"] = np.asarray(r[1]), np.asarray(r[2])
+        return r
+
+    ffm.sample_fourier_features = spy
+    tf_shim.seed(5)
+    try:
+        f_vals = np.asarray(ref.dts.sample_f(model, Xq, combs, D))
+    finally:
+        ffm.sample_fourier_features = orig
+    # the z drawn inside sample_theta_variational: replay the stream (W: D*2d normals, b: D uniforms, then z)
+    tf_shim.seed(5)
+    tf_shim._rng.standard_normal((1, D, 2 * d_obj))
+    tf_shim._rng.uniform(0, 1, size=(1, D, 1))
+    z = tf_shim._rng.standard_normal((1, n))
+    winner = ref.dts.soft_copeland_maximizer(tf_shim._t(f_vals), grid)
+    np.savez_compressed(os.path.join(OUT, "dts.npz"), grid=grid, combs=combs, lengthscales=ls, Xq=Xq,
+                        q_mu=q_mu, q_sqrt=q_sqrt, W=captured["W"], b=captured["b"], z=z,
+                        f_vals=f_vals, winner=np.asarray(winner))
+
+
+def main():
+    ref = ref_loader.load()
+    golden_fourier_features(ref)
+    golden_sample_maximizers(ref)
+    golden_rank_pes(ref)
+    golden_pes(ref)
+    golden_dts(ref)
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()
