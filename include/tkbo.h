@@ -1,0 +1,134 @@
+/*
+ * tkbo.h — C ABI of libtkbo.so: B200 (sm_100a) kernels for the one data-parallel hot path of
+ * sebtsh/Top-k-Ranking-Bayesian-Optimization: random-Fourier-feature (RFF) posterior sampling with a
+ * fused per-sample argmax, and the MPES Monte-Carlo ranking-likelihood entropy estimate.
+ *
+ * The reference is pure Python and has no FFI of its own; its boundary is the Python call signatures
+ * in fourier_features.py and acquisitions/{pes,rank_pes,dts}.py.  Each entry point below names the
+ * reference lines whose arithmetic it replaces; INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - plain C symbols, no C++/torch types; every function returns 0 on success or a negative
+ *     tkbo_status code, never throws; tkbo_last_error() returns a thread-local message.
+ *   - unless a function name ends in _host, every data pointer is a DEVICE pointer owned by the caller
+ *     (row-major, densely packed unless a leading dimension is given); calls are asynchronous on
+ *     `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *   - one handle per device; a handle is not thread-safe (the reference is single-threaded).
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU tkbo_create fails.
+ */
+#ifndef TKBO_H_
+#define TKBO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TKBO_VERSION 100  /* 0.1.0 */
+
+typedef enum {
+  TKBO_OK = 0,
+  TKBO_ERR_INVALID = -1,      /* bad argument (shape, null pointer, unsupported size) */
+  TKBO_ERR_CUDA = -2,         /* CUDA runtime / driver error, message in tkbo_last_error() */
+  TKBO_ERR_UNSUPPORTED = -3,  /* device is not sm_100, or configuration outside the kernel's limits */
+  TKBO_ERR_NOMEM = -4
+} tkbo_status;
+
+typedef struct tkbo_handle_s* tkbo_handle_t;
+typedef struct tkbo_basis_s* tkbo_basis_t;
+
+/* ---- lifecycle ----------------------------------------------------------------------------------- */
+int tkbo_version(void);
+const char* tkbo_last_error(void);
+/* Binds to CUDA device `device`; fails with TKBO_ERR_UNSUPPORTED unless it is compute capability 10.x. */
+int tkbo_create(tkbo_handle_t* out, int device);
+int tkbo_destroy(tkbo_handle_t h);
+/* Number of SMs the persistent kernels are sized for (148 on B200). */
+int tkbo_sm_count(tkbo_handle_t h);
+
+/* ---- shared-basis RFF sampler (kernel K1) ---------------------------------------------------------
+ * One basis (W, b) shared by S posterior weight samples Theta (D, S):
+ *     F[n, s] = sqrt(2/D) * sum_j cos(X[n,:].W[j,:] + b[j]) * Theta[j, s]
+ * which is fourier_features(X, W, b) @ theta  (fourier_features.py:18-21 and :162; acquisitions/dts.py:82-85)
+ * evaluated for all S samples at once.  The basis object holds the device-side operand layout
+ * (fp32 W|b slabs, Theta split into fp16 hi/lo K-major tiles with a per-sample power-of-two scale). */
+int tkbo_rff_basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S);
+int tkbo_rff_basis_destroy(tkbo_handle_t h, tkbo_basis_t basis);
+/* W [D, d], b [D], Theta [D, S] (theta_is_transposed = 0) or [S, D] (= 1); all float64 device arrays. */
+int tkbo_rff_basis_set(tkbo_handle_t h, tkbo_basis_t basis, const double* W, const double* b,
+                       const double* Theta, int theta_is_transposed, void* stream);
+
+/* out_val[s] = max_n F[n, s], out_idx[s] = idx_offset + (lowest n attaining it)  — the argmax + gather
+ * of fourier_features.py:162-167 with n_init -> N, without ever writing F.  X [N, d] float32.
+ * N < 2^32.  idx_offset lets a caller shard the candidate axis across GPUs. */
+int tkbo_rff_argmax(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, int64_t idx_offset,
+                    float* out_val, int64_t* out_idx, void* stream);
+/* out_F[s * ldf + n] = F[n, s] (sample-major, ldf >= N): the (N, count) matrix of
+ * acquisitions/dts.py:85 / the f-samples consumed by tkbo_mpes_topk. */
+int tkbo_rff_eval(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, float* out_F,
+                  int64_t ldf, void* stream);
+/* Per-rank partial results [G, S] (e.g. after an all-gather) -> global (value, lowest index). */
+int tkbo_merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, int G, int S,
+                      float* out_val, int64_t* out_idx, void* stream);
+
+/* Host-buffer convenience wrapper around basis_set + argmax (copies inside, synchronous):
+ * the end-to-end call a non-torch caller would make. All arrays are HOST pointers. */
+int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, const double* Theta,
+                         int D, int d, int S, const float* X, int64_t N, float* out_val, int64_t* out_idx);
+
+/* ---- per-sample-basis RFF (reference-exact shapes, float64 end to end) ----------------------------
+ * X [count, n, d], W [count, D, d], b [count, D], theta [count, D]:
+ *     out_f[c, i] = sqrt(2/D) * sum_j cos(X[c,i,:].W[c,j,:] + b[c,j]) * theta[c, j]     (fourier_features.py:162)
+ *     out_idx[c]  = argmax_i out_f[c, i], lowest index on ties                          (fourier_features.py:164-165)
+ * out_f may be NULL. */
+int tkbo_rff_eval_batched(tkbo_handle_t h, const double* X, const double* W, const double* b,
+                          const double* theta, int count, int n, int D, int d, double* out_f,
+                          int64_t* out_idx, void* stream);
+/* out_phi[c, i, j] = sqrt(2/D) cos(X[c,i,:].W[c,j,:] + b[c,j]) — the materialised feature map of
+ * fourier_features.py:7-21 (used on the n training / inducing inputs, never on the candidate grid). */
+int tkbo_rff_features_batched(tkbo_handle_t h, const double* X, const double* W, const double* b, int count,
+                              int n, int D, int d, double* out_phi, void* stream);
+/* fourier_features.py:133-157: sign-gradient ascent (Keras RMSprop rho=0: x <- clip(x - lr g/(|g|+eps)))
+ * on loss = -mean_{c,i} f_c(x[c,i]); stops when |dloss/loss| < rel_tol or after num_steps.
+ * X is updated in place; *steps_run (host int, may be NULL) receives the step count. Synchronous. */
+int tkbo_rff_ascent_batched(tkbo_handle_t h, double* X, const double* W, const double* b, const double* theta,
+                            int count, int n, int D, int d, double min_val, double max_val, int num_steps,
+                            double lr, double eps, double rel_tol, int* steps_run, void* stream);
+
+/* ---- MPES Monte-Carlo entropy estimate (kernel K2) -------------------------------------------------
+ * fchi [S, Q, C] float32 f-samples at the query points, fstar_argmax [S] int32 in [0, M): index of the
+ * maximiser that wins sample s (acquisitions/rank_pes.py:39), perms [P, k] int32 rows in ascending
+ * preference (rank_pes.py:139).  out_mi [Q] float64.
+ *   mode TKBO_MPES_RANK: acquisitions/rank_pes.py:58-105 (empty maximiser groups dropped).
+ *   mode TKBO_MPES_PES : acquisitions/pes.py:66-123 (k must be 1, perms NULL; eps = 1e-7 added to the
+ *                        group counts and likelihood sums, all M groups kept).
+ * perms == NULL means "all k-permutations of C" (P ignored; rank_pes.py:55): register-resident fast path
+ * for the common (C, k); an explicit table (P <= 1024 rows, e.g. the random 1000-row subset of
+ * rank_pes.py:49-53) takes the table-driven kernel.  C <= 8, Q < 2^31. */
+#define TKBO_MPES_RANK 0
+#define TKBO_MPES_PES 1
+int tkbo_mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, int S, int64_t Q,
+                   int C, int M, const int32_t* perms, int P, int k, int mode, double* out_mi,
+                   void* stream);
+/* out[s] = argmax_m fstar[s, m] (lowest index), fstar [S, M] float32 — rank_pes.py:39 / pes.py:108. */
+int tkbo_argmax_rows(tkbo_handle_t h, const float* fstar, int S, int M, int32_t* out, void* stream);
+
+/* ---- DTS tail --------------------------------------------------------------------------------------
+ * f [n*n] float32, i-major duels (acquisitions/dts.py:31-45): score[i] = mean_j sigmoid(f[i*n+j]),
+ * *out_argmax = argmax_i score[i]   (acquisitions/dts.py:94-97).  out_score may be NULL. */
+int tkbo_soft_copeland(tkbo_handle_t h, const float* f, int n, float* out_score, int64_t* out_argmax,
+                       void* stream);
+
+/* ---- introspection used by bench.py / tests --------------------------------------------------------
+ * Number of kernel launches issued through this handle since creation. */
+int64_t tkbo_launch_count(tkbo_handle_t h);
+/* Describes the tiling chosen for a basis: fills cfg[0..7] = {S_chunk, n_chunks, n_slabs, stages,
+ * accumulator buffers, d_template, smem_bytes, grid}. */
+int tkbo_rff_basis_config(tkbo_handle_t h, tkbo_basis_t basis, int64_t N, int32_t* cfg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TKBO_H_ */

@@ -1,0 +1,64 @@
+// Host-side state shared by the translation units of libtkbo.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/tkbo.h"
+
+namespace tkbo {
+
+void set_error(const std::string& msg);
+
+#define TKBO_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::tkbo::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+      return TKBO_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+#define TKBO_REQUIRE(cond, msg)                                                                    \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      ::tkbo::set_error(std::string("invalid argument: ") + (msg));                                \
+      return TKBO_ERR_INVALID;                                                                     \
+    }                                                                                              \
+  } while (0)
+
+}  // namespace tkbo
+
+struct tkbo_handle_s {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  int64_t launches = 0;
+  unsigned int* done_counter = nullptr;   // device, zero between calls
+  void* encode_tiled = nullptr;           // cuTensorMapEncodeTiled entry point
+  // scratch for the MPES kernel (grown on demand)
+  void* mpes_scratch = nullptr;
+  size_t mpes_scratch_bytes = 0;
+};
+
+struct tkbo_basis_s {
+  int D = 0, d = 0, S = 0;
+  int DT = 0;        // template input dimension (d padded up to a supported value)
+  int WS = 0;        // floats per feature row in Wpack
+  int Dpad = 0;      // multiple of 64
+  int SC = 0;        // samples per chunk
+  int n_chunks = 0;
+  int Salloc = 0;    // n_chunks * SC
+  int stages = 0;
+  int acc_bufs = 0;
+  int smem_bytes = 0;
+  float* Wpack = nullptr;            // [Dpad, WS]
+  __half* theta_hi = nullptr;        // [Salloc, Dpad]
+  __half* theta_lo = nullptr;        // [Salloc, Dpad]
+  float* unscale = nullptr;          // [Salloc]
+  unsigned long long* packed = nullptr;  // [Salloc]
+  CUtensorMap tm_hi, tm_lo;
+  bool is_set = false;
+};

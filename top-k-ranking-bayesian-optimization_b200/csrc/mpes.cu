@@ -1,0 +1,420 @@
+// K2 — MPES Monte-Carlo ranking-likelihood mutual information, given the f-samples.
+// Replaces acquisitions/rank_pes.py:38-105 (top-k ranking, Plackett-Luce likelihood over all
+// k-permutations) and acquisitions/pes.py:66-123 (top-1 with eps-smoothed counts), plus the
+// soft-Copeland tail of acquisitions/dts.py:94-97.
+//
+// Streaming form: samples are grouped by the maximiser that wins them (fstar_argmax).  For sample s and
+// query q, with e_c = exp(f_c - max_c f_c), the probability of the partial ranking o (ascending
+// preference, rank_pes.py:139) is   prod_{i=k-1..0} e[o_i] / (sum of e over the not-yet-ranked choices);
+// this equals exp of the log-likelihood built at rank_pes.py:160-166.  Per query we accumulate
+// J(z, m) = (1/S) sum_{s in group m} P_s(z) in fp32 registers, and at each group boundary fold
+//     MI += J log J - J log p(m)      and      tot(z) += J(z, m)                     (fp64 logs),
+// finishing with  MI -= sum_z tot(z) log tot(z), which is rank_pes.py:97-105 term by term.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include <vector>
+
+#include "common.h"
+
+namespace tkbo {
+
+constexpr double kPesEps = 1e-7;   // tf.keras.backend.epsilon(), pes.py:68,87
+
+// ------------------------------------------------------------------------------------------------
+// stable counting sort of the sample indices by winning maximiser
+// ------------------------------------------------------------------------------------------------
+// order[group_start[m] .. group_start[m+1]) = samples with fstar_argmax == m, ascending.
+__global__ void group_samples_kernel(const int* __restrict__ arg, int S, int M, int* __restrict__ order,
+                                     int* __restrict__ group_start) {
+  extern __shared__ int cnt[];           // [M + 1]
+  for (int m = threadIdx.x; m <= M; m += blockDim.x) cnt[m] = 0;
+  __syncthreads();
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const int m = arg[s];
+    if (m >= 0 && m < M) atomicAdd(&cnt[m + 1], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int m = 0; m < M; ++m) cnt[m + 1] += cnt[m];
+  __syncthreads();
+  for (int m = threadIdx.x; m <= M; m += blockDim.x) group_start[m] = cnt[m];
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    int w = cnt[m];
+    for (int s = 0; s < S; ++s)
+      if (arg[s] == m) order[w++] = s;
+  }
+}
+
+__global__ void argmax_rows_f32_kernel(const float* __restrict__ f, int S, int M, int* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float bv = f[static_cast<size_t>(s) * M];
+  int bi = 0;
+  for (int m = 1; m < M; ++m) {
+    const float v = f[static_cast<size_t>(s) * M + m];
+    if (v > bv) { bv = v; bi = m; }
+  }
+  out[s] = bi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compile-time enumeration of all K-permutations of C choices
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int perm_count(int C, int K) {
+  int p = 1;
+  for (int i = 0; i < K; ++i) p *= (C - i);
+  return p;
+}
+
+// sum of e over the choices not in `used` (fixed ascending order => identical masks share one expression)
+template <int C>
+__device__ __forceinline__ float remaining_sum(const float (&e)[C], unsigned used) {
+  float s = 0.f;
+  bool first = true;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    if ((used >> c) & 1u) continue;
+    s = first ? e[c] : s + e[c];
+    first = false;
+  }
+  return s;
+}
+
+template <int C, int K, int DEPTH>
+struct PermWalk {
+  // prob = probability of the choices ranked so far (best first); used = their bit mask.
+  template <int P>
+  static __device__ __forceinline__ void run(const float (&e)[C], unsigned used, float prob, float (&acc)[P], int& leaf) {
+    constexpr int remaining = C - DEPTH;
+    float pr = prob;
+    if (remaining > 1) pr = prob * __fdividef(1.f, remaining_sum<C>(e, used));   // else factor e/e = 1
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if ((used >> c) & 1u) continue;
+      if constexpr (DEPTH + 1 == K) {
+        acc[leaf] = (remaining > 1) ? fmaf(pr, e[c], acc[leaf]) : acc[leaf] + pr;
+        ++leaf;
+      } else {
+        const float child = (remaining > 1) ? pr * e[c] : pr;
+        PermWalk<C, K, DEPTH + 1>::run(e, used | (1u << c), child, acc, leaf);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// fast kernel: one thread per query, all K-permutations of C in registers; one warp per block
+// ------------------------------------------------------------------------------------------------
+template <int C, int K>
+__global__ void __launch_bounds__(32)
+mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ order, const int* __restrict__ group_start,
+                      int S, long long Q, int M, int mode, int tiles, double* __restrict__ out_mi) {
+  constexpr int P = perm_count(C, K);
+  __shared__ float tot[P][32];
+  const int lane = threadIdx.x;
+  const double invS = 1.0 / static_cast<double>(S);
+  const double eps = (mode == TKBO_MPES_PES) ? kPesEps : 0.0;
+  const long long rowstride = Q * C;
+
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long q = static_cast<long long>(tile) * 32 + lane;
+    const bool valid = q < Q;
+    const float* base = fchi + (valid ? q : Q - 1) * C;
+#pragma unroll
+    for (int z = 0; z < P; ++z) tot[z][lane] = 0.f;
+    float acc[P];
+#pragma unroll
+    for (int z = 0; z < P; ++z) acc[z] = 0.f;
+    double mi = 0.0;
+
+    for (int m = 0; m < M; ++m) {
+      const int lo = group_start[m], hi = group_start[m + 1];
+      if (hi == lo && mode == TKBO_MPES_RANK) continue;      // rank_pes.py:86-93 drops empty groups
+      // software prefetch: keep the next sample row in registers while working on the current one
+      float fnext[C];
+      if (lo < hi) {
+        const float* r = base + static_cast<long long>(order[lo]) * rowstride;
+#pragma unroll
+        for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
+      }
+      for (int i = lo; i < hi; ++i) {
+        float f[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) f[c] = fnext[c];
+        if (i + 1 < hi) {
+          const float* r = base + static_cast<long long>(order[i + 1]) * rowstride;
+#pragma unroll
+          for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
+        }
+        float mx = f[0];
+#pragma unroll
+        for (int c = 1; c < C; ++c) mx = fmaxf(mx, f[c]);
+        float e[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) e[c] = __expf(f[c] - mx);
+        int leaf = 0;
+        PermWalk<C, K, 0>::run(e, 0u, 1.f, acc, leaf);
+      }
+      // fold group m
+      const double pm = (mode == TKBO_MPES_PES)
+                            ? (static_cast<double>(hi - lo) + kPesEps) / (static_cast<double>(S) + M * kPesEps)
+                            : static_cast<double>(hi - lo) * invS;
+      const double log_pm = log(pm);
+#pragma unroll
+      for (int z = 0; z < P; ++z) {
+        const double J = (static_cast<double>(acc[z]) + eps) * invS;
+        if (J > 0.0) mi += J * (log(J) - log_pm);
+        tot[z][lane] += acc[z];
+        acc[z] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int z = 0; z < P; ++z) {
+      const double pz = (static_cast<double>(tot[z][lane]) + M * eps) * invS;
+      if (pz > 0.0) mi -= pz * log(pz);
+    }
+    if (valid) out_mi[q] = mi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel: explicit permutation table (any C <= 8, k <= C, P <= 1024); one warp per query,
+// lanes stride over table rows, <= 32 rows per lane in registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGenMaxC = 8;
+constexpr int kGenMaxP = 1024;
+
+__global__ void __launch_bounds__(128)
+mpes_table_kernel(const float* __restrict__ fchi, const int* __restrict__ order, const int* __restrict__ group_start,
+                  int S, long long Q, int C, int M, const int* __restrict__ perms, int P, int k, int mode,
+                  double* __restrict__ out_mi) {
+  extern __shared__ unsigned char sperm[];          // [P][8] choice indices, ascending preference
+  for (int i = threadIdx.x; i < P * kGenMaxC; i += blockDim.x) {
+    const int p = i / kGenMaxC, j = i % kGenMaxC;
+    sperm[i] = (j < k) ? static_cast<unsigned char>(perms[p * k + j]) : 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (q >= Q) return;
+  const double invS = 1.0 / static_cast<double>(S);
+  const double eps = (mode == TKBO_MPES_PES) ? kPesEps : 0.0;
+  const float* base = fchi + q * C;
+  const long long rowstride = Q * C;
+  float acc[32], tot[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { acc[i] = 0.f; tot[i] = 0.f; }
+  double mi = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const int lo = group_start[m], hi = group_start[m + 1];
+    if (hi == lo && mode == TKBO_MPES_RANK) continue;
+    for (int i = lo; i < hi; ++i) {
+      const float* r = base + static_cast<long long>(order[i]) * rowstride;
+      const float fmine = (lane < C) ? __ldg(r + lane) : -INFINITY;
+      float mx = fmine;
+      for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));   // C <= 8
+      mx = __shfl_sync(0xffffffffu, mx, 0);
+      const float emine = (lane < C) ? __expf(fmine - mx) : 0.f;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const int p = lane + 32 * t;
+        const bool act = p < P;
+        const unsigned char* row = sperm + (act ? p : 0) * kGenMaxC;
+        unsigned used = 0u;
+        float prob = 1.f;
+        if (t * 32 < P) {                              // warp-uniform
+          for (int j = k - 1; j >= 0; --j) {
+            const int c = row[j];
+            float rem = 0.f;
+            for (int cc = 0; cc < C; ++cc) {
+              const float ev = __shfl_sync(0xffffffffu, emine, cc);
+              if (!((used >> cc) & 1u)) rem += ev;
+            }
+            const float ec = __shfl_sync(0xffffffffu, emine, c);
+            prob *= ec / rem;
+            used |= 1u << c;
+          }
+          if (act) acc[t] += prob;
+        }
+      }
+    }
+    const double pm = (mode == TKBO_MPES_PES)
+                          ? (static_cast<double>(hi - lo) + kPesEps) / (static_cast<double>(S) + M * kPesEps)
+                          : static_cast<double>(hi - lo) * invS;
+    const double log_pm = log(pm);
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      if (lane + 32 * t < P) {
+        const double J = (static_cast<double>(acc[t]) + eps) * invS;
+        if (J > 0.0) mi += J * (log(J) - log_pm);
+        tot[t] += acc[t];
+      }
+      acc[t] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    if (lane + 32 * t < P) {
+      const double pz = (static_cast<double>(tot[t]) + M * eps) * invS;
+      if (pz > 0.0) mi -= pz * log(pz);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mi += __shfl_xor_sync(0xffffffffu, mi, o);
+  if (lane == 0) out_mi[q] = mi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DTS tail: soft-Copeland score and its argmax                               (acquisitions/dts.py:94-97)
+// ------------------------------------------------------------------------------------------------
+__global__ void soft_copeland_rows_kernel(const float* __restrict__ f, int n, float* __restrict__ score) {
+  const int i = blockIdx.x;
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) s += 1.0 / (1.0 + exp(-static_cast<double>(f[static_cast<size_t>(i) * n + j])));
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) score[i] = static_cast<float>(red[0] / n);
+}
+
+__global__ void argmax_vec_kernel(const float* __restrict__ v, int n, long long* __restrict__ out) {
+  __shared__ float bv[256];
+  __shared__ int bi[256];
+  float best = -INFINITY;
+  int idx = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = v[i];
+    if (x > best || (x == best && i < idx)) { best = x; idx = i; }
+  }
+  bv[threadIdx.x] = best; bi[threadIdx.x] = idx;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float x = bv[threadIdx.x + o];
+      const int j = bi[threadIdx.x + o];
+      if (x > bv[threadIdx.x] || (x == bv[threadIdx.x] && j < bi[threadIdx.x])) { bv[threadIdx.x] = x; bi[threadIdx.x] = j; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = bi[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+template <int C, int K>
+static void launch_all_perms(const float* fchi, const int* order, const int* gs, int S, int64_t Q, int M, int mode,
+                             int sm_count, double* out, cudaStream_t stream) {
+  const int64_t tiles = (Q + 31) / 32;
+  // equal number of tiles per resident warp: rounds = ceil(tiles / (SMs * 16)), grid = ceil(tiles / rounds)
+  const int64_t wmax = static_cast<int64_t>(sm_count) * 16;
+  const int64_t rounds = (tiles + wmax - 1) / wmax;
+  const int grid = static_cast<int>((tiles + rounds - 1) / rounds);
+  mpes_all_perms_kernel<C, K><<<grid, 32, 0, stream>>>(fchi, order, gs, S, Q, M, mode, static_cast<int>(tiles), out);
+}
+
+static bool dispatch_all_perms(int C, int K, const float* fchi, const int* order, const int* gs, int S, int64_t Q, int M,
+                               int mode, int sm, double* out, cudaStream_t st) {
+#define TKBO_CASE(c, k) \
+  if (C == c && K == k) { launch_all_perms<c, k>(fchi, order, gs, S, Q, M, mode, sm, out, st); return true; }
+  TKBO_CASE(2, 1) TKBO_CASE(2, 2)
+  TKBO_CASE(3, 1) TKBO_CASE(3, 2) TKBO_CASE(3, 3)
+  TKBO_CASE(4, 1) TKBO_CASE(4, 2) TKBO_CASE(4, 3) TKBO_CASE(4, 4)
+  TKBO_CASE(5, 1) TKBO_CASE(5, 2) TKBO_CASE(5, 3)
+  TKBO_CASE(6, 1) TKBO_CASE(6, 2)
+#undef TKBO_CASE
+  return false;
+}
+
+static void full_table(int C, int k, std::vector<int>* out) {
+  // lexicographic k-permutations, the order of rank_pes.get_all_permutation_k_in_n (rank_pes.py:218-228)
+  std::vector<int> cur;
+  std::vector<char> used(C, 0);
+  struct Rec {
+    static void go(int C, int k, std::vector<int>& cur, std::vector<char>& used, std::vector<int>* out) {
+      if (static_cast<int>(cur.size()) == k) { out->insert(out->end(), cur.begin(), cur.end()); return; }
+      for (int c = 0; c < C; ++c) {
+        if (used[c]) continue;
+        used[c] = 1; cur.push_back(c);
+        go(C, k, cur, used, out);
+        cur.pop_back(); used[c] = 0;
+      }
+    }
+  };
+  Rec::go(C, k, cur, used, out);
+}
+
+int mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, int S, int64_t Q, int C, int M,
+              const int32_t* perms, int P, int k, int mode, double* out_mi, cudaStream_t stream) {
+  TKBO_REQUIRE(h && fchi && fstar_argmax && out_mi, "null pointer");
+  TKBO_REQUIRE(S >= 1 && Q >= 1 && Q < (int64_t(1) << 31) && M >= 1, "S, Q, M must be >= 1 and Q < 2^31");
+  TKBO_REQUIRE(C >= 1 && C <= kGenMaxC && k >= 1 && k <= C, "need 1 <= k <= C <= 8");
+  TKBO_REQUIRE(mode == TKBO_MPES_RANK || mode == TKBO_MPES_PES, "unknown mode");
+  if (mode == TKBO_MPES_PES) TKBO_REQUIRE(k == 1 && perms == nullptr, "PES mode is top-1 with the implicit table");
+  const size_t need = sizeof(int) * (static_cast<size_t>(S) + M + 1) + sizeof(int) * kGenMaxP * kGenMaxC;
+  if (h->mpes_scratch_bytes < need) {
+    if (h->mpes_scratch) TKBO_CUDA_CHECK(cudaFree(h->mpes_scratch));
+    h->mpes_scratch = nullptr; h->mpes_scratch_bytes = 0;
+    TKBO_CUDA_CHECK(cudaMalloc(&h->mpes_scratch, need));
+    h->mpes_scratch_bytes = need;
+  }
+  int* order = static_cast<int*>(h->mpes_scratch);
+  int* gs = order + S;
+  int* dperm = gs + M + 1;
+  group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs);
+  h->launches += 1;
+  bool done = false;
+  if (perms == nullptr) done = dispatch_all_perms(C, k, fchi, order, gs, S, Q, M, mode, h->sm_count, out_mi, stream);
+  if (!done) {
+    const int32_t* table = perms;
+    int Pt = P;
+    if (perms == nullptr) {
+      std::vector<int> host;
+      full_table(C, k, &host);
+      Pt = static_cast<int>(host.size() / k);
+      if (Pt > kGenMaxP) {
+        set_error("all-permutation table has more than 1024 rows; pass an explicit (sub)table as rank_pes.py:49-53 does");
+        return TKBO_ERR_UNSUPPORTED;
+      }
+      TKBO_CUDA_CHECK(cudaMemcpyAsync(dperm, host.data(), sizeof(int) * host.size(), cudaMemcpyHostToDevice, stream));
+      TKBO_CUDA_CHECK(cudaStreamSynchronize(stream));     // host vector goes out of scope
+      table = dperm;
+    }
+    TKBO_REQUIRE(Pt >= 1 && Pt <= kGenMaxP, "explicit table must have 1..1024 rows");
+    const int64_t threads = Q * 32;
+    mpes_table_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, Pt * kGenMaxC, stream>>>(
+        fchi, order, gs, S, Q, C, M, table, Pt, k, mode, out_mi);
+  }
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
+int argmax_rows(tkbo_handle_t h, const float* fstar, int S, int M, int32_t* out, cudaStream_t stream) {
+  TKBO_REQUIRE(h && fstar && out && S >= 1 && M >= 1, "bad argmax_rows arguments");
+  argmax_rows_f32_kernel<<<(S + 127) / 128, 128, 0, stream>>>(fstar, S, M, out);
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
+int soft_copeland(tkbo_handle_t h, const float* f, int n, float* out_score, int64_t* out_argmax, cudaStream_t stream) {
+  TKBO_REQUIRE(h && f && n >= 1 && (out_score || out_argmax), "bad soft_copeland arguments");
+  float* score = out_score;
+  if (!score) TKBO_CUDA_CHECK(cudaMallocAsync(&score, sizeof(float) * n, stream));
+  soft_copeland_rows_kernel<<<n, 256, 0, stream>>>(f, n, score);
+  h->launches += 1;
+  if (out_argmax) {
+    argmax_vec_kernel<<<1, 256, 0, stream>>>(score, n, reinterpret_cast<long long*>(out_argmax));
+    h->launches += 1;
+  }
+  if (!out_score) TKBO_CUDA_CHECK(cudaFreeAsync(score, stream));
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
+}  // namespace tkbo

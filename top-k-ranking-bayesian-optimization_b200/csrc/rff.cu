@@ -1,0 +1,508 @@
+// Host side of the shared-basis RFF sampler (operand preparation, tiling choice, tensor maps, launch)
+// plus the small float64 kernels for the reference-exact per-sample-basis shapes.
+#include <cooperative_groups.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.h"
+#include "rff_fused.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tkbo {
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation (once per BO iteration; not the hot path)
+// ------------------------------------------------------------------------------------------------
+// Theta element (j, s) from either layout.
+__device__ __forceinline__ double theta_at(const double* T, int transposed, int D, int S, int j, int s) {
+  return transposed ? T[static_cast<size_t>(s) * D + j] : T[static_cast<size_t>(j) * S + s];
+}
+
+// unscale[s] = 2^-e_s with e_s chosen so that max_j |sqrt(2/D) Theta[j,s]| 2^e_s lies in [2^9, 2^10):
+// keeps the fp16 hi part far from overflow and the lo part (<= 2^-11 of hi) far above fp16's subnormal step.
+__global__ void prep_theta_scale_kernel(const double* __restrict__ Theta, int transposed, int D, int S, int Salloc,
+                                        float* __restrict__ unscale) {
+  const int s = blockIdx.x;
+  __shared__ double red[256];
+  double m = 0.0;
+  if (s < S)
+    for (int j = threadIdx.x; j < D; j += blockDim.x) m = fmax(m, fabs(theta_at(Theta, transposed, D, S, j, s)));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double amax = red[0] * sqrt(2.0 / D);
+    int e = 0;
+    if (amax > 0.0 && isfinite(amax)) e = 9 - ilogb(amax);
+    e = max(-100, min(100, e));
+    unscale[s] = static_cast<float>(ldexp(1.0, -e));
+  }
+}
+
+__global__ void prep_theta_split_kernel(const double* __restrict__ Theta, int transposed, int D, int S, int Dpad,
+                                        int Salloc, const float* __restrict__ unscale, __half* __restrict__ hi,
+                                        __half* __restrict__ lo) {
+  const size_t total = static_cast<size_t>(Salloc) * Dpad;
+  const double root = sqrt(2.0 / D);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(i / Dpad);
+    const int j = static_cast<int>(i % Dpad);
+    double v = 0.0;
+    if (s < S && j < D) v = theta_at(Theta, transposed, D, S, j, s) * root / static_cast<double>(unscale[s]);
+    const __half h = __double2half(v);
+    const __half l = __double2half(v - static_cast<double>(__half2float(h)));
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// Wpack[j] = (w_j[0..d-1], 0.., b_j at slot DT, 0..) as float32; padded features get w = 0, b = 0 (their
+// Theta rows are zero, so cos(0) = 1 contributes nothing).
+__global__ void prep_w_kernel(const double* __restrict__ W, const double* __restrict__ b, int D, int d, int Dpad,
+                              int DT, int WS, float* __restrict__ Wpack) {
+  const int total = Dpad * WS;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i / WS, c = i % WS;
+    float v = 0.f;
+    if (j < D) {
+      if (c < d) v = static_cast<float>(W[static_cast<size_t>(j) * d + c]);
+      else if (c == DT) v = static_cast<float>(b[j]);
+    }
+    Wpack[i] = v;
+  }
+}
+
+__global__ void merge_argmax_kernel(const float* __restrict__ vals, const long long* __restrict__ idx, int G, int S,
+                                    float* __restrict__ out_val, long long* __restrict__ out_idx) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float bv = vals[s];
+  long long bi = idx[s];
+  for (int g = 1; g < G; ++g) {
+    const float v = vals[static_cast<size_t>(g) * S + s];
+    const long long i = idx[static_cast<size_t>(g) * S + s];
+    if (i < 0) continue;
+    if (bi < 0 || v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+  out_val[s] = bv;
+  out_idx[s] = bi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-sample-basis float64 kernels (reference-exact shapes: count x n_init points, count bases)
+// ------------------------------------------------------------------------------------------------
+// One warp per point (c, i): f = sqrt(2/D) sum_j cos(x.w_cj + b_cj) theta_cj          [ff.py:20-21,162]
+__global__ void rff_eval_batched_kernel(const double* __restrict__ X, const double* __restrict__ W,
+                                        const double* __restrict__ b, const double* __restrict__ theta, int count,
+                                        int n, int D, int d, double* __restrict__ out_f) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= count * n) return;
+  const int c = gw / n;
+  const double* x = X + static_cast<size_t>(gw) * d;
+  const double* Wc = W + static_cast<size_t>(c) * D * d;
+  double acc = 0.0;
+  for (int j = lane; j < D; j += 32) {
+    double t = b[static_cast<size_t>(c) * D + j];
+    for (int k = 0; k < d; ++k) t += Wc[static_cast<size_t>(j) * d + k] * x[k];
+    acc += cos(t) * theta[static_cast<size_t>(c) * D + j];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out_f[gw] = acc * sqrt(2.0 / D);
+}
+
+// phi[c, i, j] = sqrt(2/D) cos(x_ci . w_cj + b_cj)                                       [ff.py:18-21]
+__global__ void rff_features_batched_kernel(const double* __restrict__ X, const double* __restrict__ W,
+                                            const double* __restrict__ b, int count, int n, int D, int d,
+                                            double* __restrict__ phi) {
+  const size_t total = static_cast<size_t>(count) * n * D;
+  const double root = sqrt(2.0 / D);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % D);
+    const size_t ci = i / D;                       // c * n + row
+    const int c = static_cast<int>(ci / n);
+    double t = b[static_cast<size_t>(c) * D + j];
+    for (int k = 0; k < d; ++k) t += W[(static_cast<size_t>(c) * D + j) * d + k] * X[ci * d + k];
+    phi[i] = root * cos(t);
+  }
+}
+
+// argmax over axis 1 of f [count, n], lowest index on ties                              [ff.py:164-165]
+__global__ void argmax_rows_f64_kernel(const double* __restrict__ f, int count, int n, long long* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= count) return;
+  double bv = f[static_cast<size_t>(c) * n];
+  int bi = 0;
+  for (int i = 1; i < n; ++i) {
+    const double v = f[static_cast<size_t>(c) * n + i];
+    if (v > bv) { bv = v; bi = i; }
+  }
+  out[c] = bi;
+}
+
+// Persistent cooperative kernel for ff.py:133-157.  One warp per start point; every step evaluates
+// f and df/dx at the current x, block-reduces the loss, grid-syncs, checks the early-stop rule on the
+// global mean loss and applies  x <- clip(x - lr g / (sqrt(g^2) + eps))  with g = dloss/dx.
+struct AscentState {
+  double* partial;     // [gridDim.x] per-block sum of f
+  int* steps;          // steps actually run
+};
+
+__global__ void rff_ascent_batched_kernel(double* __restrict__ X, const double* __restrict__ W,
+                                          const double* __restrict__ b, const double* __restrict__ theta, int count,
+                                          int n, int D, int d, double min_val, double max_val, int num_steps,
+                                          double lr, double eps, double rel_tol, AscentState st) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double sh[];                       // [warps_per_block] f partials
+  const int warps_per_block = blockDim.x >> 5;
+  const int wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = count * n;
+  const int warps_total = gridDim.x * warps_per_block;
+  const double root = sqrt(2.0 / D);
+  const double gcoef = root / static_cast<double>(total);
+  constexpr int kMaxD = 16;
+  double prev_loss = 0.0;
+  int steps_done = 0;
+  bool stop = false;
+
+  for (int step = 0; step <= num_steps && !stop; ++step) {
+    // pass `step`: evaluate loss at the current x (step 0 = prev_loss of ff.py:148) and the gradient
+    double fsum = 0.0;
+    for (int pt = blockIdx.x * warps_per_block + wib; pt < total; pt += warps_total) {
+      const int c = pt / n;
+      double* x = X + static_cast<size_t>(pt) * d;
+      const double* Wc = W + static_cast<size_t>(c) * D * d;
+      double f = 0.0;
+      double g[kMaxD];
+#pragma unroll
+      for (int k = 0; k < kMaxD; ++k) g[k] = 0.0;
+      for (int j = lane; j < D; j += 32) {
+        double t = b[static_cast<size_t>(c) * D + j];
+        for (int k = 0; k < d; ++k) t += Wc[static_cast<size_t>(j) * d + k] * x[k];
+        double sn, cs;
+        sincos(t, &sn, &cs);
+        const double th = theta[static_cast<size_t>(c) * D + j];
+        f += cs * th;
+        const double ts = th * sn;
+#pragma unroll
+        for (int k = 0; k < kMaxD; ++k)
+          if (k < d) g[k] += ts * Wc[static_cast<size_t>(j) * d + k];
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        f += __shfl_xor_sync(0xffffffffu, f, o);
+#pragma unroll
+        for (int k = 0; k < kMaxD; ++k)
+          if (k < d) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
+      }
+      fsum += f * root;
+      // stash the gradient of the loss in registers of lane k: applied after the stop test below
+      // (every lane holds all g[k]; lane k < d owns coordinate k)
+      __syncwarp();
+      if (lane < d) {
+        double gk = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxD; ++k)
+          if (k == lane) gk = g[k] * gcoef;
+        // tentative update is written to a shadow so that a stop at this step leaves x untouched
+        // (shadow lives behind X: X has room for 2 * total * d doubles)
+        const double xn = x[lane] - lr * gk / (sqrt(gk * gk) + eps);
+        X[static_cast<size_t>(total) * d + static_cast<size_t>(pt) * d + lane] = fmin(fmax(xn, min_val), max_val);
+      }
+    }
+    if (lane == 0) sh[wib] = fsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < warps_per_block; ++w) s += sh[w];
+      st.partial[blockIdx.x] = s;
+    }
+    grid.sync();
+    double tot = 0.0;
+    for (int bl = 0; bl < gridDim.x; ++bl) tot += st.partial[bl];
+    const double loss = -tot / static_cast<double>(total);
+    if (step > 0) {
+      steps_done = step;
+      if (fabs((loss - prev_loss) / prev_loss) < rel_tol) stop = true;      // ff.py:154
+    }
+    prev_loss = loss;
+    if (!stop && step < num_steps) {
+      // commit the update computed from this pass's gradient (ff.py:150)
+      for (int pt = blockIdx.x * warps_per_block + wib; pt < total; pt += warps_total)
+        if (lane < d) X[static_cast<size_t>(pt) * d + lane] = X[static_cast<size_t>(total) * d + static_cast<size_t>(pt) * d + lane];
+    }
+    grid.sync();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *st.steps = steps_done;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+static int pick_dt(int d) {
+  const int supported[] = {1, 2, 3, 4, 6, 8, 12, 16};
+  for (int v : supported)
+    if (d <= v) return v;
+  return -1;
+}
+
+static int wstride_of(int DT) { return (DT == 1) ? 2 : ((DT + 1 + 3) / 4) * 4; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_theta_map(tkbo_handle_t h, CUtensorMap* map, __half* base, int Salloc, int Dpad, int SC) {
+  auto fn = reinterpret_cast<EncodeTiledFn>(h->encode_tiled);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(Dpad), static_cast<cuuint64_t>(Salloc)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Dpad) * sizeof(__half)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kSlabK), static_cast<cuuint32_t>(SC)};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return TKBO_ERR_CUDA;
+  }
+  return TKBO_OK;
+}
+
+int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
+  TKBO_REQUIRE(h && out, "null handle/out");
+  TKBO_REQUIRE(D >= 1 && d >= 1 && S >= 1, "D, d, S must be >= 1");
+  const int DT = pick_dt(d);
+  if (DT < 0) {
+    set_error("input dimension d > 16 is not supported by the fused kernel");
+    return TKBO_ERR_UNSUPPORTED;
+  }
+  auto* bs = new tkbo_basis_s();
+  bs->D = D; bs->d = d; bs->S = S; bs->DT = DT; bs->WS = wstride_of(DT);
+  bs->Dpad = ((D + kSlabK - 1) / kSlabK) * kSlabK;
+  const int S32 = ((S + 31) / 32) * 32;
+  bs->n_chunks = (S32 + 255) / 256;
+  bs->SC = ((((S32 + bs->n_chunks - 1) / bs->n_chunks) + 31) / 32) * 32;
+  bs->Salloc = bs->n_chunks * bs->SC;
+  const int stride = stage_stride_bytes(bs->SC, bs->WS);
+  const int smem_limit = h->max_smem_optin - 2048;      // static barriers + 1024-byte alignment slack
+  bs->stages = 0;
+  for (int ab = 2; ab >= 1 && bs->stages == 0; --ab) {
+    int ns = std::min(kMaxStages, (kTmemCols - ab * bs->SC) / kSlabK);
+    ns = std::min(ns, smem_limit / stride);
+    if (ns >= (ab == 2 ? 3 : 2)) { bs->stages = ns; bs->acc_bufs = ab; }
+  }
+  if (bs->stages == 0) {
+    delete bs;
+    set_error("no feasible pipeline configuration for this (S, d)");
+    return TKBO_ERR_UNSUPPORTED;
+  }
+  bs->smem_bytes = bs->stages * stride + 1024;
+  cudaError_t e = cudaSuccess;
+  e = e ? e : cudaMalloc(&bs->Wpack, static_cast<size_t>(bs->Dpad) * bs->WS * sizeof(float));
+  e = e ? e : cudaMalloc(&bs->theta_hi, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
+  e = e ? e : cudaMalloc(&bs->theta_lo, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
+  e = e ? e : cudaMalloc(&bs->unscale, static_cast<size_t>(bs->Salloc) * sizeof(float));
+  e = e ? e : cudaMalloc(&bs->packed, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc (basis): ") + cudaGetErrorString(e));
+    cudaFree(bs->Wpack); cudaFree(bs->theta_hi); cudaFree(bs->theta_lo); cudaFree(bs->unscale); cudaFree(bs->packed);
+    delete bs;
+    return TKBO_ERR_NOMEM;
+  }
+  int rc = make_theta_map(h, &bs->tm_hi, bs->theta_hi, bs->Salloc, bs->Dpad, bs->SC);
+  if (rc == TKBO_OK) rc = make_theta_map(h, &bs->tm_lo, bs->theta_lo, bs->Salloc, bs->Dpad, bs->SC);
+  if (rc != TKBO_OK) {
+    cudaFree(bs->Wpack); cudaFree(bs->theta_hi); cudaFree(bs->theta_lo); cudaFree(bs->unscale); cudaFree(bs->packed);
+    delete bs;
+    return rc;
+  }
+  *out = bs;
+  return TKBO_OK;
+}
+
+int basis_destroy(tkbo_handle_t, tkbo_basis_t bs) {
+  if (!bs) return TKBO_OK;
+  cudaFree(bs->Wpack); cudaFree(bs->theta_hi); cudaFree(bs->theta_lo); cudaFree(bs->unscale); cudaFree(bs->packed);
+  delete bs;
+  return TKBO_OK;
+}
+
+int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b, const double* Theta,
+              int transposed, cudaStream_t stream) {
+  TKBO_REQUIRE(h && bs && W && b && Theta, "null pointer");
+  prep_theta_scale_kernel<<<bs->Salloc, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Salloc, bs->unscale);
+  const size_t total = static_cast<size_t>(bs->Salloc) * bs->Dpad;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  prep_theta_split_kernel<<<blocks, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Dpad, bs->Salloc,
+                                                     bs->unscale, bs->theta_hi, bs->theta_lo);
+  prep_w_kernel<<<(bs->Dpad * bs->WS + 255) / 256, 256, 0, stream>>>(W, b, bs->D, bs->d, bs->Dpad, bs->DT, bs->WS,
+                                                                    bs->Wpack);
+  h->launches += 3;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  bs->is_set = true;
+  return TKBO_OK;
+}
+
+template <int DT, int MODE>
+static int launch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  auto kern = rff_fused_kernel<DT, MODE>;
+  TKBO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs->smem_bytes));
+  kern<<<grid, kNumThreads, bs->smem_bytes, stream>>>(bs->tm_hi, bs->tm_lo, p);
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
+template <int MODE>
+static int dispatch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  switch (bs->DT) {
+    case 1: return launch_fused<1, MODE>(h, bs, p, grid, stream);
+    case 2: return launch_fused<2, MODE>(h, bs, p, grid, stream);
+    case 3: return launch_fused<3, MODE>(h, bs, p, grid, stream);
+    case 4: return launch_fused<4, MODE>(h, bs, p, grid, stream);
+    case 6: return launch_fused<6, MODE>(h, bs, p, grid, stream);
+    case 8: return launch_fused<8, MODE>(h, bs, p, grid, stream);
+    case 12: return launch_fused<12, MODE>(h, bs, p, grid, stream);
+    case 16: return launch_fused<16, MODE>(h, bs, p, grid, stream);
+  }
+  set_error("internal: unsupported DT");
+  return TKBO_ERR_UNSUPPORTED;
+}
+
+static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, RffParams* p, int* grid) {
+  TKBO_REQUIRE(h && bs && X, "null pointer");
+  TKBO_REQUIRE(bs->is_set, "basis has no data: call tkbo_rff_basis_set first");
+  TKBO_REQUIRE(N >= 1 && N < (int64_t(1) << 32) - 256, "N must be in [1, 2^32 - 256)");
+  p->X = X; p->Wpack = bs->Wpack; p->unscale = bs->unscale; p->packed = bs->packed;
+  p->done_counter = h->done_counter;
+  p->out_val = nullptr; p->out_idx = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
+  p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
+  p->n_slabs = bs->Dpad / kSlabK;
+  const int64_t mt = (N + kTileM - 1) / kTileM;
+  TKBO_REQUIRE(mt * bs->n_chunks < (int64_t(1) << 31), "too many work items");
+  p->n_mtiles = static_cast<int>(mt);
+  p->stages = bs->stages; p->acc_bufs = bs->acc_bufs;
+  *grid = static_cast<int>(std::min<int64_t>(h->sm_count, mt * bs->n_chunks));
+  return TKBO_OK;
+}
+
+int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, float* out_val,
+               int64_t* out_idx, cudaStream_t stream) {
+  RffParams p;
+  int grid = 0;
+  int rc = fill_params(h, bs, X, N, &p, &grid);
+  if (rc != TKBO_OK) return rc;
+  TKBO_REQUIRE(out_val && out_idx, "null output");
+  p.out_val = out_val;
+  p.out_idx = reinterpret_cast<long long*>(out_idx);
+  p.idx_offset = idx_offset;
+  TKBO_CUDA_CHECK(cudaMemsetAsync(bs->packed, 0, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long), stream));
+  return dispatch_fused<0>(h, bs, p, grid, stream);
+}
+
+int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float* out_F, int64_t ldf,
+             cudaStream_t stream) {
+  RffParams p;
+  int grid = 0;
+  int rc = fill_params(h, bs, X, N, &p, &grid);
+  if (rc != TKBO_OK) return rc;
+  TKBO_REQUIRE(out_F && ldf >= N, "out_F null or ldf < N");
+  p.out_F = out_F;
+  p.ldf = ldf;
+  return dispatch_fused<1>(h, bs, p, grid, stream);
+}
+
+int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg) {
+  TKBO_REQUIRE(h && bs && cfg, "null pointer");
+  const int64_t mt = (N + kTileM - 1) / kTileM;
+  cfg[0] = bs->SC; cfg[1] = bs->n_chunks; cfg[2] = bs->Dpad / kSlabK; cfg[3] = bs->stages; cfg[4] = bs->acc_bufs;
+  cfg[5] = bs->DT; cfg[6] = bs->smem_bytes;
+  cfg[7] = static_cast<int32_t>(std::min<int64_t>(h->sm_count, std::max<int64_t>(1, mt) * bs->n_chunks));
+  return TKBO_OK;
+}
+
+int merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, int G, int S, float* out_val,
+                 int64_t* out_idx, cudaStream_t stream) {
+  TKBO_REQUIRE(h && vals && idx && out_val && out_idx && G >= 1 && S >= 1, "bad merge arguments");
+  merge_argmax_kernel<<<(S + 127) / 128, 128, 0, stream>>>(vals, reinterpret_cast<const long long*>(idx), G, S, out_val,
+                                                          reinterpret_cast<long long*>(out_idx));
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
+int rff_eval_batched(tkbo_handle_t h, const double* X, const double* W, const double* b, const double* theta,
+                     int count, int n, int D, int d, double* out_f, int64_t* out_idx, cudaStream_t stream) {
+  TKBO_REQUIRE(h && X && W && b && theta, "null pointer");
+  TKBO_REQUIRE(count >= 1 && n >= 1 && D >= 1 && d >= 1, "count, n, D, d must be >= 1");
+  TKBO_REQUIRE(out_f || out_idx, "nothing to compute");
+  double* f = out_f;
+  if (!f) TKBO_CUDA_CHECK(cudaMallocAsync(&f, sizeof(double) * count * n, stream));
+  const long long threads = static_cast<long long>(count) * n * 32;
+  rff_eval_batched_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, stream>>>(X, W, b, theta, count, n, D, d, f);
+  h->launches += 1;
+  if (out_idx) {
+    argmax_rows_f64_kernel<<<(count + 63) / 64, 64, 0, stream>>>(f, count, n, reinterpret_cast<long long*>(out_idx));
+    h->launches += 1;
+  }
+  if (!out_f) TKBO_CUDA_CHECK(cudaFreeAsync(f, stream));
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
+int rff_features_batched(tkbo_handle_t h, const double* X, const double* W, const double* b, int count, int n, int D,
+                         int d, double* out_phi, cudaStream_t stream) {
+  TKBO_REQUIRE(h && X && W && b && out_phi, "null pointer");
+  TKBO_REQUIRE(count >= 1 && n >= 1 && D >= 1 && d >= 1, "count, n, D, d must be >= 1");
+  const size_t total = static_cast<size_t>(count) * n * D;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(h->sm_count) * 32));
+  rff_features_batched_kernel<<<blocks, 256, 0, stream>>>(X, W, b, count, n, D, d, out_phi);
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
+int rff_ascent_batched(tkbo_handle_t h, double* X, const double* W, const double* b, const double* theta, int count,
+                       int n, int D, int d, double min_val, double max_val, int num_steps, double lr, double eps,
+                       double rel_tol, int* steps_run, cudaStream_t stream) {
+  TKBO_REQUIRE(h && X && W && b && theta, "null pointer");
+  TKBO_REQUIRE(count >= 1 && n >= 1 && D >= 1 && d >= 1 && d <= 16, "count, n, D >= 1 and 1 <= d <= 16 required");
+  TKBO_REQUIRE(num_steps >= 0, "num_steps must be >= 0");
+  const int total = count * n;
+  const int block = 256, wpb = block / 32;
+  int per_sm = 0;
+  TKBO_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rff_ascent_batched_kernel, block,
+                                                                wpb * sizeof(double)));
+  TKBO_REQUIRE(per_sm >= 1, "ascent kernel does not fit on an SM");
+  int grid = std::min(h->sm_count * per_sm, (total + wpb - 1) / wpb);
+  grid = std::max(grid, 1);
+  // X + shadow copy for the tentative update
+  double* work = nullptr;
+  TKBO_CUDA_CHECK(cudaMallocAsync(&work, sizeof(double) * (2 * static_cast<size_t>(total) * d + grid) + sizeof(int), stream));
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(work, X, sizeof(double) * total * d, cudaMemcpyDeviceToDevice, stream));
+  AscentState st;
+  st.partial = work + 2 * static_cast<size_t>(total) * d;
+  st.steps = reinterpret_cast<int*>(st.partial + grid);
+  void* args[] = {&work, &W, &b, &theta, &count, &n, &D, &d, &min_val, &max_val, &num_steps, &lr, &eps, &rel_tol, &st};
+  TKBO_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rff_ascent_batched_kernel), dim3(grid), dim3(block),
+                                              args, wpb * sizeof(double), stream));
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(X, work, sizeof(double) * total * d, cudaMemcpyDeviceToDevice, stream));
+  int steps = 0;
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(&steps, st.steps, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  TKBO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  TKBO_CUDA_CHECK(cudaFreeAsync(work, stream));
+  if (steps_run) *steps_run = steps;
+  return TKBO_OK;
+}
+
+}  // namespace tkbo
