@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the RFF maximiser-sampling hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3s|c4s] [--no-mpes]
+
+A step = one fused RFF-sample + per-sample argmax pass over one batch of synthetic candidates (workload c2 by
+default: configs[1], N = 2^20 Six-Hump-Camel grid points, d = 2, D = 1024 features, S = 64 posterior samples),
+followed for N > 1 GPUs by the all-gather merge of the (value, index) pairs.  Multi-GPU runs shard the candidate
+axis: every rank owns its own 2^20-candidate shard (weak scaling), launched by torchrun, one rank per GPU, NCCL.
+
+Printed JSON (rank 0, one line): `value` = candidate*samples/s with inputs resident in HBM (CUDA events, max over
+ranks); `e2e` = the same through the public API with HOST buffers (pinned host -> device copy of the step's
+candidates and basis, kernel, device -> host read of the result, every step); `roofline` for the fused kernel
+(tensor pipe; algorithmic flops 2*N*D*S per launch, plus the executed figure: the fp32-emulating split issues 3
+fp16 MMAs per product); `cpu_baseline` = the CPU oracle port timed on this host on a bounded sample;
+`mpes` = the K2 kernel at c5 (10^5 query sets x 1024 MC samples, k = 3 of 5) with its HBM roofline.
+
+`--impl reference` times the CPU implementation of the same path (the fp64 NumPy oracle port of the reference's
+data-flow: TF 2.1 / GPflow 2.0.0-rc1 cannot be installed offline) on all host threads, same metric and config.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RFF posterior-sample candidate*samples/s (fused argmax)"
+UNIT = "candidate*samples/s"
+
+WORKLOADS = {
+    # name: (N per GPU, d, D, S, domain lo, hi, lengthscale, description)
+    "c2": (1 << 20, 2, 1024, 64, -1.5, 1.5, 0.6, "c2: Six-Hump-Camel 2-D grid 1024x1024, D=1024 RFF, S=64 samples"),
+    "c3s": (1 << 21, 6, 4096, 256, 0.0, 1.0, 0.2, "c3 shard: Hartmann-6, 2^21 of the 2^24 candidates, D=4096, S=256"),
+    "c4s": (1 << 19, 4, 2048, 4096, 0.0, 1.0, 0.2, "c4 shard: DTS duels, 2^19 of the 2^22 candidates, D=2048, S=4096"),
+}
+N_ROTATING = 32     # distinct candidate buffers cycled through so every step reads its candidates from HBM, not L2
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "MEASURED_PEAKS.json (measured)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "B200_PROFILING.md fallback"}
+
+
+def make_basis_arrays(D, d, S, ls, lo, hi, seed=0, n_train=41):
+    """W, b and Theta from the ff.py:56-87 regression on a synthetic fitted posterior; host float64."""
+    rng = np.random.default_rng(seed)
+    W = rng.standard_normal((D, d)) / ls
+    b = rng.uniform(0.0, 2.0 * np.pi, D)
+    Xtr = rng.uniform(lo, hi, size=(n_train, d))
+    K = np.exp(-0.5 * (((Xtr[:, None] - Xtr[None]) / ls) ** 2).sum(-1))
+    L = np.linalg.cholesky(K + 1e-6 * np.eye(n_train))
+    q_mu, q_sqrt = L @ rng.standard_normal((n_train, 1)), 0.3 * L
+    phi = np.sqrt(2.0 / D) * np.cos(Xtr @ W.T + b)                       # (n, D)
+    Q = q_sqrt @ rng.standard_normal((n_train, S)) + q_mu                # (n, S)
+    Theta = phi.T @ np.linalg.inv(phi @ phi.T) @ Q                       # n < D branch of ff.py:82
+    return W, b, Theta
+
+
+def candidates_host(N, d, lo, hi, variant):
+    """c2: the 1024x1024 uniform grid (i-major like dts.uniform_grid), jittered per variant so the rotating buffers
+    differ; other shapes: uniform random points."""
+    rng = np.random.default_rng(1000 + variant)
+    if d == 2 and N == 1 << 20:
+        g = np.linspace(lo, hi, 1024)
+        X = np.stack(np.meshgrid(g, g, indexing="xy"), axis=-1).reshape(-1, 2)
+        X = X + rng.uniform(-0.5, 0.5, size=(1, 2)) * (hi - lo) / 1023.0
+        return np.clip(X, lo, hi).astype(np.float32)
+    return rng.uniform(lo, hi, size=(N, d)).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.05] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_argmax_threads(X, W, b, Theta, threads):
+    """The oracle's chunked shared-basis evaluation + argmax (ff.py:20-21, 162-167 with n_init -> N), row ranges
+    spread over `threads` workers (NumPy releases the GIL in cos and matmul)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import rff_oracle
+    N = X.shape[0]
+    bounds = np.linspace(0, N, threads + 1).astype(int)
+
+    def work(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        if hi <= lo:
+            return None
+        v, ix, _ = rff_oracle.rff_argmax_shared(X[lo:hi], W, b, Theta, chunk=4096, idx_offset=lo)
+        return v, ix
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = [p for p in ex.map(work, range(threads)) if p is not None]
+    vals = np.stack([p[0] for p in parts])
+    idxs = np.stack([p[1] for p in parts])
+    best = vals.max(axis=0)
+    idx = np.where(vals == best[None], idxs, np.iinfo(np.int64).max).min(axis=0)
+    return best, idx
+
+
+def time_cpu(workload, n_sample, steps, warmup):
+    N, d, D, S, lo, hi, ls, desc = WORKLOADS[workload]
+    threads = os.cpu_count() or 1
+    import contextlib
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)          # one BLAS thread per worker; workers cover the cores
+    except Exception:
+        limiter = contextlib.nullcontext()
+    W, b, Theta = make_basis_arrays(D, d, S, ls, lo, hi)
+    X = candidates_host(N, d, lo, hi, 0)[:n_sample].astype(np.float64)
+    with limiter:
+        for _ in range(warmup):
+            cpu_argmax_threads(X[: max(4096, n_sample // 8)], W, b, Theta, threads)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_argmax_threads(X, W, b, Theta, threads)
+        dt = (time.perf_counter() - t0) / steps
+    return {"value": n_sample * S / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_sample} of the {N} candidates per step (fp64 NumPy oracle port of ff.py:20-21,162-167, shared basis, "
+                      f"{threads} worker threads); TF 2.1/TFP 0.9/GPflow 2.0.0-rc1 not installable offline",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, d, D, S, lo, hi, ls, desc = WORKLOADS[args.workload]
+    # bounded sample: calibrate on 2^14 rows, then size each step so that K steps take about a minute
+    probe = time_cpu(args.workload, 1 << 14, 1, 1)
+    rows_per_s = probe["value"] / S
+    steps = max(1, args.steps)
+    n_sample = int(min(N, max(1 << 12, rows_per_s * 60.0 / steps)))
+    n_sample -= n_sample % 128
+    res = time_cpu(args.workload, n_sample, steps, max(0, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "N_per_gpu": N, "d": d, "D": D, "S": S},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
+    nat = pkg._native
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, d, D, S, lo, hi, ls, desc = WORKLOADS[args.workload]
+    W, b, Theta = make_basis_arrays(D, d, S, ls, lo, hi)
+    basis = pkg.fourier_features.SharedBasis(W, b, Theta, device=dev)
+    cfg = basis.config(N)
+    n_rot = N_ROTATING if N * d * 4 * N_ROTATING <= (8 << 30) else max(2, (8 << 30) // (N * d * 4))
+    host_bufs = [torch.from_numpy(candidates_host(N, d, lo, hi, world * 0 + v + 100 * rank)).pin_memory()
+                 for v in range(min(n_rot, 4))]
+    dev_bufs = []
+    for v in range(n_rot):
+        if v < len(host_bufs):
+            dev_bufs.append(host_bufs[v].to(dev))
+        else:                                   # further variants: device-side shifted copies (content differs)
+            dev_bufs.append((dev_bufs[v % len(host_bufs)] + (v * 1e-4)).clamp_(lo, hi).contiguous())
+    offset = rank * N
+    h = nat.handle(local)
+
+    def step(i):
+        val, idx = basis.argmax(dev_bufs[i % n_rot], idx_offset=offset)
+        if world > 1:
+            val, idx = pkg.distributed.allgather_argmax(val, idx)
+        return val, idx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = nat.lib().tkbo_launch_count(h)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        out = step(args.warmup + i)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = nat.lib().tkbo_launch_count(h) - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * N * S / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers (every step: H2D of candidates + basis, D2H of result)
+    W_h, b_h, T_h = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (W, b, Theta))
+    res_val = torch.empty(S, dtype=torch.float32).pin_memory()
+    res_idx = torch.empty(S, dtype=torch.int64).pin_memory()
+
+    def e2e_step(i):
+        Xd = host_bufs[i % len(host_bufs)].to(dev, non_blocking=True)
+        basis.set(W_h.to(dev, non_blocking=True), b_h.to(dev, non_blocking=True), T_h.to(dev, non_blocking=True))
+        val, idx = basis.argmax(Xd, idx_offset=offset)
+        if world > 1:
+            val, idx = pkg.distributed.allgather_argmax(val, idx)
+        res_val.copy_(val, non_blocking=True)
+        res_idx.copy_(idx, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return float(res_val[0])
+
+    for i in range(min(3, args.warmup)):
+        e2e_step(i)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    tw0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_ms = (time.perf_counter() - tw0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = N * d * 4 + (D * d + D + D * S) * 8
+    d2h = S * (4 + 8)
+
+    line = None
+    if rank == 0:
+        pk = peaks()
+        alg_tf = 2.0 * N * D * S / (ms_per_step * 1e-3) / 1e12        # per GPU: one launch processes N candidates
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (fp16 hi/lo split x3 tcgen05.mma, fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": desc, "N_per_gpu": N, "d": d, "D": D, "S": S,
+                           "l2": f"{n_rot} rotating candidate buffers ({n_rot * N * d * 4 >> 20} MiB > 126 MiB L2)",
+                           "tiling": cfg, "parallelism": f"candidate shards x{world}, all-gather merge"},
+                "e2e": {"value": world * N * S / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "what": "pinned host candidates + fp64 basis -> device, basis_set, fused argmax, result -> host"},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": {"bound": "tensor", "achieved": alg_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                             "frac": alg_tf / pk["bf16_tflops"], "traffic": None,
+                             "kernel": "rff_fused_kernel", "flops_per_launch": 2.0 * N * D * S,
+                             "executed": 3 * alg_tf, "executed_frac": 3 * alg_tf / pk["bf16_tflops"],
+                             "note": "achieved = algorithmic 2*N*D*S per launch / CUDA-event time; executed = 3 fp16 MMAs per "
+                                     "product (hi*hi + hi*lo + lo*hi, fp32-accurate); peak = measured bf16 cuBLAS burst (" + pk["source"] + ")"}}
+    # ---- MPES kernel at c5
+    if rank == 0 and not args.no_mpes:
+        Sm, Q, C, k, M = 1024, 100000, 5, 3, 20
+        gen = torch.Generator(device=dev).manual_seed(4)
+        fchi = torch.randn((Sm, Q, C), device=dev, generator=gen)
+        fstar = torch.randn((Sm, M), device=dev, generator=gen)
+        common = importlib.import_module("top-k-ranking-bayesian-optimization_b200.acquisitions._common")
+        for _ in range(2):
+            common.mpes_from_device_samples(fchi, fstar, k, nat.MPES_RANK)
+        torch.cuda.synchronize()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        m0.record()
+        for _ in range(reps):
+            mi = common.mpes_from_device_samples(fchi, fstar, k, nat.MPES_RANK)
+        m1.record()
+        torch.cuda.synchronize()
+        mms = m0.elapsed_time(m1) / reps
+        bytes_alg = 4.0 * Sm * Q * C + 4.0 * Sm + 8.0 * Q
+        pk = peaks()
+        line["mpes"] = {"metric": "MPES acq evals/s", "value": Q / (mms * 1e-3), "unit": "acq evals/s", "ms_per_call": mms,
+                        "config": {"workload": "c5: 1e5 query sets x 1024 MC samples, k=3 of 5, M=20 maximisers (f-samples 2.05 GB > L2)"},
+                        "roofline": {"bound": "hbm", "achieved": bytes_alg / (mms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                     "frac": bytes_alg / (mms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                                     "kernel": "mpes_all_perms_kernel<5,3>"},
+                        "checksum": float(mi.sum())}
+        del fchi, fstar
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        res = time_cpu(args.workload, min(N, 1 << 18), 1, 1)
+        line["cpu_baseline"] = {k2: res[k2] for k2 in ("value", "unit", "cores", "kind", "sample")}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-mpes", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

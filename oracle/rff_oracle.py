@@ -185,10 +185,11 @@ def rff_values_shared(X, W, b, Theta, chunk=8192):
     return out
 
 
-def rff_argmax_shared(X, W, b, Theta, chunk=8192, idx_offset=0):
+def rff_argmax_shared(X, W, b, Theta, chunk=8192, idx_offset=0, return_absmax=False):
     """Per-sample (max value, lowest arg max) over all N candidates, plus the runner-up value
     (for tie accounting: an index mismatch only counts when the top-2 gap exceeds tolerance).
-    Returns (val[S], idx[S] int64, second[S])."""
+    Returns (val[S], idx[S] int64, second[S]) and, with return_absmax, max_n |F[n, s]| (the scale
+    relative tolerances are measured against)."""
     X = np.asarray(X, dtype=np.float64)
     W = np.asarray(W, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64).reshape(-1)
@@ -199,10 +200,12 @@ def rff_argmax_shared(X, W, b, Theta, chunk=8192, idx_offset=0):
     best = np.full(S, -np.inf)
     second = np.full(S, -np.inf)
     best_idx = np.zeros(S, dtype=np.int64)
+    absmax = np.zeros(S)
     cols = np.arange(S)
     for lo in range(0, N, chunk):
         hi = min(N, lo + chunk)
         F = (scale * np.cos(X[lo:hi] @ W.T + b)) @ Theta            # (chunk, S)
+        absmax = np.maximum(absmax, np.abs(F).max(axis=0))
         i1 = np.argmax(F, axis=0)
         v1 = F[i1, cols]
         if hi - lo > 1:
@@ -214,6 +217,8 @@ def rff_argmax_shared(X, W, b, Theta, chunk=8192, idx_offset=0):
         second = np.where(better, np.maximum(best, v2), np.maximum(second, v1))
         best_idx = np.where(better, i1 + lo, best_idx)
         best = np.where(better, v1, best)
+    if return_absmax:
+        return best, best_idx + idx_offset, second, absmax
     return best, best_idx + idx_offset, second
 
 

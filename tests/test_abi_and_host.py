@@ -1,0 +1,179 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/tkbo.h declares (no compute calls
+without a GPU), the product fails loudly without CUDA, host-side helpers agree with the oracle."""
+import ctypes
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpes_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pbo):
+    nat = pbo._native
+    declared = nat.declared_symbols()
+    assert len(declared) >= 18 and "tkbo_rff_argmax" in declared and "tkbo_mpes_topk" in declared
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"libtkbo.so does not export {name}"
+    # and the binding table covers exactly the header
+    assert sorted(nat._SIGNATURES) == declared
+    assert nat.lib().tkbo_version() == 100
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(pbo):
+    """The shipped binary really contains the Blackwell paths (UTCHMMA = tcgen05.mma, UTMALDG = TMA, LDTM/STTM)."""
+    out = subprocess.run(["cuobjdump", "-sass", pbo._native.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    sass = out.stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "CREDUX", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly(pbo):
+    with pytest.raises(pbo.TkboError):
+        pbo.fourier_features.SharedBasis(np.zeros((64, 2)), np.zeros(64), np.zeros((64, 4)))
+    with pytest.raises(pbo.TkboError):
+        pbo.acquisitions.rank_pes.I_batch(np.zeros((2, 3, 1)), np.zeros((2, 1)), None, f_samples=np.zeros((8, 8)))
+    out = ctypes.c_void_p()
+    rc = pbo._native.lib().tkbo_create(ctypes.byref(out), 0)
+    assert rc != 0 and "no CUDA device" in pbo._native.last_error()
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no file of the product package may reference it."""
+    pkg_dir = os.path.join(ROOT, "top-k-ranking-bayesian-optimization_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("CPU oracle", ""), f"{f} mentions the oracle"
+
+
+def test_import_by_directory_name_and_alias():
+    a = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
+    import tkbo_b200
+    assert tkbo_b200 is a
+    for name in ("fourier_features", "sample_fourier_features", "sample_theta_variational", "sample_features_weights",
+                 "sample_maximizers"):
+        assert callable(getattr(a.fourier_features, name))
+    assert callable(a.acquisitions.pes.I) and callable(a.acquisitions.pes.I_batch)
+    assert callable(a.acquisitions.rank_pes.I_batch) and callable(a.acquisitions.dts.sample_f)
+    assert callable(a.acquisitions.dts.soft_copeland_maximizer)
+
+
+def test_signatures_match_reference_defaults(pbo):
+    import inspect
+    sig = inspect.signature(pbo.fourier_features.sample_maximizers)
+    assert list(sig.parameters)[:8] == ["X", "count", "n_init", "D", "model", "min_val", "max_val", "num_steps"]
+    assert sig.parameters["num_steps"].default == 3000                          # ff.py:110
+    assert inspect.signature(pbo.fourier_features.sample_fourier_features).parameters["D"].default == 100   # ff.py:24
+    sig = inspect.signature(pbo.acquisitions.rank_pes.I_batch)
+    assert list(sig.parameters)[:6] == ["chi", "x_star", "model", "topk", "num_samples", "indifference_threshold"]
+    assert sig.parameters["num_samples"].default == 10000 and sig.parameters["topk"].default is None   # rank_pes.py:10
+    assert inspect.signature(pbo.acquisitions.pes.I).parameters["num_samples"].default == 1000        # pes.py:92
+    assert inspect.signature(pbo.acquisitions.dts.sample_f).parameters["D"].default == 1000           # dts.py:71
+
+
+def test_permutation_helpers_match_oracle(pbo, golden):
+    rp = pbo.acquisitions.rank_pes
+    g = golden("rank_pes.npz")
+    np.testing.assert_array_equal(rp.get_all_permutation_k_in_n(5, 3), g["perms_5_3"])
+    np.testing.assert_array_equal(rp.get_all_permutation_k_in_n(4, 2), g["perms_4_2"])
+    np.testing.assert_array_equal(rp.precompute_n_permutations(5, 3), g["nperm_5_3"])
+    np.random.seed(0)
+    r = rp.get_rand_permutation_k_in_n(6, 4, 50)
+    assert r.shape == (50, 4) and all(len(set(row)) == 4 for row in r.tolist())
+    for n, k in [(3, 1), (4, 4), (6, 2)]:
+        np.testing.assert_array_equal(rp.get_all_permutation_k_in_n(n, k), mpes_oracle.all_permutations_k_in_n(n, k))
+
+
+def test_dts_grid_helpers(pbo, golden):
+    g = golden("dts.npz")
+    dts = pbo.acquisitions.dts
+    np.testing.assert_array_equal(dts.uniform_grid(2, 12, 0, 1), g["grid"])
+    np.testing.assert_array_equal(dts.combinations(g["grid"]), g["combs"])
+
+
+def test_kernel_lengthscales_product_and_rbf(pbo):
+    m = pbo.model
+    assert m.kernel_lengthscales(m.RBF([0.2, 0.3]), 2).tolist() == [0.2, 0.3]
+    assert m.kernel_lengthscales(m.RBF(0.2), 3).tolist() == [0.2, 0.2, 0.2]
+    prod = m.Product([m.RBF(0.25), m.RBF(0.4)])
+    assert m.is_product_kernel(prod) and not m.is_product_kernel(m.RBF(1.0))
+    assert m.kernel_lengthscales(prod, 4).tolist() == [0.25, 0.4, 0.25, 0.4]      # ff.py:33-40
+
+
+def test_exact_predict_f_samples_shape_and_moments(pbo):
+    mdl = pbo.model.synthetic_model(12, 2, -1.5, 1.5, 0.6, seed=3)
+    X = np.random.default_rng(0).uniform(-1.5, 1.5, (7, 2))
+    s = mdl.predict_f_samples(X, 4000)
+    assert tuple(s.shape) == (4000, 7, 1) and s.numpy().dtype == np.float64
+    mu, cov = mdl.predict_f(X, full_cov=True)
+    assert np.allclose(s.numpy()[:, :, 0].mean(0), mu[:, 0], atol=5 * np.sqrt(np.diag(cov).max() / 4000) + 1e-3)
+
+
+def test_shard_ranges_cover_and_align(pbo):
+    sr = pbo.distributed.shard_range
+    for N, G in [(1000, 3), (1 << 20, 8), (129, 4), (5, 2)]:
+        parts = [sr(N, r, G) for r in range(G)]
+        assert parts[0][0] == 0 and parts[-1][1] == N
+        for (a, b), (c, d) in zip(parts, parts[1:]):
+            assert b == c and (a % 128 == 0 or a == b)
+        tiles = [(b - a + 127) // 128 for a, b in parts]
+        assert max(tiles) - min(tiles) <= 1
+
+
+def test_merge_pairs_lowest_index_on_ties(pbo):
+    vals = torch.tensor([[1.0, 5.0, 2.0], [1.0, 4.0, 3.0], [0.5, 5.0, 3.0]])
+    idxs = torch.tensor([[10, 11, 12], [3, 4, 5], [7, 2, -1]])
+    v, i = pbo.distributed.merge_pairs(vals, idxs)
+    assert v.tolist() == [1.0, 5.0, 3.0] and i.tolist() == [3, 2, 5]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    pkg = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    F = rng.standard_normal((1000, 16)).astype(np.float32)          # full (N, S) sample matrix, same on all ranks
+    F[500, 3] = F[100, 3] = F[:, 3].max() + 1.0                      # exact tie across shards -> lowest index wins
+    lo, hi = pkg.distributed.shard_range(1000, rank, world)
+    loc = torch.from_numpy(F[lo:hi])
+    val, idx = loc.max(dim=0)
+    # torch.max returns an arbitrary tied index; recompute the lowest like the kernel does
+    idx = torch.from_numpy(np.argmax(F[lo:hi], axis=0)) + lo
+    v, i = pkg.distributed.allgather_argmax(val, idx)
+    q.put((rank, v.numpy(), i.numpy()))
+    dist.destroy_process_group()
+
+
+def test_allgather_merge_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(0)
+    F = rng.standard_normal((1000, 16)).astype(np.float32)
+    F[500, 3] = F[100, 3] = F[:, 3].max() + 1.0
+    for _, v, i in res:
+        np.testing.assert_array_equal(i, np.argmax(F, axis=0))
+        np.testing.assert_array_equal(v, F.max(axis=0))
+    assert res[0][2][3] == 100

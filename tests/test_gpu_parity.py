@@ -1,0 +1,459 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test calls the product through its public
+Python surface, which reaches the kernels through the C ABI (ctypes -> libtkbo.so), and compares with the
+fp64 CPU oracle and/or the reference-produced golden vectors in tests/golden.
+
+Tolerances (BASELINE.json north star): sampled function values within 1e-4 relative to the sample's scale
+(max |f| over the candidates); maximiser indices identical except where the fp64 top-2 gap is below that
+tolerance (tie counts are asserted small and printed); acquisition values within 1e-4 relative.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpes_oracle, rff_oracle
+
+pytestmark = pytest.mark.gpu
+
+VAL_RTOL = 1e-4
+
+
+def _basis_inputs(rng, N, D, d, S, lo, hi, ls, realistic_theta=True, n_train=24):
+    X = rng.uniform(lo, hi, size=(N, d)).astype(np.float32)
+    W = rng.standard_normal((D, d)) / ls
+    b = rng.uniform(0, 2 * np.pi, D)
+    if realistic_theta:
+        # theta from the ff.py:56-87 regression on a synthetic fitted posterior
+        Xtr = rng.uniform(lo, hi, size=(n_train, d))
+        K = np.exp(-0.5 * (((Xtr[:, None] - Xtr[None]) / ls) ** 2).sum(-1))
+        L = np.linalg.cholesky(K + 1e-6 * np.eye(n_train))
+        q_mu, q_sqrt = L @ rng.standard_normal((n_train, 1)), (0.3 * L)[None]
+        phi = rff_oracle.fourier_features(Xtr[None], W[None], b[None, :, None])[0]
+        Theta = rff_oracle.theta_shared_basis(phi, q_mu, q_sqrt, rng.standard_normal((S, n_train)))
+    else:
+        Theta = rng.standard_normal((D, S)) * rng.uniform(0.05, 20.0, size=(1, S))
+    return X, W, b, Theta
+
+
+def _check_argmax(val, idx, X, W, b, Theta, idx_offset=0):
+    ref_val, ref_idx, second, absmax = rff_oracle.rff_argmax_shared(X.astype(np.float64), W, b, Theta, return_absmax=True)
+    F_scale = np.maximum(absmax, 1e-300)
+    val = val.cpu().numpy().astype(np.float64)
+    idx = idx.cpu().numpy() - idx_offset
+    assert np.all((idx >= 0) & (idx < X.shape[0]))
+    assert np.max(np.abs(val - ref_val) / F_scale) < VAL_RTOL
+    mism = idx != ref_idx
+    gap = (ref_val - second) / F_scale
+    ties = int(mism.sum())
+    assert not np.any(mism & (gap > VAL_RTOL)), "argmax differs where the top-2 gap exceeds tolerance"
+    return ties
+
+
+@pytest.mark.parametrize("N,D,d,S,lo,hi,ls", [
+    (128, 64, 2, 32, -1.5, 1.5, 0.6),         # one tile, one slab
+    (1000, 200, 1, 20, 0.0, 1.0, 0.2),        # ragged N, D not a multiple of 64, S not a multiple of 32
+    (5000, 1000, 6, 96, 0.0, 1.0, 0.2),       # SUSHI-like d=6
+    (4096, 256, 4, 256, 0.0, 1.0, 0.3),       # single-buffered 256-sample accumulator
+    (3000, 192, 3, 300, -1.0, 1.0, 0.5),      # two sample chunks of 160
+    (2048, 128, 12, 512, 0.0, 1.0, 0.8),      # d=12 (SUSHI duels), two chunks of 256
+    (777, 70, 5, 7, 0.0, 1.0, 0.4),           # d padded to the 6-wide template, tiny S
+    (20000, 512, 2, 64, -1.5, 1.5, 0.6),      # many tiles per CTA
+])
+def test_rff_eval_and_argmax_vs_oracle(pbo, N, D, d, S, lo, hi, ls):
+    rng = np.random.default_rng(N + D + S)
+    # 1-D inputs with 24 training points make phi phi^T numerically singular (cond ~ 1e16): see
+    # test_rff_error_scales_with_weight_norm for that regime; here keep the regression well posed.
+    X, W, b, Theta = _basis_inputs(rng, N, D, d, S, lo, hi, ls, n_train=8 if d == 1 else 24)
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    F = basis.eval(X).cpu().numpy().T.astype(np.float64)
+    Fref = rff_oracle.rff_values_shared(X.astype(np.float64), W, b, Theta)
+    scale = np.abs(Fref).max(axis=0)
+    assert np.isfinite(F).all()
+    assert np.max(np.abs(F - Fref) / scale) < VAL_RTOL
+    val, idx = basis.argmax(X, idx_offset=12345)
+    _check_argmax(val, idx, X, W, b, Theta, idx_offset=12345)
+    # calling twice gives identical results (workspace is re-initialised per call)
+    val2, idx2 = basis.argmax(X, idx_offset=12345)
+    assert torch.equal(val, val2) and torch.equal(idx, idx2)
+
+
+def test_rff_argmax_wide_dynamic_range_theta(pbo):
+    """Per-sample power-of-two scaling keeps tiny and huge weight samples equally accurate."""
+    rng = np.random.default_rng(5)
+    X, W, b, Theta = _basis_inputs(rng, 3000, 256, 2, 64, -1.5, 1.5, 0.6, realistic_theta=False)
+    Theta[:, 0] *= 1e-12
+    Theta[:, 1] *= 1e12
+    Theta[:, 2] = 0.0                       # all-equal sample: exact ties everywhere -> index 0
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    val, idx = basis.argmax(X)
+    _check_argmax(val, idx, X, W, b, Theta)
+    assert int(idx[2]) == 0 and float(val[2]) == 0.0
+
+
+def test_rff_error_scales_with_weight_norm(pbo):
+    """The fp32-grade feature map bounds the absolute error by ~4e-6 * ||sqrt(2/D) theta_s||_2.  With an
+    ill-posed regression (24 training points in 1-D, cond(phi phi^T) ~ 1e16, no jitter in ff.py:80-82) the
+    weights cancel massively (||theta'|| / max|f| ~ 1e3) and the relative error grows by that factor; the
+    bound reported by SharedBasis.error_bound() must still hold, and the argmax must stay within it."""
+    rng = np.random.default_rng(1000 + 200 + 20)
+    X, W, b, Theta = _basis_inputs(rng, 1000, 200, 1, 20, 0.0, 1.0, 0.2, n_train=24)
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    F = basis.eval(X).cpu().numpy().T.astype(np.float64)
+    Fref = rff_oracle.rff_values_shared(X.astype(np.float64), W, b, Theta)
+    bound = basis.error_bound().cpu().numpy()
+    kappa = np.linalg.norm(Theta * np.sqrt(2.0 / 200), axis=0) / np.abs(Fref).max(axis=0)
+    assert kappa.max() > 100                                     # this really is the ill-conditioned regime
+    assert np.all(np.abs(F - Fref).max(axis=0) <= bound)
+    val, idx = basis.argmax(X)
+    ref_val = Fref.max(axis=0)
+    got = Fref[idx.cpu().numpy(), np.arange(20)]                 # fp64 value at the returned index
+    assert np.all(ref_val - got <= 2 * bound) and np.all(np.abs(val.cpu().numpy() - ref_val) <= bound)
+
+
+def test_rff_argmax_exact_ties_pick_lowest_index(pbo):
+    """Duplicate candidates produce bit-identical values; np.argmax / tf.argmax keep the first."""
+    rng = np.random.default_rng(6)
+    X, W, b, Theta = _basis_inputs(rng, 1024, 128, 2, 32, -1.5, 1.5, 0.6)
+    ref_val, ref_idx, _ = rff_oracle.rff_argmax_shared(X.astype(np.float64), W, b, Theta)
+    Xd = np.concatenate([X, X, X], axis=0)                     # every maximiser now appears 3 times, 1024 rows apart
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    _, idx = basis.argmax(Xd)
+    idx = idx.cpu().numpy()
+    assert np.all(idx < 1024)
+    val1, idx1 = basis.argmax(X)
+    np.testing.assert_array_equal(idx, idx1.cpu().numpy())
+
+
+def test_rff_sharded_equals_single(pbo):
+    """Candidate shards with idx_offset + merge == one call over all candidates (the multi-GPU decomposition)."""
+    rng = np.random.default_rng(7)
+    X, W, b, Theta = _basis_inputs(rng, 10000, 256, 3, 48, 0.0, 1.0, 0.3)
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    val, idx = basis.argmax(X)
+    vals, idxs = [], []
+    for r in range(4):
+        lo, hi = pbo.distributed.shard_range(10000, r, 4)
+        v, i = basis.argmax(X[lo:hi], idx_offset=lo)
+        vals.append(v)
+        idxs.append(i)
+    mv, mi = pbo.distributed.merge_pairs(torch.stack(vals).cpu(), torch.stack(idxs).cpu())
+    assert torch.equal(mv, val.cpu()) and torch.equal(mi, idx.cpu())
+    # and the C-ABI merge kernel agrees
+    nat = pbo._native
+    ov = torch.empty(48, dtype=torch.float32, device="cuda:0")
+    oi = torch.empty(48, dtype=torch.int64, device="cuda:0")
+    sv, si = torch.stack(vals).contiguous(), torch.stack(idxs).contiguous()
+    nat.check(nat.lib().tkbo_merge_argmax(nat.handle(0), nat.ptr(sv), nat.ptr(si), 4, 48, nat.ptr(ov), nat.ptr(oi),
+                                          nat.current_stream_ptr(torch.device("cuda:0"))), "merge")
+    assert torch.equal(ov, val) and torch.equal(oi, idx)
+
+
+def test_rff_argmax_host_entry_point(pbo):
+    """tkbo_rff_argmax_host: the pure C-ABI end-to-end call with host buffers (no torch memory involved)."""
+    rng = np.random.default_rng(8)
+    X, W, b, Theta = _basis_inputs(rng, 2500, 128, 2, 40, -1.5, 1.5, 0.6)
+    nat = pbo._native
+    val = np.empty(40, dtype=np.float32)
+    idx = np.empty(40, dtype=np.int64)
+    as_p = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    Wc, bc, Tc = np.ascontiguousarray(W), np.ascontiguousarray(b), np.ascontiguousarray(Theta)
+    nat.check(nat.lib().tkbo_rff_argmax_host(nat.handle(0), as_p(Wc), as_p(bc), as_p(Tc), 128, 2, 40, as_p(X), 2500,
+                                             as_p(val), as_p(idx)), "argmax_host")
+    _check_argmax(torch.from_numpy(val), torch.from_numpy(idx), X, W, b, Theta)
+
+
+def test_argument_validation_errors(pbo):
+    nat = pbo._native
+    basis = ctypes.c_void_p()
+    assert nat.lib().tkbo_rff_basis_create(nat.handle(0), ctypes.byref(basis), 64, 40, 8) == -3   # d > 16 unsupported
+    assert "not supported" in nat.last_error()
+    assert nat.lib().tkbo_rff_basis_create(nat.handle(0), ctypes.byref(basis), 0, 2, 8) == -1
+    nat.check(nat.lib().tkbo_rff_basis_create(nat.handle(0), ctypes.byref(basis), 64, 2, 8), "create")
+    x = torch.zeros((4, 2), device="cuda:0")
+    v = torch.zeros(8, device="cuda:0")
+    i = torch.zeros(8, dtype=torch.int64, device="cuda:0")
+    rc = nat.lib().tkbo_rff_argmax(nat.handle(0), basis, nat.ptr(x), 4, 0, nat.ptr(v), nat.ptr(i), None)
+    assert rc == -1 and "basis_set" in nat.last_error()                                        # unset basis
+    nat.lib().tkbo_rff_basis_destroy(nat.handle(0), basis)
+
+
+# ------------------------------------------------------------------------------------------- reference-shaped API
+@pytest.mark.parametrize("tag", ["forr", "shc"])
+def test_eval_argmax_gather_matches_reference_golden(pbo, golden, tag):
+    """ff.py:162-167 on the exact arrays the reference drew (per-sample basis, float64)."""
+    g = golden("ff_sample_maximizers.npz")
+    fvals, idx, maxi = pbo.fourier_features.eval_argmax_gather(g[f"{tag}_x_star"], g[f"{tag}_W"], g[f"{tag}_b"],
+                                                               g[f"{tag}_theta"], device="cuda:0")
+    np.testing.assert_array_equal(maxi.cpu().numpy(), g[f"{tag}_maximizers"])
+    f_ref, idx_ref, _ = rff_oracle.eval_argmax_gather(g[f"{tag}_x_star"], g[f"{tag}_W"], g[f"{tag}_b"], g[f"{tag}_theta"])
+    np.testing.assert_allclose(fvals.cpu().numpy(), f_ref, rtol=0, atol=1e-11 * np.abs(f_ref).max())
+    np.testing.assert_array_equal(idx.cpu().numpy(), idx_ref)
+
+
+@pytest.mark.parametrize("tag", ["under", "over"])
+def test_fourier_features_and_theta_match_reference_golden(pbo, golden, tag):
+    g = golden("ff_features_theta.npz")
+    ff = pbo.fourier_features
+    phi = ff.fourier_features(g[f"{tag}_X"], g[f"{tag}_W"], g[f"{tag}_b"], device="cuda:0")
+    np.testing.assert_allclose(phi.cpu().numpy(), g[f"{tag}_phi"], rtol=0, atol=1e-14)
+    theta = ff.sample_theta_variational(phi, g[f"{tag}_q_mu"], g[f"{tag}_q_sqrt"], z=g[f"{tag}_z"])
+    ref = g[f"{tag}_theta"]
+    assert tuple(theta.shape) == ref.shape
+    np.testing.assert_allclose(theta.cpu().numpy(), ref, rtol=0, atol=1e-6 * np.abs(ref).max())
+
+
+def test_ascent_matches_oracle_restatement(pbo):
+    """ff.py:139-157 on the device vs the NumPy restatement of Keras RMSprop(rho=0)."""
+    rng = np.random.default_rng(9)
+    count, n_init, D, d = 6, 10, 128, 2
+    W = rng.standard_normal((count, D, d)) / 0.4
+    b = rng.uniform(0, 2 * np.pi, (count, D, 1))
+    theta = rng.standard_normal((count, D, 1))
+    x0 = rng.uniform(-1, 1, (count, n_init, d))
+    x_ref, steps_ref = rff_oracle.rmsprop_rho0_ascent(x0, W, b, theta, -1.0, 1.0, num_steps=400)
+    x, steps = pbo.fourier_features.ascend(x0, W, b, theta, -1.0, 1.0, num_steps=400, device="cuda:0")
+    assert steps == steps_ref
+    # sign-gradient steps of size lr * g / (|g| + 1e-7): coordinates whose gradient passes through ~1e-7 amplify
+    # the last-bit differences of the two summation orders, hence 1e-7 rather than 1e-12
+    np.testing.assert_allclose(x.cpu().numpy(), x_ref, rtol=0, atol=1e-7)
+    assert float(x.min()) >= -1.0 and float(x.max()) <= 1.0
+    # early stop: a flat objective (theta = 0 would divide by zero like the reference; use tiny gradient instead)
+    x1, steps1 = pbo.fourier_features.ascend(x0, W, b, theta, -1.0, 1.0, num_steps=0, device="cuda:0")
+    assert steps1 == 0 and np.array_equal(x1.cpu().numpy(), x0)
+
+
+def test_sample_maximizers_reference_semantics(pbo):
+    """End-to-end ff.py:110-169 at MPES_Forr defaults scaled down: shapes, bounds, and the returned point is the
+    argmax start of each sample (checked with the oracle on the arrays the call actually drew)."""
+    ff = pbo.fourier_features
+    mdl = pbo.model.synthetic_model(10, 1, 0.0, 1.0, 0.2, seed=1)
+    ff.seed(123)
+    maxi, info = ff.sample_maximizers(X=mdl.Z, count=5, n_init=12, D=200, model=mdl, min_val=0.0, max_val=1.0,
+                                      num_steps=60, device="cuda:0", return_info=True)
+    assert tuple(maxi.shape) == (5, 1) and maxi.dtype == torch.float64 and maxi.device.type == "cpu"
+    assert float(maxi.min()) >= 0.0 and float(maxi.max()) <= 1.0
+    W, b, theta = (info[k].cpu().numpy() for k in ("W", "b", "theta"))
+    _, _, ref_max = rff_oracle.eval_argmax_gather(info["x_star"].numpy(), W, b, theta)
+    np.testing.assert_array_equal(maxi.numpy(), ref_max)
+    # interpolation property of ff.py:80-84 (n < D): Phi(X_train) theta reproduces the q-samples it was fitted to
+    assert theta.shape == (5, 200, 1) and info["steps"] <= 60
+
+
+def test_sample_maximizers_grid_mode(pbo):
+    ff = pbo.fourier_features
+    mdl = pbo.model.synthetic_model(20, 2, -1.5, 1.5, 0.6, seed=2)
+    grid = pbo.acquisitions.dts.uniform_grid(2, 64, -1.5, 1.5)
+    ff.seed(7)
+    maxi, info = ff.sample_maximizers(X=mdl.Z, count=16, n_init=50, D=256, model=mdl, min_val=-1.5, max_val=1.5,
+                                      candidates=grid, device="cuda:0", return_info=True)
+    assert tuple(maxi.shape) == (16, 2)
+    bs = info["basis"]
+    ties = _check_argmax(info["values"], info["indices"], grid.astype(np.float32), bs.W.cpu().numpy(), bs.b.cpu().numpy(),
+                         bs.Theta.cpu().numpy())
+    assert ties <= 2
+    np.testing.assert_array_equal(maxi.numpy(), grid[info["indices"].numpy()])
+
+
+def test_singular_regression_retries_then_fails(pbo):
+    """ff.py:92-105: a regression that cannot be inverted on any draw exhausts 100 retries -> ValueError("Failed")."""
+    ff = pbo.fourier_features
+    # exactly singular Gram matrix [[1, 1], [1, 1]]: the LU hits a zero pivot (tf.linalg.inv -> InvalidArgumentError)
+    phi = torch.tensor([[[1.0, 0.0, 0.0], [1.0, 0.0, 0.0]]], dtype=torch.float64, device="cuda:0")
+    with pytest.raises(ff.SingularMatrixError):
+        ff.sample_theta_variational(phi, np.zeros((2, 1)), np.eye(2)[None])
+    # a zero lengthscale makes every draw of W infinite, so every retry fails the same way
+    mdl = pbo.model.PreferentialGP(pbo.model.RBF([0.0]), np.zeros((4, 1)), np.zeros((4, 1)), np.eye(4)[None])
+    X = np.zeros((2, 4, 1))
+    import contextlib
+    import io
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out), np.errstate(all="ignore"), pytest.raises(ValueError, match="Failed"):
+        ff.sample_features_weights(X, mdl, 16, device="cuda:0")
+    assert out.getvalue().count("Resampling phi, W, b, theta") == 100 and "Retry limit exceeded" in out.getvalue()
+
+
+# ------------------------------------------------------------------------------------------- MPES / PES / DTS
+@pytest.mark.parametrize("tag", ["c5k3", "c4k4", "c3k1", "c5k2_sparse"])
+def test_rank_pes_matches_reference_golden(pbo, golden, tag, capsys):
+    """rank_pes.I_batch (imported unmodified from the reference when the golden file was made) vs K2 on the
+    same fp32 samples."""
+    g = golden("rank_pes.npz")
+    S, Q, C, k, M = [int(v) for v in g[f"{tag}_meta"]]
+    mi = pbo.acquisitions.rank_pes.I_batch(np.zeros((Q, C, 6)), np.zeros((M, 6)), None, topk=k, num_samples=S,
+                                           f_samples=g[f"{tag}_fsample_all"], device="cuda:0")
+    assert "all possible observations" in capsys.readouterr().out                   # rank_pes.py:65-69
+    ref = g[f"{tag}_mi"]
+    np.testing.assert_allclose(mi.numpy(), ref, rtol=1e-4, atol=1e-9)
+
+
+def test_rank_pes_through_model_predict_f_samples(pbo):
+    """The reference call path: I_batch asks the model for (S, N, 1) samples (rank_pes.py:28)."""
+    rng = np.random.default_rng(3)
+    S, Q, C, M, d = 256, 9, 4, 5, 2
+    fs = rng.standard_normal((S, Q * C + M)).astype(np.float32)
+
+    class Stub:
+        def predict_f_samples(self, x, n):
+            assert x.shape == (Q * C + M, d) and n == S
+            return torch.from_numpy(fs.astype(np.float64)[:, :, None])
+
+    chi, xs = rng.uniform(size=(Q, C, d)), rng.uniform(size=(M, d))
+    mi = pbo.acquisitions.rank_pes.I_batch(chi, xs, Stub(), topk=2, num_samples=S, device="cuda:0")
+    ref = mpes_oracle.rank_mpes_from_samples(fs[:, :Q * C].reshape(S, Q, C).astype(np.float64),
+                                             fs[:, Q * C:].astype(np.float64), topk=2)
+    np.testing.assert_allclose(mi.numpy(), ref, rtol=1e-4, atol=1e-9)
+
+
+def test_rank_pes_explicit_table_and_random_subset(pbo):
+    """Explicit permutation tables (the reference's >1000-permutation path ships a random table)."""
+    rng = np.random.default_rng(4)
+    S, Q, C, M, k = 200, 11, 6, 4, 3
+    fs = (rng.standard_normal((S, 3)) @ rng.standard_normal((3, Q * C + M))).astype(np.float32)
+    fchi = torch.from_numpy(fs[:, :Q * C].reshape(S, Q, C).copy()).cuda()
+    fstar = torch.from_numpy(fs[:, Q * C:].copy()).cuda()
+    from importlib import import_module
+    common = import_module("top-k-ranking-bayesian-optimization_b200.acquisitions._common")
+    perms = mpes_oracle.all_permutations_k_in_n(C, k)                               # 120 rows: generic kernel
+    sub = perms[rng.integers(0, 120, size=37)]                                      # duplicates allowed
+    for table in (perms, sub):
+        mi = common.mpes_from_device_samples(fchi, fstar, k, 0, table).cpu().numpy()
+        ref = mpes_oracle.rank_mpes_streaming(fs[:, :Q * C].reshape(S, Q, C).astype(np.float64),
+                                              np.argmax(fs[:, Q * C:], axis=1), M, table)
+        np.testing.assert_allclose(mi, ref, rtol=1e-4, atol=1e-9)
+    # all-permutation call without a table for a (C, k) that has no register-resident instantiation
+    mi_all = common.mpes_from_device_samples(fchi, fstar, k, 0, None).cpu().numpy()
+    ref_all = mpes_oracle.rank_mpes_from_samples(fs[:, :Q * C].reshape(S, Q, C).astype(np.float64),
+                                                 fs[:, Q * C:].astype(np.float64), topk=k)
+    np.testing.assert_allclose(mi_all, ref_all, rtol=1e-4, atol=1e-9)
+
+
+def test_rank_pes_properties(pbo):
+    """MI >= 0; MI == 0 when the query samples are independent of which maximiser wins; topk=1 == pes.I up to eps."""
+    rng = np.random.default_rng(11)
+    S, Q, C, M = 512, 40, 4, 6
+    fchi = rng.standard_normal((S, Q, C)).astype(np.float32)
+    fstar = rng.standard_normal((S, M)).astype(np.float32)
+    fs = np.concatenate([fchi.reshape(S, Q * C), fstar], axis=1)
+    mi = pbo.acquisitions.rank_pes.I_batch(np.zeros((Q, C, 1)), np.zeros((M, 1)), None, topk=2, num_samples=S,
+                                           f_samples=fs, device="cuda:0").numpy()
+    assert np.all(mi > -1e-9)
+    fstar_const = np.zeros((S, M), dtype=np.float32)
+    fstar_const[:, 2] = 1.0                                  # one maximiser always wins -> no information
+    fs0 = np.concatenate([fchi.reshape(S, Q * C), fstar_const], axis=1)
+    mi0 = pbo.acquisitions.rank_pes.I_batch(np.zeros((Q, C, 1)), np.zeros((M, 1)), None, topk=2, num_samples=S,
+                                            f_samples=fs0, device="cuda:0").numpy()
+    assert np.max(np.abs(mi0)) < 1e-6
+    mi1 = pbo.acquisitions.rank_pes.I_batch(np.zeros((Q, C, 1)), np.zeros((M, 1)), None, topk=1, num_samples=S,
+                                            f_samples=fs, device="cuda:0").numpy()
+    for q in range(0, Q, 7):
+        p = float(pbo.acquisitions.pes.I(np.zeros((C, 1)), np.zeros((M, 1)), None, num_samples=S, device="cuda:0",
+                                         f_samples=np.concatenate([fstar, fchi[:, q, :]], axis=1)))
+        assert abs(p - mi1[q]) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["c1", "c3"])
+def test_pes_I_matches_reference_golden(pbo, golden, tag):
+    """pes.I / pes.I_batch executed from the reference source (golden) vs K2 in PES mode, c1 sizes S=1000, M=20, C=2."""
+    g = golden("pes.npz")
+    S, M, C, Qn = [int(v) for v in g[f"{tag}_meta"]]
+    smp = g[f"{tag}_samples"]
+    got = np.array([float(pbo.acquisitions.pes.I(np.zeros((C, 1)), np.zeros((M, 1)), None, num_samples=S,
+                                                 f_samples=smp[q], device="cuda:0")) for q in range(Qn)])
+    np.testing.assert_allclose(got, g[f"{tag}_I"], rtol=1e-4, atol=1e-9)
+
+
+def test_pes_I_batch_reference_loop_semantics(pbo, golden):
+    """I_batch with a model that only has predict_f_samples: one draw per query, like pes.py:132."""
+    g = golden("pes.npz")
+    S, M, C, Qn = [int(v) for v in g["c1_meta"]]
+    smp = g["c1_samples"]
+
+    class Stub:
+        calls = 0
+
+        def predict_f_samples(self, x, n):
+            assert x.shape == (M + C, 1) and n == S
+            out = torch.from_numpy(smp[Stub.calls].astype(np.float64)[:, :, None])
+            Stub.calls += 1
+            return out
+
+    vals = pbo.acquisitions.pes.I_batch(np.zeros((Qn, C, 1)), np.zeros((M, 1)), Stub(), device="cuda:0")
+    assert isinstance(vals, np.ndarray) and vals.shape == (Qn,)
+    np.testing.assert_allclose(vals, g["c1_I"], rtol=1e-4, atol=1e-9)
+
+
+def test_dts_sample_f_and_copeland_match_reference_golden(pbo, golden):
+    """dts.sample_f on the basis the reference drew (W, b, z from the golden file) and the soft-Copeland winner."""
+    g = golden("dts.npz")
+    ff = pbo.fourier_features
+    n = g["Xq"].shape[0]
+    phi_y = ff.fourier_features(g["Xq"][None], g["W"], g["b"], device="cuda:0")
+    theta = ff.sample_theta_variational(phi_y, g["q_mu"], g["q_sqrt"], z=g["z"])            # (1, D, 1)
+    basis = ff.SharedBasis(g["W"][0], g["b"][0, :, 0], theta[0], device="cuda:0")
+    f = basis.eval(g["combs"]).reshape(-1, 1)
+    ref = g["f_vals"]
+    assert np.max(np.abs(f.cpu().numpy() - ref)) < VAL_RTOL * np.abs(ref).max()
+    winner = pbo.acquisitions.dts.soft_copeland_maximizer(f, g["grid"])
+    np.testing.assert_array_equal(winner, g["winner"])
+    # CPU-tensor input path and the scores themselves
+    w2, scores = pbo.acquisitions.dts.soft_copeland_maximizer(ref, g["grid"], device="cuda:0", return_scores=True)
+    np.testing.assert_array_equal(w2, g["winner"])
+    np.testing.assert_allclose(scores.numpy(), mpes_oracle.soft_copeland_scores(ref), rtol=1e-5)
+    assert n == 9
+
+
+def test_dts_sample_f_signature_path(pbo):
+    """sample_f(m, query_points, combs, D) with a Product kernel: shape, dtype, finite, Copeland winner on the grid."""
+    dts = pbo.acquisitions.dts
+    mdl = pbo.model.synthetic_model(9, 4, 0.0, 1.0, [0.25, 0.4, 0.25, 0.4], seed=5, product=True)
+    grid = dts.uniform_grid(2, 10, 0, 1)
+    combs = dts.combinations(grid)
+    f = dts.sample_f(mdl, mdl.Z, combs, 64, device="cuda:0")
+    assert tuple(f.shape) == (10000, 1) and f.dtype == torch.float64 and bool(torch.isfinite(f).all())
+    assert dts.soft_copeland_maximizer(f, grid, device="cuda:0").shape == (2,)
+
+
+def test_rff_joint_sampling_feeds_mpes(pbo):
+    """model.predict_f_samples_device (RFF draws through the store-F epilogue) -> K2, nothing leaves the GPU."""
+    mdl = pbo.model.synthetic_model(16, 6, 0.0, 1.0, 0.4, seed=8)
+    rng = np.random.default_rng(0)
+    chi = rng.uniform(size=(300, 5, 6))
+    xs = rng.uniform(size=(12, 6))
+    mi = pbo.acquisitions.rank_pes.I_batch(chi, xs, mdl, topk=3, num_samples=256, rff_features=256, device="cuda:0")
+    assert tuple(mi.shape) == (300,) and bool(torch.isfinite(mi).all()) and float(mi.min()) > -1e-9
+    vals = pbo.acquisitions.pes.I_batch(chi[:50, :2], xs, mdl, device="cuda:0")
+    assert vals.shape == (50,) and np.isfinite(vals).all()
+
+
+def test_large_shape_properties(pbo):
+    """Size-independent properties at a BASELINE-sized tile count (c2: N = 2^20, D = 1024, S = 64): the argmax
+    is invariant to candidate order up to the permutation, the fused max equals the max of the store-F output on
+    a slice containing the winner, and sharding leaves it unchanged."""
+    rng = np.random.default_rng(1)
+    N, D, d, S = 1 << 20, 1024, 2, 64
+    W = rng.standard_normal((D, d)) / 0.6
+    b = rng.uniform(0, 2 * np.pi, D)
+    Theta = rng.standard_normal((D, S))
+    X = torch.rand((N, d), device="cuda:0") * 3.0 - 1.5
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    val, idx = basis.argmax(X)
+    perm = torch.randperm(N, device="cuda:0")
+    val_p, idx_p = basis.argmax(X[perm].contiguous())
+    assert torch.equal(val, val_p)
+    # at N = 2^20 distinct candidates can tie bit-for-bit in fp32, so the winner may change with the order;
+    # what must hold is that every returned index attains the returned maximum
+    rows = basis.eval(X[idx].contiguous())                     # (S, S): sample s at its own winner
+    assert torch.equal(rows.diagonal(), val)
+    rows_p = basis.eval(X[perm[idx_p]].contiguous())
+    assert torch.equal(rows_p.diagonal(), val)
+    assert int((perm[idx_p] != idx).sum()) <= 8               # exact cross-candidate ties are rare
+    half = N // 2
+    v0, i0 = basis.argmax(X[:half])
+    v1, i1 = basis.argmax(X[half:], idx_offset=half)
+    mv, mi = pbo.distributed.merge_pairs(torch.stack([v0, v1]).cpu(), torch.stack([i0, i1]).cpu())
+    assert torch.equal(mv, val.cpu()) and torch.equal(mi, idx.cpu())
+    # oracle spot check on the winners' neighbourhood only (cheap): fp64 value at the returned index
+    xw = X[idx].cpu().numpy().astype(np.float64)
+    f64 = rff_oracle.rff_values_shared(xw, W, b, Theta)
+    assert np.max(np.abs(np.diag(f64) - val.cpu().numpy()) / np.abs(np.diag(f64))) < VAL_RTOL

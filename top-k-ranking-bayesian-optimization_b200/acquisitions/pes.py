@@ -1,0 +1,64 @@
+"""Predictive Entropy Search (top-1 of C choices) — signatures of the reference's acquisitions/pes.py.
+
+``I`` (pes.py:92-123) draws one sample matrix at [x_star; chi] and evaluates the eps-smoothed MI; the
+Monte-Carlo body (pes.py:44-89, 108-123) runs in ``tkbo_mpes_topk`` (mode TKBO_MPES_PES).  ``I_batch``
+(pes.py:126-132) is a Python loop over ``I`` in the reference, i.e. one independent sample matrix per query;
+that remains the behaviour for a model that only offers ``predict_f_samples``.  With ``joint=True`` (default
+when the model can sample on the device) all queries share one joint draw at [x_star; chi_1; ...; chi_Q] and
+are scored by a single kernel launch — the same estimator, without 3000 tiny launches per BO iteration.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _native as nat
+from ..model import to_numpy
+from . import _common
+
+
+def I(chi, x_star, model, num_samples=1000, *, device=None, f_samples=None):
+    """chi (num_choices, d), x_star (num_max, d) -> scalar (0-d CPU float64 tensor).        [pes.py:92-123]
+    ``f_samples`` (S, num_max + num_choices) supplies the matrix pes.py:106 would draw."""
+    chi = to_numpy(chi)
+    x_star = to_numpy(x_star)
+    num_choices, num_max = chi.shape[0], x_star.shape[0]
+    dev = _common.device_of(device)
+    if f_samples is None:
+        x_vals = np.concatenate([x_star, chi], axis=0)                       # pes.py:105
+        fs = _common.joint_samples(model, x_vals, num_samples, dev)          # pes.py:106
+    else:
+        fs = _common.as_f32_device(f_samples, dev)
+    S = fs.shape[0]
+    fstar = fs[:, :num_max].contiguous()                                     # pes.py:107
+    fchi = fs[:, num_max:].contiguous().reshape(S, 1, num_choices)
+    return _common.mpes_from_device_samples(fchi, fstar, 1, nat.MPES_PES)[0].cpu()
+
+
+def I_batch(chi_batch, x_star, model, *, num_samples=1000, joint=None, device=None, rff_features=None):
+    """chi_batch (num_queries, num_choices, d) -> np.ndarray (num_queries,), as pes.py:126-132."""
+    chi_batch = to_numpy(chi_batch)
+    x_star = to_numpy(x_star)
+    Q, C, d = chi_batch.shape
+    M = x_star.shape[0]
+    if joint is None:
+        joint = hasattr(model, "predict_f_samples_device") or rff_features is not None
+    if not joint:
+        return np.array([float(I(chi, x_star, model, num_samples=num_samples, device=device)) for chi in chi_batch])
+    dev = _common.device_of(device)
+    x_all = np.concatenate([x_star, chi_batch.reshape(Q * C, d)], axis=0)
+    fs = _common.joint_samples(model, x_all, num_samples, dev, rff_features if rff_features is not None else 1024)
+    S = fs.shape[0]
+    fstar = fs[:, :M].contiguous()
+    fchi = fs[:, M:].contiguous().reshape(S, Q, C)
+    return _common.mpes_from_device_samples(fchi, fstar, 1, nat.MPES_PES).cpu().numpy()
+
+
+def sample_maximizers_discrete(model, count, data, batch_size=1000, *, D=1024, device=None):
+    """Grid-argmax maximiser sampling (signature of pes.py:24-41).  The reference draws exact GP samples in
+    independent 1000-point batches; here the ``count`` samples are RFF posterior draws evaluated on ALL of
+    ``data`` by the fused kernel, argmax'd per sample (``batch_size`` is accepted and unused).
+    -> (count, input_dims) CPU float64 tensor."""
+    from .. import fourier_features as ff
+    basis = ff.SharedBasis.sample(model.Z if hasattr(model, "Z") else to_numpy(model.inducing_variable.Z), model, D=D,
+                                  count=count, device=device)
+    return basis.maximizers(data)

@@ -1,0 +1,78 @@
+"""Multi-GPU use of the RFF sampler: the candidate axis shards across ranks, (W, b, Theta) are replicated, and
+the only exchange is one all-gather of each rank's S (value, index) pairs (8 S bytes per rank, over NCCL /
+NVLink on GPUs; gloo in the CPU tests of the merge logic).  One process per GPU (torchrun).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(N, rank, world_size):
+    """Contiguous row range [lo, hi) of rank's candidate shard; sizes differ by at most one 128-row tile."""
+    tiles = (N + 127) // 128
+    per, rem = divmod(tiles, world_size)
+    lo_t = rank * per + min(rank, rem)
+    hi_t = lo_t + per + (1 if rank < rem else 0)
+    return min(N, lo_t * 128), min(N, hi_t * 128)
+
+
+def merge_pairs(vals, idxs):
+    """vals, idxs: [G, S] arrays/tensors of per-rank (max value, global arg max; idx < 0 = empty shard).
+    -> (val[S], idx[S]): largest value, lowest index on exact ties — np.argmax semantics over the union."""
+    import torch
+    vals = torch.as_tensor(vals)
+    idxs = torch.as_tensor(idxs)
+    G, S = vals.shape
+    v = vals.clone()
+    v[idxs < 0] = -float("inf")
+    best = v.max(dim=0).values
+    big = torch.iinfo(torch.int64).max
+    cand = torch.where((v == best[None, :]) & (idxs >= 0), idxs, torch.full_like(idxs, big))
+    idx = cand.min(dim=0).values
+    idx = torch.where(idx == big, torch.full_like(idx, -1), idx)
+    return best, idx
+
+
+def allgather_argmax(val, idx, group=None):
+    """All ranks contribute (val[S], idx[S]) and receive the merged global pairs.  Works with any
+    torch.distributed backend (NCCL on GPUs, gloo on CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return val, idx
+    # one collective: pack (float32 value bits, int64 index) into an int64 [2, S] payload
+    payload = torch.stack([val.to(torch.float32).view(torch.int32).to(torch.int64), idx.to(torch.int64)])
+    gathered = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload, group=group)
+    allp = torch.stack(gathered)                                        # [G, 2, S]
+    vals = allp[:, 0, :].to(torch.int32).view(torch.float32)
+    idxs = allp[:, 1, :]
+    return merge_pairs(vals, idxs)
+
+
+def sharded_argmax(basis, X_local, idx_offset, group=None):
+    """K1 on this rank's shard, then the all-gather merge.  ``basis`` is a fourier_features.SharedBasis holding
+    the same (W, b, Theta) on every rank; X_local (N_local, d) are rows [idx_offset, idx_offset + N_local)."""
+    import torch
+    if X_local.shape[0] == 0:                       # more ranks than 128-row tiles: this shard is empty
+        val = torch.full((basis.S,), -float("inf"), dtype=torch.float32, device=basis.device)
+        idx = torch.full((basis.S,), -1, dtype=torch.int64, device=basis.device)
+    else:
+        val, idx = basis.argmax(X_local, idx_offset=idx_offset)
+    return allgather_argmax(val, idx, group=group)
+
+
+def broadcast_basis_arrays(W, b, Theta, src=0, group=None, device=None):
+    """Replicate the host-drawn basis from rank ``src`` (once per BO iteration; <= 34 MB at the c4 shape)."""
+    import torch
+    import torch.distributed as dist
+    out = []
+    for a in (W, b, Theta):
+        t = torch.as_tensor(np.ascontiguousarray(a)) if not isinstance(a, torch.Tensor) else a
+        if device is not None:
+            t = t.to(device)
+        t = t.contiguous()
+        dist.broadcast(t, src=src, group=group)
+        out.append(t)
+    return out
