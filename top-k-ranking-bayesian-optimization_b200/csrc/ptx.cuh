@@ -117,6 +117,26 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t tile_smem_addr, uint
   return desc;
 }
 
+// Same descriptor split into a runtime low word (start address field, LBO) and the constant high word, so that
+// the issue loop advances along K / across ring stages with one 32-bit add.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t tile_smem_addr) {
+  return ((tile_smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t smem_desc_from_lo(uint32_t lo) {
+  constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO | version 1 | SWIZZLE_128B
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// One elected lane of a converged warp.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Instruction descriptor, kind::f16: fp16 A and B (K-major), fp32 D, M x N tile.
 __host__ __device__ constexpr uint32_t idesc_f16_f32(uint32_t M, uint32_t N) {
   return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);

@@ -140,15 +140,14 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const uint32_t a_col0 = kTmemCols - p.stages * kSlabK;   // TMEM A ring occupies the top columns
 
   if (warp == 12) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int chunk = item % p.n_chunks;
-        for (int slab = 0; slab < p.n_slabs; ++slab, ++it) {
-          const int st = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&bar_empty[st], ph ^ 1);
+    // ------------------------------------------------------------------ TMA producer (warp-converged, one elected issuer)
+    int st = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int chunk = item % p.n_chunks;
+      for (int slab = 0; slab < p.n_slabs; ++slab) {
+        mbar_wait(&bar_empty[st], ph ^ 1);
+        if (elect_one()) {
           uint8_t* sb = smem + st * sbytes;
           mbar_arrive_expect_tx(&bar_b_full[st], txbytes);
           tma_load_2d(sb, &tm_hi, &bar_b_full[st], slab * kSlabK, chunk * SC);
@@ -156,61 +155,68 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           bulk_load_1d(sb + 2 * SC * 128, p.Wpack + static_cast<size_t>(slab) * kSlabK * WS, kSlabK * WS * 4,
                        &bar_b_full[st]);
         }
+        __syncwarp();
+        if (++st == p.stages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 13) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = idesc_f16_f32(kTileM, SC);
-      uint32_t it = 0, local = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
-        const int ab = local % p.acc_bufs;
-        const uint32_t aph = (local / p.acc_bufs) & 1;
-        mbar_wait(&bar_acc_empty[ab], aph ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (warp-converged, one elected issuer)
+    const uint32_t idesc = idesc_f16_f32(kTileM, SC);
+    // descriptor low words advance by plain adds: (addr >> 4) never carries out of its 14-bit field
+    const uint32_t desc_lo0 = smem_desc_lo(smem_u32(smem));
+    const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
+    const uint32_t desc_lopart = static_cast<uint32_t>(SC * 128) >> 4;     // Theta-lo tile follows the hi tile
+    int st = 0, ab = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      mbar_wait(&bar_acc_empty[ab], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * SC;
+      for (int slab = 0; slab < p.n_slabs; ++slab) {
+        mbar_wait(&bar_b_full[st], ph);
+        mbar_wait(&bar_a_full[st], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * SC;
-        for (int slab = 0; slab < p.n_slabs; ++slab, ++it) {
-          const int st = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&bar_b_full[st], ph);
-          mbar_wait(&bar_a_full[st], ph);
-          tc_fence_after();
-          const uint32_t sb = smem_u32(smem + st * sbytes);
+        if (elect_one()) {
+          const uint32_t b_hi = desc_lo0 + st * desc_stage;
+          const uint32_t b_lo = b_hi + desc_lopart;
           const uint32_t a_hi = tmem_base + a_col0 + st * kSlabK;
           const uint32_t a_lo = a_hi + kSlabK / 2;
 #pragma unroll
           for (int k = 0; k < kSlabK / kUmmaK; ++k) {
-            const uint64_t b_hi = smem_desc_k128(sb, k * kUmmaK * 2);
-            const uint64_t b_lo = smem_desc_k128(sb + SC * 128, k * kUmmaK * 2);
-            const uint32_t a_h = a_hi + k * (kUmmaK / 2);
-            const uint32_t a_l = a_lo + k * (kUmmaK / 2);
-            mma_f16_ts(d_tmem, a_h, b_hi, idesc, (slab | k) != 0);
-            mma_f16_ts(d_tmem, a_h, b_lo, idesc, 1);
-            mma_f16_ts(d_tmem, a_l, b_hi, idesc, 1);
+            const uint32_t koff = k * ((kUmmaK * 2) >> 4);               // 32 bytes of K per step, in 16-byte units
+            mma_f16_ts(d_tmem, a_hi + k * (kUmmaK / 2), smem_desc_from_lo(b_hi + koff), idesc, (slab | k) != 0);
+            mma_f16_ts(d_tmem, a_hi + k * (kUmmaK / 2), smem_desc_from_lo(b_lo + koff), idesc, 1);
+            mma_f16_ts(d_tmem, a_lo + k * (kUmmaK / 2), smem_desc_from_lo(b_hi + koff), idesc, 1);
           }
           tc_commit(&bar_empty[st]);
+          if (slab == p.n_slabs - 1) tc_commit(&bar_acc_full[ab]);
         }
-        tc_commit(&bar_acc_full[ab]);
+        __syncwarp();
+        if (++st == p.stages) { st = 0; ph ^= 1; }
       }
+      if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ feature producers
+    // group g owns the global slab iterations it = g, g + 2, g + 4, ... (across work items), so its ring
+    // position always advances by two
     const int group = (warp - 4) >> 2;               // 0 or 1
     const int q = warp & 3;                          // TMEM lane quarter of this warp
     const int r = q * 32 + lane;                     // row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t it0 = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, it0 += p.n_slabs) {
+    int st = group % p.stages;
+    uint32_t ph = (group / p.stages) & 1;
+    int slab = group;
+    int item = blockIdx.x;
+    while (slab >= p.n_slabs && item < n_items) { slab -= p.n_slabs; item += gridDim.x; }
+    while (item < n_items) {
       const int mtile = item / p.n_chunks;
       long long row = static_cast<long long>(mtile) * kTileM + r;
       if (row >= p.N) row = p.N - 1;                 // clamp: tail rows are masked in the epilogue
       float x[DT];
 #pragma unroll
       for (int i = 0; i < DT; ++i) x[i] = (i < p.d) ? __ldg(p.X + row * p.d + i) : 0.f;
-      for (int slab = group; slab < p.n_slabs; slab += 2) {
-        const uint32_t it = it0 + slab;
-        const int st = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
+      for (; slab < p.n_slabs; slab += 2) {
         mbar_wait(&bar_b_full[st], ph);              // W slab present; also implies the TMEM stage is free
         const float* wslab = reinterpret_cast<const float*>(smem + st * sbytes + 2 * SC * 128);
         uint32_t hi[32], lo[32];
@@ -221,18 +227,22 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bar_a_full[st]);
+        st += 2;
+        if (st >= p.stages) { st -= p.stages; ph ^= 1; }
       }
+      slab -= p.n_slabs;                             // 0 or 1: first slab of this group in the next item
+      item += gridDim.x;
+      while (slab >= p.n_slabs && item < n_items) { slab -= p.n_slabs; item += gridDim.x; }   // n_slabs == 1
     }
   } else {
     // ------------------------------------------------------------------ epilogue
     const int q = warp;                              // warps 0..3 <-> TMEM lanes 32q..32q+31
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t local = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+    int ab = 0;
+    uint32_t aph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int mtile = item / p.n_chunks;
       const int chunk = item % p.n_chunks;
-      const int ab = local % p.acc_bufs;
-      const uint32_t aph = (local / p.acc_bufs) & 1;
       const long long row0 = static_cast<long long>(mtile) * kTileM + q * 32;
       const long long row = row0 + lane;
       const bool partial = (row0 + 32 > p.N);
@@ -317,6 +327,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       }
       tc_fence_before();
       mbar_arrive(&bar_acc_empty[ab]);
+      if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
     }
   }
 
