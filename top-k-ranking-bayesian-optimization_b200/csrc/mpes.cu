@@ -13,9 +13,11 @@
 #include <cuda_fp16.h>
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace tkbo {
 
@@ -66,29 +68,51 @@ __host__ __device__ constexpr int perm_count(int C, int K) {
   for (int i = 0; i < K; ++i) p *= (C - i);
   return p;
 }
+__host__ __device__ constexpr int popcount_c(unsigned m) {
+  int n = 0;
+  for (; m; m &= m - 1) ++n;
+  return n;
+}
 
-// sum of e over the choices not in `used` (fixed ascending order => identical masks share one expression)
-template <int C>
-__device__ __forceinline__ float remaining_sum(const float (&e)[C], unsigned used) {
-  float s = 0.f;
-  bool first = true;
+__device__ __forceinline__ float fast_ex2(float x) {      // raw MUFU.EX2 (flushes denormals; inputs here are <= 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {      // raw MUFU.RCP, ~1 ulp
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 1 / (sum of e over the choices NOT in mask) for every mask with fewer than K members: the Plackett-Luce
+// denominators depend on the *set* of already-ranked choices only, so C=5, K=3 needs 1 + 5 + 10 reciprocals for
+// its 60 orderings.  Sums are taken directly over the remaining entries (no T - e_a cancellation).
+template <int C, int K>
+__device__ __forceinline__ void subset_reciprocals(const float (&e)[C], float (&rs)[1 << C]) {
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    if ((used >> c) & 1u) continue;
-    s = first ? e[c] : s + e[c];
-    first = false;
+  for (unsigned m = 0; m < (1u << C); ++m) {
+    if (popcount_c(m) >= K || popcount_c(m) >= C - 1) continue;       // a lone remaining choice has probability 1
+    float s = 0.f;
+    bool first = true;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if ((m >> c) & 1u) continue;
+      s = first ? e[c] : s + e[c];
+      first = false;
+    }
+    rs[m] = fast_rcp(s);
   }
-  return s;
 }
 
 template <int C, int K, int DEPTH>
 struct PermWalk {
   // prob = probability of the choices ranked so far (best first); used = their bit mask.
   template <int P>
-  static __device__ __forceinline__ void run(const float (&e)[C], unsigned used, float prob, float (&acc)[P], int& leaf) {
+  static __device__ __forceinline__ void run(const float (&e)[C], const float (&rs)[1 << C], unsigned used, float prob,
+                                             float (&acc)[P], int& leaf) {
     constexpr int remaining = C - DEPTH;
-    float pr = prob;
-    if (remaining > 1) pr = prob * __fdividef(1.f, remaining_sum<C>(e, used));   // else factor e/e = 1
+    const float pr = (remaining > 1) ? ((DEPTH == 0) ? rs[0] : prob * rs[used]) : prob;   // else factor e/e = 1
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       if ((used >> c) & 1u) continue;
@@ -97,84 +121,162 @@ struct PermWalk {
         ++leaf;
       } else {
         const float child = (remaining > 1) ? pr * e[c] : pr;
-        PermWalk<C, K, DEPTH + 1>::run(e, used | (1u << c), child, acc, leaf);
+        PermWalk<C, K, DEPTH + 1>::run(e, rs, used | (1u << c), child, acc, leaf);
       }
     }
   }
 };
 
 // ------------------------------------------------------------------------------------------------
-// fast kernel: one thread per query, all K-permutations of C in registers; one warp per block
+// fast kernel: one thread per query, all K-permutations of C in registers.  Blocks of four independent warps
+// (one per SM sub-partition), three blocks per SM, persistent over 32-query tiles: an equal warp count on every
+// sub-partition matters because the loop is issue / MUFU bound.  Each warp streams its 32 queries' sample rows
+// (32*C contiguous floats per sample) through a private shared-memory ring filled by 1-D bulk copies (TMA)
+// kRing rows ahead, or by plain loads when the rows are not 16-byte aligned / the tile is ragged (STAGED = false).
 // ------------------------------------------------------------------------------------------------
-template <int C, int K>
-__global__ void __launch_bounds__(32)
+constexpr int kRing = 4;
+constexpr int kMpesWarps = 4;
+__host__ __device__ constexpr int mpes_warp_smem_bytes(int C, int P) {
+  return ((kRing * 32 * C * 4 + 2 * P * 32 * 4 + kRing * 8 + 127) / 128) * 128;
+}
+
+template <int C, int K, bool STAGED>
+__global__ void __launch_bounds__(32 * kMpesWarps, 3)
 mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ order, const int* __restrict__ group_start,
-                      int S, long long Q, int M, int mode, int tiles, double* __restrict__ out_mi) {
+                      int S, long long Q, int M, int mode, int tile_begin, int tile_end, double* __restrict__ out_mi) {
   constexpr int P = perm_count(C, K);
-  __shared__ float tot[P][32];
-  const int lane = threadIdx.x;
+  constexpr float kLog2e = 1.4426950408889634f;
+  // dynamic shared memory, one private slice per warp: ring | tot | ruz | mbarriers (see mpes_warp_smem_bytes)
+  extern __shared__ __align__(128) unsigned char mpes_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;                        // warps never synchronise with each other
+  unsigned char* slice = mpes_smem + static_cast<size_t>(wib) * mpes_warp_smem_bytes(C, P);
+  float (*ring)[32 * C] = reinterpret_cast<float (*)[32 * C]>(slice);
+  float (*tot)[32] = reinterpret_cast<float (*)[32]>(slice + kRing * 32 * C * 4);      // sum over groups of acc
+  float (*ruz)[32] = tot + P;                              // 1 / u_z, the reference distribution of the MI fold
+  uint64_t* full = reinterpret_cast<uint64_t*>(ruz + P);
+  const int warp_gid = blockIdx.x * kMpesWarps + wib;
+  const int warp_total = gridDim.x * kMpesWarps;
   const double invS = 1.0 / static_cast<double>(S);
   const double eps = (mode == TKBO_MPES_PES) ? kPesEps : 0.0;
+  const float epsf = static_cast<float>(eps);
   const long long rowstride = Q * C;
+  const int n_used = group_start[M];                       // samples with a valid group (all of them normally)
+  if constexpr (STAGED) {
+    if (lane == 0)
+      for (int i = 0; i < kRing; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+    __syncwarp();
+  }
+  uint32_t ring_phase = 0;                                 // bit i = parity to wait for on slot i
 
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (int tile = tile_begin + warp_gid; tile < tile_end; tile += warp_total) {
     const long long q = static_cast<long long>(tile) * 32 + lane;
     const bool valid = q < Q;
-    const float* base = fchi + (valid ? q : Q - 1) * C;
+    const float* base = fchi + (valid ? q : Q - 1) * C;                          // direct path
+    const float* tile_base = fchi + static_cast<long long>(tile) * 32 * C;       // staged path
 #pragma unroll
     for (int z = 0; z < P; ++z) tot[z][lane] = 0.f;
     float acc[P];
 #pragma unroll
     for (int z = 0; z < P; ++z) acc[z] = 0.f;
-    double mi = 0.0;
+    float t1 = 0.f;
+    bool have_ref = false;
 
-    for (int m = 0; m < M; ++m) {
-      const int lo = group_start[m], hi = group_start[m + 1];
-      if (hi == lo && mode == TKBO_MPES_RANK) continue;      // rank_pes.py:86-93 drops empty groups
-      // software prefetch: keep the next sample row in registers while working on the current one
-      float fnext[C];
-      if (lo < hi) {
-        const float* r = base + static_cast<long long>(order[lo]) * rowstride;
+    if constexpr (STAGED) {                                // prime the ring with the first kRing rows of this tile
+      if (lane == 0) {
+        for (int j = 0; j < kRing && j < n_used; ++j) {
+          mbar_arrive_expect_tx(&full[j], 32 * C * 4);
+          bulk_load_1d(ring[j], tile_base + static_cast<long long>(order[j]) * rowstride, 32 * C * 4, &full[j]);
+        }
+      }
+      __syncwarp();
+    }
+    float fnext[C];
+    if constexpr (!STAGED) {
+      if (n_used > 0) {
+        const float* r = base + static_cast<long long>(order[0]) * rowstride;
 #pragma unroll
         for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
       }
-      for (int i = lo; i < hi; ++i) {
+    }
+
+    int i = 0;                                             // position in the grouped sample order
+    for (int m = 0; m < M; ++m) {
+      const int hi = group_start[m + 1];
+      const int cnt = hi - group_start[m];
+      if (cnt == 0 && mode == TKBO_MPES_RANK) continue;    // rank_pes.py:86-93 drops empty groups
+      for (; i < hi; ++i) {
         float f[C];
+        if constexpr (STAGED) {
+          const int slot = i % kRing;
+          mbar_wait(&full[slot], (ring_phase >> slot) & 1u);
+          ring_phase ^= 1u << slot;
 #pragma unroll
-        for (int c = 0; c < C; ++c) f[c] = fnext[c];
-        if (i + 1 < hi) {
-          const float* r = base + static_cast<long long>(order[i + 1]) * rowstride;
+          for (int c = 0; c < C; ++c) f[c] = ring[slot][lane * C + c];
+        } else {
 #pragma unroll
-          for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
+          for (int c = 0; c < C; ++c) f[c] = fnext[c];
+          if (i + 1 < n_used) {
+            const float* r = base + static_cast<long long>(order[i + 1]) * rowstride;
+#pragma unroll
+            for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
+          }
         }
         float mx = f[0];
 #pragma unroll
         for (int c = 1; c < C; ++c) mx = fmaxf(mx, f[c]);
+        const float mxs = mx * kLog2e;
         float e[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) e[c] = __expf(f[c] - mx);
+        for (int c = 0; c < C; ++c) e[c] = fast_ex2(fmaf(f[c], kLog2e, -mxs));
+        if constexpr (STAGED) {
+          __syncwarp();                                    // every lane has consumed its slot values
+          if (lane == 0 && i + kRing < n_used) {
+            const int slot = i % kRing;
+            mbar_arrive_expect_tx(&full[slot], 32 * C * 4);
+            bulk_load_1d(ring[slot], tile_base + static_cast<long long>(order[i + kRing]) * rowstride, 32 * C * 4, &full[slot]);
+          }
+        }
+        float rs[1 << C];
+        subset_reciprocals<C, K>(e, rs);
         int leaf = 0;
-        PermWalk<C, K, 0>::run(e, 0u, 1.f, acc, leaf);
+        PermWalk<C, K, 0>::run(e, rs, 0u, 1.f, acc, leaf);
       }
-      // fold group m
+      // fold group m.  MI = sum_{m,z} p_m c_{zm} log(c_{zm} / p_z), c_{zm} = p(z | m).  Written against a fixed
+      // reference distribution u_z (= c_{z,m0} of the first folded group):
+      //   MI = sum_m p_m sum_z c_{zm} log(c_{zm} / u_z)  -  sum_z p_z log(p_z / u_z)
+      // both sums are small KL-type quantities whose log arguments sit near 1, so float32 logf is accurate to
+      // ~1e-8 absolute and nothing of the size of the entropies (~log P) is ever subtracted.
       const double pm = (mode == TKBO_MPES_PES)
-                            ? (static_cast<double>(hi - lo) + kPesEps) / (static_cast<double>(S) + M * kPesEps)
-                            : static_cast<double>(hi - lo) * invS;
-      const double log_pm = log(pm);
+                            ? (static_cast<double>(cnt) + kPesEps) / (static_cast<double>(S) + M * kPesEps)
+                            : static_cast<double>(cnt) * invS;
+      const float cm = static_cast<float>(invS / pm);              // (acc + eps) * cm = p(z | m)
+      const float pmf = static_cast<float>(pm);
+      if (!have_ref) {
+#pragma unroll
+        for (int z = 0; z < P; ++z) ruz[z][lane] = 1.f / fmaxf((acc[z] + epsf) * cm, 1e-30f);
+        have_ref = true;
+      }
+      float tg = 0.f;
 #pragma unroll
       for (int z = 0; z < P; ++z) {
-        const double J = (static_cast<double>(acc[z]) + eps) * invS;
-        if (J > 0.0) mi += J * (log(J) - log_pm);
+        const float c = (acc[z] + epsf) * cm;
+        if (c > 0.f) tg = fmaf(c, logf(c * ruz[z][lane]), tg);
         tot[z][lane] += acc[z];
         acc[z] = 0.f;
       }
+      t1 = fmaf(pmf, tg, t1);
     }
+    float t2 = 0.f;
+    const float meps = static_cast<float>(M * eps);
+    const float invSf = static_cast<float>(invS);
 #pragma unroll
     for (int z = 0; z < P; ++z) {
-      const double pz = (static_cast<double>(tot[z][lane]) + M * eps) * invS;
-      if (pz > 0.0) mi -= pz * log(pz);
+      const float pz = (tot[z][lane] + meps) * invSf;
+      if (pz > 0.f) t2 = fmaf(pz, logf(pz * ruz[z][lane]), t2);
     }
-    if (valid) out_mi[q] = mi;
+    if (valid) out_mi[q] = static_cast<double>(t1) - static_cast<double>(t2);
   }
 }
 
@@ -310,11 +412,24 @@ template <int C, int K>
 static void launch_all_perms(const float* fchi, const int* order, const int* gs, int S, int64_t Q, int M, int mode,
                              int sm_count, double* out, cudaStream_t stream) {
   const int64_t tiles = (Q + 31) / 32;
-  // equal number of tiles per resident warp: rounds = ceil(tiles / (SMs * 16)), grid = ceil(tiles / rounds)
-  const int64_t wmax = static_cast<int64_t>(sm_count) * 16;
-  const int64_t rounds = (tiles + wmax - 1) / wmax;
-  const int grid = static_cast<int>((tiles + rounds - 1) / rounds);
-  mpes_all_perms_kernel<C, K><<<grid, 32, 0, stream>>>(fchi, order, gs, S, Q, M, mode, static_cast<int>(tiles), out);
+  // the bulk-copy path needs 16-byte aligned rows (Q*C % 4 == 0, base aligned) and full 32-query tiles
+  const bool aligned = ((Q * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(fchi) & 15) == 0);
+  const int64_t staged_tiles = aligned ? Q / 32 : 0;
+  const int threads = 32 * kMpesWarps;
+  const int smem = kMpesWarps * mpes_warp_smem_bytes(C, perm_count(C, K));
+  cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (staged_tiles > 0) {
+    const int grid = static_cast<int>(std::min<int64_t>(3 * sm_count, (staged_tiles + kMpesWarps - 1) / kMpesWarps));
+    mpes_all_perms_kernel<C, K, true><<<grid, threads, smem, stream>>>(fchi, order, gs, S, Q, M, mode, 0,
+                                                                   static_cast<int>(staged_tiles), out);
+  }
+  if (staged_tiles < tiles) {
+    const int64_t rest = tiles - staged_tiles;
+    const int grid = static_cast<int>(std::min<int64_t>(3 * sm_count, (rest + kMpesWarps - 1) / kMpesWarps));
+    mpes_all_perms_kernel<C, K, false><<<grid, threads, smem, stream>>>(fchi, order, gs, S, Q, M, mode,
+                                                                    static_cast<int>(staged_tiles), static_cast<int>(tiles), out);
+  }
 }
 
 static bool dispatch_all_perms(int C, int K, const float* fchi, const int* order, const int* gs, int S, int64_t Q, int M,
