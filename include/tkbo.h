@@ -69,6 +69,12 @@ int tkbo_rff_argmax(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t
  * acquisitions/dts.py:85 / the f-samples consumed by tkbo_mpes_topk. */
 int tkbo_rff_eval(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, float* out_F,
                   int64_t ldf, void* stream);
+/* Same as tkbo_rff_argmax but returns one signed 64-bit key per sample whose integer maximum is "largest value, then
+ * lowest global index" (idx_offset + N < 2^32): ranks holding candidate shards merge with ONE all-reduce(MAX) over
+ * int64 (NCCL), then tkbo_unpack_argmax_key recovers (value, index).  An empty / all-NaN sample has key INT64_MIN. */
+int tkbo_rff_argmax_key(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, int64_t idx_offset,
+                        int64_t* out_key, void* stream);
+int tkbo_unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, void* stream);
 /* Per-rank partial results [G, S] (e.g. after an all-gather) -> global (value, lowest index). */
 int tkbo_merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, int G, int S,
                       float* out_val, int64_t* out_idx, void* stream);

@@ -149,6 +149,30 @@ def test_rff_sharded_equals_single(pbo):
     assert torch.equal(ov, val) and torch.equal(oi, idx)
 
 
+def test_rff_argmax_key_form_and_merge(pbo):
+    """The int64 merge-key output: max over shard keys == the single-call (value, lowest index), including an exact
+    cross-shard tie (duplicated candidates) and an empty shard."""
+    rng = np.random.default_rng(17)
+    X, W, b, Theta = _basis_inputs(rng, 6000, 128, 2, 40, -1.5, 1.5, 0.6)
+    X = np.concatenate([X, X[:3000]], axis=0)              # rows 6000.. duplicate rows 0..2999 -> exact ties
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    val, idx = basis.argmax(X)
+    keys = []
+    for r in range(3):
+        lo, hi = pbo.distributed.shard_range(X.shape[0], r, 3)
+        keys.append(basis.argmax_key(X[lo:hi], idx_offset=lo))
+    keys.append(torch.full((40,), pbo.distributed.EMPTY_KEY, dtype=torch.int64, device="cuda:0"))
+    merged = torch.stack(keys).max(dim=0).values
+    v2, i2 = basis.unpack_key(merged)
+    assert torch.equal(v2, val) and torch.equal(i2, idx)
+    assert int(idx.max()) < 6000                           # ties resolved to the first copy
+    ve, ie = basis.unpack_key(keys[-1])
+    assert bool((ie == -1).all()) and bool(torch.isnan(ve).all())
+    # single-process call of the distributed helper (no process group): identity merge
+    v3, i3 = pbo.distributed.sharded_argmax_fast(basis, torch.from_numpy(X).cuda(), 0)
+    assert torch.equal(v3, val) and torch.equal(i3, idx)
+
+
 def test_rff_argmax_host_entry_point(pbo):
     """tkbo_rff_argmax_host: the pure C-ABI end-to-end call with host buffers (no torch memory involved)."""
     rng = np.random.default_rng(8)

@@ -19,6 +19,9 @@ int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg);
 int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, float* out_val,
                int64_t* out_idx, cudaStream_t stream);
 int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float* out_F, int64_t ldf, cudaStream_t stream);
+int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, int64_t* out_key,
+                   cudaStream_t stream);
+int unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, cudaStream_t stream);
 int merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, int G, int S, float* out_val, int64_t* out_idx,
                  cudaStream_t stream);
 int rff_eval_batched(tkbo_handle_t h, const double* X, const double* W, const double* b, const double* theta, int count,
@@ -146,6 +149,15 @@ int tkbo_rff_argmax(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t
                     int64_t* out_idx, void* stream) {
   TKBO_ENTER(h);
   return rff_argmax(h, basis, X, N, idx_offset, out_val, out_idx, as_stream(stream));
+}
+int tkbo_rff_argmax_key(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, int64_t idx_offset,
+                        int64_t* out_key, void* stream) {
+  TKBO_ENTER(h);
+  return rff_argmax_key(h, basis, X, N, idx_offset, out_key, as_stream(stream));
+}
+int tkbo_unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, void* stream) {
+  TKBO_ENTER(h);
+  return unpack_argmax_key(h, key, S, out_val, out_idx, as_stream(stream));
 }
 int tkbo_rff_eval(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, float* out_F, int64_t ldf, void* stream) {
   TKBO_ENTER(h);

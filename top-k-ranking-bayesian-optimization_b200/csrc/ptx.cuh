@@ -209,4 +209,27 @@ __host__ __device__ __forceinline__ unsigned long long pack_val_row(float v, uin
   return (static_cast<unsigned long long>(f32_orderable(v)) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - row);
 }
 
+// Cross-rank merge key: a SIGNED 64-bit integer whose maximum is "largest value, then lowest global index", so
+// one all-reduce(MAX) over int64 merges the per-rank results.  High word = orderable(value) with the top bit
+// flipped (signed order), low word = ~index (unsigned order inside equal high words).  Requires index < 2^32.
+constexpr long long kEmptyKey = static_cast<long long>(0x8000000000000000ull);
+__host__ __device__ __forceinline__ long long argmax_key(float v, uint32_t gidx) {
+  const uint32_t hi = f32_orderable(v) ^ 0x80000000u;
+  return static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | (0xFFFFFFFFu - gidx));
+}
+__host__ __device__ __forceinline__ void argmax_unkey(long long key, float* v, long long* gidx) {
+  if (key == kEmptyKey) {
+#ifdef __CUDA_ARCH__
+    *v = __int_as_float(0x7fc00000);
+#else
+    union { float f; uint32_t u; } c; c.u = 0x7fc00000u; *v = c.f;
+#endif
+    *gidx = -1;
+    return;
+  }
+  const unsigned long long u = static_cast<unsigned long long>(key);
+  *v = f32_from_orderable(static_cast<uint32_t>(u >> 32) ^ 0x80000000u);
+  *gidx = static_cast<long long>(0xFFFFFFFFu - static_cast<uint32_t>(u));
+}
+
 }  // namespace tkbo

@@ -384,7 +384,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   TKBO_REQUIRE(N >= 1 && N < (int64_t(1) << 32) - 256, "N must be in [1, 2^32 - 256)");
   p->X = X; p->Wpack = bs->Wpack; p->unscale = bs->unscale; p->packed = bs->packed;
   p->done_counter = h->done_counter;
-  p->out_val = nullptr; p->out_idx = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
+  p->out_val = nullptr; p->out_idx = nullptr; p->out_key = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
   p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
   p->n_slabs = bs->Dpad / kSlabK;
   const int64_t mt = (N + kTileM - 1) / kTileM;
@@ -407,6 +407,40 @@ int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int6
   p.idx_offset = idx_offset;
   TKBO_CUDA_CHECK(cudaMemsetAsync(bs->packed, 0, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long), stream));
   return dispatch_fused<0>(h, bs, p, grid, stream);
+}
+
+int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, int64_t* out_key,
+                   cudaStream_t stream) {
+  RffParams p;
+  int grid = 0;
+  int rc = fill_params(h, bs, X, N, &p, &grid);
+  if (rc != TKBO_OK) return rc;
+  TKBO_REQUIRE(out_key, "null output");
+  TKBO_REQUIRE(idx_offset >= 0 && idx_offset + N <= (int64_t(1) << 32) - 1, "global index must stay below 2^32 - 1 for the key form");
+  p.out_key = reinterpret_cast<long long*>(out_key);
+  p.idx_offset = idx_offset;
+  TKBO_CUDA_CHECK(cudaMemsetAsync(bs->packed, 0, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long), stream));
+  return dispatch_fused<0>(h, bs, p, grid, stream);
+}
+
+__global__ void unpack_key_kernel(const long long* __restrict__ key, int S, float* __restrict__ out_val,
+                                  long long* __restrict__ out_idx) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float v;
+  long long gi;
+  argmax_unkey(key[s], &v, &gi);
+  out_val[s] = v;
+  out_idx[s] = gi;
+}
+
+int unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, cudaStream_t stream) {
+  TKBO_REQUIRE(h && key && out_val && out_idx && S >= 1, "bad unpack arguments");
+  unpack_key_kernel<<<(S + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const long long*>(key), S, out_val,
+                                                        reinterpret_cast<long long*>(out_idx));
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
 }
 
 int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float* out_F, int64_t ldf,

@@ -35,6 +35,7 @@ struct RffParams {
   unsigned int* done_counter;  // last-CTA detection
   float* out_val;            // [S]
   long long* out_idx;        // [S]
+  long long* out_key;        // [S] or null: signed-orderable (value, ~global index) key instead of out_val/out_idx
   float* out_F;              // [S, ldf] (eval mode)
   long long ldf;
   long long idx_offset;
@@ -348,12 +349,15 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       __threadfence();
       for (int s = threadIdx.x; s < p.S; s += blockDim.x) {
         const unsigned long long pk = __ldcg(p.packed + s);
-        if (pk == 0ull) {                         // only NaNs seen for this sample
-          p.out_val[s] = __int_as_float(0x7fc00000);
-          p.out_idx[s] = -1;
+        const bool none = (pk == 0ull);           // only NaNs seen for this sample
+        const float v = none ? __int_as_float(0x7fc00000)
+                             : f32_from_orderable(static_cast<uint32_t>(pk >> 32)) * p.unscale[s];
+        const long long gi = none ? -1 : static_cast<long long>(0xFFFFFFFFu - static_cast<uint32_t>(pk)) + p.idx_offset;
+        if (p.out_key != nullptr) {
+          p.out_key[s] = none ? kEmptyKey : argmax_key(v, static_cast<uint32_t>(gi));
         } else {
-          p.out_val[s] = f32_from_orderable(static_cast<uint32_t>(pk >> 32)) * p.unscale[s];
-          p.out_idx[s] = static_cast<long long>(0xFFFFFFFFu - static_cast<uint32_t>(pk)) + p.idx_offset;
+          p.out_val[s] = v;
+          p.out_idx[s] = gi;
         }
       }
       if (threadIdx.x == 0) *p.done_counter = 0u;

@@ -51,6 +51,28 @@ def allgather_argmax(val, idx, group=None):
     return merge_pairs(vals, idxs)
 
 
+EMPTY_KEY = -(1 << 63)
+
+
+def allreduce_argmax(basis, key, group=None):
+    """Merge per-rank key vectors (SharedBasis.argmax_key) with ONE all_reduce(MAX) over int64 and unpack:
+    the whole exchange is 8*S bytes per rank, one NCCL launch + one unpack launch."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(key, op=dist.ReduceOp.MAX, group=group)
+    return basis.unpack_key(key)
+
+
+def sharded_argmax_fast(basis, X_local, idx_offset, group=None):
+    """K1 on this rank's shard (key output) + all_reduce(MAX).  Needs global indices < 2^32 - 1."""
+    import torch
+    if X_local.shape[0] == 0:
+        key = torch.full((basis.S,), EMPTY_KEY, dtype=torch.int64, device=basis.device)
+    else:
+        key = basis.argmax_key(X_local, idx_offset=idx_offset)
+    return allreduce_argmax(basis, key, group=group)
+
+
 def sharded_argmax(basis, X_local, idx_offset, group=None):
     """K1 on this rank's shard, then the all-gather merge.  ``basis`` is a fourier_features.SharedBasis holding
     the same (W, b, Theta) on every rank; X_local (N_local, d) are rows [idx_offset, idx_offset + N_local)."""

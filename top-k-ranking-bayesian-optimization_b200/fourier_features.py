@@ -306,6 +306,26 @@ class SharedBasis:
                                             nat.ptr(idx), nat.current_stream_ptr(self.device)), "tkbo_rff_argmax")
         return val, idx
 
+    def argmax_key(self, X, idx_offset=0):
+        """(S,) int64 CUDA tensor of merge keys: integer max == largest value then lowest global index, so shards
+        held by different ranks merge with a single all_reduce(MAX) (see distributed.allreduce_argmax)."""
+        torch = self._torch
+        X = self._candidates(X)
+        key = torch.empty(self.S, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().tkbo_rff_argmax_key(self._h, self._basis, nat.ptr(X), X.shape[0], int(idx_offset), nat.ptr(key),
+                                                nat.current_stream_ptr(self.device)), "tkbo_rff_argmax_key")
+        return key
+
+    def unpack_key(self, key):
+        """(val[S] float32, idx[S] int64) from merge keys (idx = -1 where no candidate was seen)."""
+        torch = self._torch
+        key = key.contiguous()
+        val = torch.empty(key.shape[0], dtype=torch.float32, device=self.device)
+        idx = torch.empty(key.shape[0], dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().tkbo_unpack_argmax_key(self._h, nat.ptr(key), key.shape[0], nat.ptr(val), nat.ptr(idx),
+                                                   nat.current_stream_ptr(self.device)), "tkbo_unpack_argmax_key")
+        return val, idx
+
     def eval(self, X, out=None):
         """(S, N) float32 CUDA tensor, F[s, n] = f_s(X[n])."""
         torch = self._torch
