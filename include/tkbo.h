@@ -133,6 +133,10 @@ int64_t tkbo_launch_count(tkbo_handle_t h);
 /* Describes the tiling chosen for a basis: fills cfg[0..7] = {S_chunk, n_chunks, n_slabs, stages,
  * accumulator buffers, d_template, smem_bytes, grid}. */
 int tkbo_rff_basis_config(tkbo_handle_t h, tkbo_basis_t basis, int64_t N, int32_t* cfg);
+/* Diagnostics: while `trace` (device, uint64 [TKBO_TRACE_EVENTS][cap]) is set, CTA 0 of every K1 launch logs
+ * clock64() at its pipeline events (rff_fused.cuh TraceEvent); pass NULL to switch it off. */
+#define TKBO_TRACE_EVENTS 14
+int tkbo_debug_set_trace(tkbo_handle_t h, uint64_t* trace, int cap);
 
 #ifdef __cplusplus
 }

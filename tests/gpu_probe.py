@@ -179,6 +179,10 @@ def batched_case():
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     print("device:", torch.cuda.get_device_name(0), "SMs:", L.tkbo_sm_count(H), flush=True)
+    if what == "k1time":
+        for (N, D, d, S) in [(1 << 20, 1024, 2, 64), (1 << 18, 4096, 6, 256)]:
+            ms, cs, tf = k1_timing(N, D, d, S)
+            print(f"K1 timing N={N} D={D} d={d} S={S}: {ms:.3f} ms  {cs:.3e} cand*samples/s  {tf:.1f} TFLOP/s(alg)", flush=True)
     if what in ("k1", "all"):
         for (N, D, d, S) in [(128, 64, 2, 32), (256, 128, 2, 64), (1000, 200, 1, 20), (5000, 1000, 6, 96),
                              (4096, 256, 4, 256), (3000, 192, 3, 300), (2048, 128, 12, 512)]:

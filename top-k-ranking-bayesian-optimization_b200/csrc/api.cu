@@ -127,6 +127,12 @@ int tkbo_destroy(tkbo_handle_t h) {
 
 int tkbo_sm_count(tkbo_handle_t h) { return h ? h->sm_count : TKBO_ERR_INVALID; }
 int64_t tkbo_launch_count(tkbo_handle_t h) { return h ? h->launches : TKBO_ERR_INVALID; }
+int tkbo_debug_set_trace(tkbo_handle_t h, uint64_t* trace, int cap) {
+  if (!h || cap < 0) return TKBO_ERR_INVALID;
+  h->trace = reinterpret_cast<unsigned long long*>(trace);
+  h->trace_cap = trace ? cap : 0;
+  return TKBO_OK;
+}
 
 int tkbo_rff_basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
   TKBO_ENTER(h);

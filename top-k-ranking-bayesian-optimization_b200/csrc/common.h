@@ -41,6 +41,9 @@ struct tkbo_handle_s {
   // scratch for the MPES kernel (grown on demand)
   void* mpes_scratch = nullptr;
   size_t mpes_scratch_bytes = 0;
+  // optional K1 pipeline trace target (tkbo_debug_set_trace); caller-owned device memory
+  unsigned long long* trace = nullptr;
+  int trace_cap = 0;
 };
 
 struct tkbo_basis_s {
@@ -53,6 +56,8 @@ struct tkbo_basis_s {
   int Salloc = 0;    // n_chunks * SC
   int stages = 0;
   int acc_bufs = 0;
+  int tiles = 1;     // candidate tiles per work item (1 or 2)
+  int npg = 2;       // producer warp groups (2 or 3)
   int smem_bytes = 0;
   float* Wpack = nullptr;            // [Dpad, WS]
   __half* theta_hi = nullptr;        // [Salloc, Dpad]

@@ -4,6 +4,8 @@
 #include <cuda_fp16.h>
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -294,11 +296,27 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
   bs->Salloc = bs->n_chunks * bs->SC;
   const int stride = stage_stride_bytes(bs->SC, bs->WS);
   const int smem_limit = h->max_smem_optin - 2048;      // static barriers + 1024-byte alignment slack
+  // TILES = 2 (two candidate tiles share every W|b read and every Theta slab) when the tensor pipe is not the
+  // bound, i.e. small sample chunks; TKBO_TILES=1|2 overrides for experiments.
+  bs->tiles = (bs->SC <= 64) ? 2 : 1;
+  if (const char* env = getenv("TKBO_TILES")) {
+    const int t = atoi(env);
+    if (t == 1 || (t == 2 && bs->SC <= 128)) bs->tiles = t;
+  }
+  bs->npg = 2;
+  if (const char* env = getenv("TKBO_NPG")) {
+    const int t = atoi(env);
+    if (t == 2 || t == 3) bs->npg = t;
+  }
   bs->stages = 0;
   for (int ab = 2; ab >= 1 && bs->stages == 0; --ab) {
-    int ns = std::min(kMaxStages, (kTmemCols - ab * bs->SC) / kSlabK);
+    int ns = std::min(kMaxStages, (kTmemCols - ab * bs->tiles * bs->SC) / (bs->tiles * kSlabK));
     ns = std::min(ns, smem_limit / stride);
-    if (ns >= (ab == 2 ? 3 : 2)) { bs->stages = ns; bs->acc_bufs = ab; }
+    if (ns >= (ab == 2 ? 3 : 2) && ns >= bs->npg) { bs->stages = ns; bs->acc_bufs = ab; }
+  }
+  if (const char* env = getenv("TKBO_STAGES")) {
+    const int t = atoi(env);
+    if (t >= bs->npg && t <= bs->stages) bs->stages = t;
   }
   if (bs->stages == 0) {
     delete bs;
@@ -352,14 +370,25 @@ int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b
   return TKBO_OK;
 }
 
-template <int DT, int MODE>
-static int launch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
-  auto kern = rff_fused_kernel<DT, MODE>;
+template <int DT, int MODE, int TILES, int NPG>
+static int launch_fused_tn(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  auto kern = rff_fused_kernel<DT, MODE, TILES, NPG>;
   TKBO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs->smem_bytes));
-  kern<<<grid, kNumThreads, bs->smem_bytes, stream>>>(bs->tm_hi, bs->tm_lo, p);
+  kern<<<grid, kNumThreadsFor(NPG), bs->smem_bytes, stream>>>(bs->tm_hi, bs->tm_lo, p);
   h->launches += 1;
   TKBO_CUDA_CHECK(cudaGetLastError());
   return TKBO_OK;
+}
+
+template <int DT, int MODE, int TILES>
+static int launch_fused_t(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  return bs->npg == 3 ? launch_fused_tn<DT, MODE, TILES, 3>(h, bs, p, grid, stream)
+                      : launch_fused_tn<DT, MODE, TILES, 2>(h, bs, p, grid, stream);
+}
+
+template <int DT, int MODE>
+static int launch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  return bs->tiles == 2 ? launch_fused_t<DT, MODE, 2>(h, bs, p, grid, stream) : launch_fused_t<DT, MODE, 1>(h, bs, p, grid, stream);
 }
 
 template <int MODE>
@@ -391,7 +420,10 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   TKBO_REQUIRE(mt * bs->n_chunks < (int64_t(1) << 31), "too many work items");
   p->n_mtiles = static_cast<int>(mt);
   p->stages = bs->stages; p->acc_bufs = bs->acc_bufs;
-  *grid = static_cast<int>(std::min<int64_t>(h->sm_count, mt * bs->n_chunks));
+  p->debug = 0;
+  if (const char* env = getenv("TKBO_DEBUG")) p->debug = atoi(env);
+  p->trace = h->trace; p->trace_cap = h->trace_cap;
+  *grid = static_cast<int>(std::min<int64_t>(h->sm_count, ((mt + bs->tiles - 1) / bs->tiles) * bs->n_chunks));
   return TKBO_OK;
 }
 
@@ -460,7 +492,8 @@ int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg) {
   const int64_t mt = (N + kTileM - 1) / kTileM;
   cfg[0] = bs->SC; cfg[1] = bs->n_chunks; cfg[2] = bs->Dpad / kSlabK; cfg[3] = bs->stages; cfg[4] = bs->acc_bufs;
   cfg[5] = bs->DT; cfg[6] = bs->smem_bytes;
-  cfg[7] = static_cast<int32_t>(std::min<int64_t>(h->sm_count, std::max<int64_t>(1, mt) * bs->n_chunks));
+  cfg[7] = static_cast<int32_t>(std::min<int64_t>(h->sm_count, ((std::max<int64_t>(1, mt) + bs->tiles - 1) / bs->tiles) * bs->n_chunks));
+  cfg[5] = bs->DT * 100 + bs->tiles;              // d_template * 100 + tiles per work item
   return TKBO_OK;
 }
 

@@ -289,7 +289,10 @@ class SharedBasis:
         cfg = (ctypes.c_int32 * 8)()
         nat.check(nat.lib().tkbo_rff_basis_config(self._h, self._basis, int(N), cfg), "tkbo_rff_basis_config")
         keys = ["S_chunk", "n_chunks", "n_slabs", "stages", "acc_bufs", "d_template", "smem_bytes", "grid"]
-        return dict(zip(keys, list(cfg)))
+        out = dict(zip(keys, list(cfg)))
+        out["tiles_per_item"] = out["d_template"] % 100
+        out["d_template"] //= 100
+        return out
 
     def _candidates(self, X):
         X = _f32(X, self.device)
