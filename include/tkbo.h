@@ -130,12 +130,13 @@ int tkbo_soft_copeland(tkbo_handle_t h, const float* f, int n, float* out_score,
 /* ---- introspection used by bench.py / tests --------------------------------------------------------
  * Number of kernel launches issued through this handle since creation. */
 int64_t tkbo_launch_count(tkbo_handle_t h);
-/* Describes the tiling chosen for a basis: fills cfg[0..7] = {S_chunk, n_chunks, n_slabs, stages,
- * accumulator buffers, d_template, smem_bytes, grid}. */
+/* Describes the tiling chosen for a basis: fills cfg[0..12] = {S_chunk, n_chunks, n_slabs, smem stages,
+ * accumulator buffers, d_template, smem_bytes, grid, TMEM ring slots, threads per CTA, candidate-row
+ * buffers, producer warp groups, projection-issuing warps}; cfg must have room for 16 int32. */
 int tkbo_rff_basis_config(tkbo_handle_t h, tkbo_basis_t basis, int64_t N, int32_t* cfg);
 /* Diagnostics: while `trace` (device, uint64 [TKBO_TRACE_EVENTS][cap]) is set, CTA 0 of every K1 launch logs
  * clock64() at its pipeline events (rff_fused.cuh TraceEvent); pass NULL to switch it off. */
-#define TKBO_TRACE_EVENTS 14
+#define TKBO_TRACE_EVENTS 15
 int tkbo_debug_set_trace(tkbo_handle_t h, uint64_t* trace, int cap);
 
 #ifdef __cplusplus

@@ -34,7 +34,7 @@ def k1_case(N, D, d, S, seed=0, ls=0.5, lo=-1.0, hi=1.0, check_eval=True):
     Theta = rng.standard_normal((D, S)) * rng.uniform(0.1, 3.0, size=(1, S))
     basis = ctypes.c_void_p()
     nat.check(L.tkbo_rff_basis_create(H, ctypes.byref(basis), D, d, S), "basis_create")
-    cfg = (ctypes.c_int32 * 8)()
+    cfg = (ctypes.c_int32 * 16)()
     L.tkbo_rff_basis_config(H, basis, N, cfg)
     tW, tb, tT = (torch.from_numpy(a).to(dev) for a in (W, b, Theta))
     tX = torch.from_numpy(X).to(dev)
@@ -65,7 +65,7 @@ def k1_case(N, D, d, S, seed=0, ls=0.5, lo=-1.0, hi=1.0, check_eval=True):
     gap = np.where(ok_idx, (ref_val - Fref[np.clip(got_idx, 0, N - 1), np.arange(S)]) / scale, np.inf)
     out["idx_mismatch"] = int(mism.sum())
     out["idx_bad"] = int((mism & (gap > 1e-4)).sum())
-    out["cfg"] = list(cfg)
+    out["cfg"] = list(cfg)[:13]
     nat.check(L.tkbo_rff_basis_destroy(H, basis), "basis_destroy")
     return out
 

@@ -14,11 +14,12 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("TKBO_LIB", os.path.join(ROOT, "top-k-ranking-bayesian-optimization_b200", "libtkbo_trace.so"))
 pkg = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
 nat = pkg._native
 
-EV = ["tma_empty", "tma_issued", "p0_bfull", "p0_arrived", "p1_bfull", "p1_arrived", "p2_bfull", "p2_arrived",
-      "mma_bfull", "mma_afull", "mma_committed", "epi_accfull", "epi_done", "mma_accempty"]
+EV = ["tma_empty", "tma_issued", "p0_pfull", "p0_arrived", "p1_pfull", "p1_arrived", "p2_pfull", "p2_arrived",
+      "mma_proj", "mma_afull", "mma_committed", "epi_accfull", "epi_done", "mma_accempty", "mma_proj_issued"]
 
 
 def main():
@@ -47,39 +48,44 @@ def main():
     t = trace.cpu().numpy().astype(np.int64)
     t0 = t[t > 0].min()
     npg = 3 if t[6].any() else 2
-    n_it = int((t[8] > 0).sum())
+    n_it = int((t[10] > 0).sum())
     n_items = int((t[11] > 0).sum())
     total = t.max() - t0
     print(f"CTA 0: {n_it} slab iterations, {n_items} items, {total} cycles total, {total / max(n_it, 1):.0f} cycles/slab")
     rel = lambda v: int(v - t0) if v > 0 else -1
-    print(f"{'it':>5} {'tma_empty':>10} {'tma_iss':>8} {'prod_bfull':>10} {'prod_arr':>9} {'prod_dur':>8} {'mma_bfull':>10} "
+    print(f"{'it':>5} {'tma_empty':>10} {'tma_iss':>8} {'mma_proj':>9} {'prod_pfull':>10} {'prod_arr':>9} {'prod_dur':>8} "
           f"{'mma_afull':>10} {'mma_commit':>10} {'d_commit':>8}")
     for it in range(first, min(first + count, n_it)):
         g, k = it % npg, it // npg
         pb, pa = t[2 + 2 * g][k], t[3 + 2 * g][k]
         dc = t[10][it] - t[10][it - 1] if it > 0 else 0
-        print(f"{it:>5} {rel(t[0][it]):>10} {rel(t[1][it]):>8} {rel(pb):>10} {rel(pa):>9} {int(pa - pb):>8} {rel(t[8][it]):>10} "
+        print(f"{it:>5} {rel(t[0][it]):>10} {rel(t[1][it]):>8} {rel(t[8][it]):>9} {rel(pb):>10} {rel(pa):>9} {int(pa - pb):>8} "
               f"{rel(t[9][it]):>10} {rel(t[10][it]):>10} {int(dc):>8}")
     print("items: epi_accfull, epi_done (dur), mma_accempty")
     for i in range(min(n_items, 6)):
         print(f"{i:>5} {rel(t[11][i]):>10} {rel(t[12][i]):>10} ({int(t[12][i] - t[11][i])}) {rel(t[13][i]):>10}")
-    # aggregate: where does the MMA warp wait?
-    wait_b = (t[8][1:n_it] - t[10][:n_it - 1]).clip(min=0)
-    wait_a = t[9][:n_it] - t[8][:n_it]
+    ii = np.arange(1, n_it)
+    print(f"proj warp per slab: waits {(t[8][ii] - t[14][ii - 1]).mean():.0f} | issue {(t[14][ii] - t[8][ii]).mean():.0f};  "
+          f"main warp per slab: waits {(t[9][ii] - t[10][ii - 1]).mean():.0f} | issue {(t[10][ii] - t[9][ii]).mean():.0f}")
+    print(f"proj runs ahead of main by {(t[9][ii] - t[14][ii]).mean():.0f} cycles")
+    wait_a = (t[9][1:n_it] - t[10][:n_it - 1]).clip(min=0)
     issue = t[10][:n_it] - t[9][:n_it]
-    print(f"MMA warp per slab: wait b_full {wait_b.mean():.0f}, then a_full {wait_a.mean():.0f}, issue+commit {issue.mean():.0f}")
+    print(f"MMA warp per slab: from previous commit to a_full seen (projection issue + waiting) {wait_a.mean():.0f}, "
+          f"main issue+commit {issue.mean():.0f}")
     for g in range(npg):
-        k = int((t[2 + 2 * g] > 0).sum())
+        k = int((t[3 + 2 * g] > 0).sum())
         dur = t[3 + 2 * g][:k] - t[2 + 2 * g][:k]
         gap = t[2 + 2 * g][1:k] - t[3 + 2 * g][:k - 1]
-        print(f"producer group {g}: {k} slabs, busy {dur.mean():.0f} cycles/slab, waiting for b_full {gap.mean():.0f}")
+        print(f"producer group {g}: {k} slabs, busy {dur.mean():.0f} cycles/slab, waiting for p_full {gap.mean():.0f}")
     k = n_it
-    print(f"TMA warp per slab: wait empty {(t[0][1:k] - t[1][:k - 1]).mean():.0f}, issue {(t[1][:k] - t[0][:k]).mean():.0f}")
+    print(f"TMA warp per slab: wait b_empty {(t[0][1:k] - t[1][:k - 1]).mean():.0f}, issue {(t[1][:k] - t[0][:k]).mean():.0f}")
     lat = []
     for it in range(k):
         g, kk = it % npg, it // npg
-        lat.append(t[2 + 2 * g][kk] - t[1][it])
-    print(f"TMA issue -> producer sees b_full: mean {np.mean(lat):.0f}, min {np.min(lat)}, max {np.max(lat)}")
+        lat.append(t[2 + 2 * g][kk] - t[8][it])
+    print(f"projection issue -> producer sees p_full: mean {np.mean(lat):.0f}, min {np.min(lat)}, max {np.max(lat)}")
+    lat2 = [t[9][it] - t[3 + 2 * (it % npg)][it // npg] for it in range(k)]
+    print(f"producer arrival -> MMA warp sees a_full: mean {np.mean(lat2):.0f}, min {np.min(lat2)}, max {np.max(lat2)}")
 
 
 if __name__ == "__main__":

@@ -12,7 +12,8 @@ import re
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtkbo.so")
+# TKBO_LIB selects another build of the same library (tools/trace_k1.py uses libtkbo_trace.so, compiled with -DTKBO_TRACE)
+LIB_PATH = os.environ.get("TKBO_LIB") or os.path.join(_HERE, "libtkbo.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "tkbo.h")
 
 MPES_RANK, MPES_PES = 0, 1

@@ -50,9 +50,9 @@ def _digest():
     return h.hexdigest()
 
 
-def _compile_one(nvcc, src):
-    obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
-    cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+def _compile_one(nvcc, src, extra=(), suffix=""):
+    obj = os.path.join(BUILD, os.path.basename(src)[:-3] + suffix + ".o")
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + ".log", "w") as fh:
@@ -84,5 +84,20 @@ def build(force=False, verbose=True):
     return LIB
 
 
+def build_trace():
+    """libtkbo_trace.so: the same library with the K1 pipeline trace compiled in (-DTKBO_TRACE); diagnostics only."""
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = nvcc_path()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(lambda s: _compile_one(nvcc, s, ("-DTKBO_TRACE",), "_trace"), sources()))
+    out = os.path.join(HERE, "libtkbo_trace.so")
+    r = subprocess.run([nvcc, "-shared", "-o", out, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    if "--trace" in sys.argv:
+        print(build_trace())

@@ -49,21 +49,22 @@ struct tkbo_handle_s {
 struct tkbo_basis_s {
   int D = 0, d = 0, S = 0;
   int DT = 0;        // template input dimension (d padded up to a supported value)
-  int WS = 0;        // floats per feature row in Wpack
   int Dpad = 0;      // multiple of 64
   int SC = 0;        // samples per chunk
   int n_chunks = 0;
   int Salloc = 0;    // n_chunks * SC
-  int stages = 0;
+  int stages = 0;    // smem ring depth
+  int ring = 0;      // TMEM ring depth
   int acc_bufs = 0;
-  int tiles = 1;     // candidate tiles per work item (1 or 2)
+  int xa_bufs = 0;
+  int proj_warps = 1;
   int npg = 2;       // producer warp groups (2 or 3)
   int smem_bytes = 0;
-  float* Wpack = nullptr;            // [Dpad, WS]
+  uint16_t* Wproj = nullptr;         // [Dpad, proj_k_alloc(DT)] bf16 split (W | b) rows, K order of rff_fused.cuh
   __half* theta_hi = nullptr;        // [Salloc, Dpad]
   __half* theta_lo = nullptr;        // [Salloc, Dpad]
   float* unscale = nullptr;          // [Salloc]
-  unsigned long long* packed = nullptr;  // [Salloc]
-  CUtensorMap tm_hi, tm_lo;
+  unsigned long long* packed = nullptr;  // [Salloc], zero between launches
+  CUtensorMap tm_hi, tm_lo, tm_w;
   bool is_set = false;
 };

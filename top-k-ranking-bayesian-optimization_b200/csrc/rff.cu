@@ -66,19 +66,42 @@ __global__ void prep_theta_split_kernel(const double* __restrict__ Theta, int tr
   }
 }
 
-// Wpack[j] = (w_j[0..d-1], 0.., b_j at slot DT, 0..) as float32; padded features get w = 0, b = 0 (their
-// Theta rows are zero, so cos(0) = 1 contributes nothing).
-__global__ void prep_w_kernel(const double* __restrict__ W, const double* __restrict__ b, int D, int d, int Dpad,
-                              int DT, int WS, float* __restrict__ Wpack) {
-  const int total = Dpad * WS;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int j = i / WS, c = i % WS;
-    float v = 0.f;
-    if (j < D) {
-      if (c < d) v = static_cast<float>(W[static_cast<size_t>(j) * d + c]);
-      else if (c == DT) v = static_cast<float>(b[j]);
+// bf16(v) with round-to-nearest-even, as raw bits and as the double it represents.
+__device__ __forceinline__ uint16_t bf16_rn_bits(double v) {
+  const float f = static_cast<float>(v);
+  uint32_t u = __float_as_uint(f);
+  if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(u >> 16);      // inf / nan
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+__device__ __forceinline__ double bf16_bits_value(uint16_t h) {
+  return static_cast<double>(__uint_as_float(static_cast<uint32_t>(h) << 16));
+}
+
+// Wproj[j, :] = the K-row of feature j for the projection MMA (rff_fused.cuh): per input dimension i the six
+// entries  w1 w2 w1 w3 w2 w1  (w = w1 + w2 + w3 in bf16, paired with x1 x1 x2 x1 x2 x3), then b1 b2 b3 at
+// k = 6 DT .. 6 DT + 2 (paired with ones), zero padding.  Padded features get all zeros: cos(0) = 1 against
+// zero Theta rows.
+__global__ void prep_wproj_kernel(const double* __restrict__ W, const double* __restrict__ b, int D, int d, int Dpad,
+                                  int DT, int KA, uint16_t* __restrict__ Wproj) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Dpad) return;
+  uint16_t* row = Wproj + static_cast<size_t>(j) * KA;
+  for (int k = 0; k < KA; ++k) row[k] = 0;
+  if (j >= D) return;
+  for (int i = 0; i <= d; ++i) {                    // i == d: the phase b_j
+    const double w = (i < d) ? W[static_cast<size_t>(j) * d + i] : b[j];
+    const uint16_t w1 = bf16_rn_bits(w);
+    const double r1 = w - bf16_bits_value(w1);
+    const uint16_t w2 = bf16_rn_bits(r1);
+    const uint16_t w3 = bf16_rn_bits(r1 - bf16_bits_value(w2));
+    if (i < d) {
+      uint16_t* o = row + 6 * i;
+      o[0] = w1; o[1] = w2; o[2] = w1; o[3] = w3; o[4] = w2; o[5] = w1;
+    } else {
+      uint16_t* o = row + 6 * DT;
+      o[0] = w1; o[1] = w2; o[2] = w3;
     }
-    Wpack[i] = v;
   }
 }
 
@@ -257,8 +280,6 @@ static int pick_dt(int d) {
   return -1;
 }
 
-static int wstride_of(int DT) { return (DT == 1) ? 2 : ((DT + 1 + 3) / 4) * 4; }
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -279,6 +300,33 @@ static int make_theta_map(tkbo_handle_t h, CUtensorMap* map, __half* base, int S
   return TKBO_OK;
 }
 
+// (W | b) projection rows: [Dpad, KA] bf16, box = one slab (64 features) x one 64-wide (or narrower) K block,
+// swizzle span = the box row.
+static int make_wproj_map(tkbo_handle_t h, CUtensorMap* map, uint16_t* base, int Dpad, int DT) {
+  auto fn = reinterpret_cast<EncodeTiledFn>(h->encode_tiled);
+  const int KA = proj_k_alloc(DT);
+  const int row_bytes = proj_row_bytes(DT);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(KA), static_cast<cuuint64_t>(Dpad)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(KA) * sizeof(uint16_t)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(row_bytes / 2), static_cast<cuuint32_t>(kSlabK)};
+  cuuint32_t estride[2] = {1, 1};
+  const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (W) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return TKBO_ERR_CUDA;
+  }
+  return TKBO_OK;
+}
+
+static void free_basis(tkbo_basis_t bs) {
+  cudaFree(bs->Wproj); cudaFree(bs->theta_hi); cudaFree(bs->theta_lo); cudaFree(bs->unscale); cudaFree(bs->packed);
+  delete bs;
+}
+
 int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
   TKBO_REQUIRE(h && out, "null handle/out");
   TKBO_REQUIRE(D >= 1 && d >= 1 && S >= 1, "D, d, S must be >= 1");
@@ -288,59 +336,72 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
     return TKBO_ERR_UNSUPPORTED;
   }
   auto* bs = new tkbo_basis_s();
-  bs->D = D; bs->d = d; bs->S = S; bs->DT = DT; bs->WS = wstride_of(DT);
+  bs->D = D; bs->d = d; bs->S = S; bs->DT = DT;
   bs->Dpad = ((D + kSlabK - 1) / kSlabK) * kSlabK;
   const int S32 = ((S + 31) / 32) * 32;
-  bs->n_chunks = (S32 + 255) / 256;
-  bs->SC = ((((S32 + bs->n_chunks - 1) / bs->n_chunks) + 31) / 32) * 32;
-  bs->Salloc = bs->n_chunks * bs->SC;
-  const int stride = stage_stride_bytes(bs->SC, bs->WS);
   const int smem_limit = h->max_smem_optin - 2048;      // static barriers + 1024-byte alignment slack
-  // TILES = 2 (two candidate tiles share every W|b read and every Theta slab) when the tensor pipe is not the
-  // bound, i.e. small sample chunks; TKBO_TILES=1|2 overrides for experiments.
-  bs->tiles = (bs->SC <= 64) ? 2 : 1;
-  if (const char* env = getenv("TKBO_TILES")) {
-    const int t = atoi(env);
-    if (t == 1 || (t == 2 && bs->SC <= 128)) bs->tiles = t;
+  const int xa_cols = proj_k_alloc(DT) / 2;
+  // Sample chunk: as wide as possible (every chunk re-evaluates the features of its tile), narrowed until three
+  // smem stages fit.  TMEM budget: acc_bufs * SC accumulator columns + xa_bufs * xa_cols split-candidate columns +
+  // ring * 64; prefer double-buffered accumulators, then double-buffered candidate rows; the ring needs >= 3 slots
+  // (projection one slab ahead of the main MMAs plus one being consumed).
+  bs->ring = 0;
+  for (int nc = (S32 + 255) / 256; nc <= S32 / 32 && bs->ring == 0; ++nc) {
+    const int SC = ((((S32 + nc - 1) / nc) + 31) / 32) * 32;
+    const int stages = std::min(kMaxStages, smem_limit / stage_stride_bytes(SC, DT));
+    if (stages < 3) continue;
+    for (int ab = 2; ab >= 1 && bs->ring == 0; --ab)
+      for (int xb = 2; xb >= 1 && bs->ring == 0; --xb) {
+        const int ring = std::min(kMaxRing, (kTmemCols - ab * SC - xb * xa_cols) / kSlabK);
+        if (ring >= 3) {
+          bs->ring = ring; bs->acc_bufs = ab; bs->xa_bufs = xb; bs->stages = stages;
+          bs->SC = SC; bs->n_chunks = (S32 + SC - 1) / SC;
+        }
+      }
   }
-  bs->npg = 2;
-  if (const char* env = getenv("TKBO_NPG")) {
-    const int t = atoi(env);
-    if (t == 2 || t == 3) bs->npg = t;
-  }
-  bs->stages = 0;
-  for (int ab = 2; ab >= 1 && bs->stages == 0; --ab) {
-    int ns = std::min(kMaxStages, (kTmemCols - ab * bs->tiles * bs->SC) / (bs->tiles * kSlabK));
-    ns = std::min(ns, smem_limit / stride);
-    if (ns >= (ab == 2 ? 3 : 2) && ns >= bs->npg) { bs->stages = ns; bs->acc_bufs = ab; }
-  }
-  if (const char* env = getenv("TKBO_STAGES")) {
-    const int t = atoi(env);
-    if (t >= bs->npg && t <= bs->stages) bs->stages = t;
-  }
-  if (bs->stages == 0) {
+  if (bs->ring == 0) {
     delete bs;
     set_error("no feasible pipeline configuration for this (S, d)");
     return TKBO_ERR_UNSUPPORTED;
   }
+  bs->Salloc = bs->n_chunks * bs->SC;
+  const int stride = stage_stride_bytes(bs->SC, DT);
+  if (const char* env = getenv("TKBO_STAGES")) {
+    const int t = atoi(env);
+    if (t >= 3 && t <= bs->stages) bs->stages = t;
+  }
+  if (const char* env = getenv("TKBO_RING")) {
+    const int t = atoi(env);
+    if (t >= 3 && t <= bs->ring) bs->ring = t;
+  }
+  // two projection-issuing warps alternate slabs, which needs an even smem ring; the ring slots must not outnumber
+  // the smem stages (a slot is known free through its stage's b_empty barrier)
+  if (bs->stages % 2 == 1 && bs->stages >= 5) bs->stages -= 1;
+  bs->proj_warps = (bs->stages % 2 == 0) ? 2 : 1;
+  bs->ring = std::min(bs->ring, bs->stages);
+  bs->npg = bs->ring >= 5 ? 3 : 2;       // producer groups that can be busy at once: ring slots ahead of the main MMAs
+  if (const char* env = getenv("TKBO_NPG")) {
+    const int t = atoi(env);
+    if (t == 2 || t == 3) bs->npg = t;
+  }
   bs->smem_bytes = bs->stages * stride + 1024;
   cudaError_t e = cudaSuccess;
-  e = e ? e : cudaMalloc(&bs->Wpack, static_cast<size_t>(bs->Dpad) * bs->WS * sizeof(float));
+  e = e ? e : cudaMalloc(&bs->Wproj, static_cast<size_t>(bs->Dpad) * proj_k_alloc(DT) * sizeof(uint16_t));
   e = e ? e : cudaMalloc(&bs->theta_hi, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
   e = e ? e : cudaMalloc(&bs->theta_lo, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
   e = e ? e : cudaMalloc(&bs->unscale, static_cast<size_t>(bs->Salloc) * sizeof(float));
   e = e ? e : cudaMalloc(&bs->packed, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long));
+  e = e ? e : cudaMemset(bs->packed, 0, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     set_error(std::string("cudaMalloc (basis): ") + cudaGetErrorString(e));
-    cudaFree(bs->Wpack); cudaFree(bs->theta_hi); cudaFree(bs->theta_lo); cudaFree(bs->unscale); cudaFree(bs->packed);
-    delete bs;
+    free_basis(bs);
     return TKBO_ERR_NOMEM;
   }
   int rc = make_theta_map(h, &bs->tm_hi, bs->theta_hi, bs->Salloc, bs->Dpad, bs->SC);
   if (rc == TKBO_OK) rc = make_theta_map(h, &bs->tm_lo, bs->theta_lo, bs->Salloc, bs->Dpad, bs->SC);
+  if (rc == TKBO_OK) rc = make_wproj_map(h, &bs->tm_w, bs->Wproj, bs->Dpad, DT);
   if (rc != TKBO_OK) {
-    cudaFree(bs->Wpack); cudaFree(bs->theta_hi); cudaFree(bs->theta_lo); cudaFree(bs->unscale); cudaFree(bs->packed);
-    delete bs;
+    free_basis(bs);
     return rc;
   }
   *out = bs;
@@ -349,8 +410,7 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
 
 int basis_destroy(tkbo_handle_t, tkbo_basis_t bs) {
   if (!bs) return TKBO_OK;
-  cudaFree(bs->Wpack); cudaFree(bs->theta_hi); cudaFree(bs->theta_lo); cudaFree(bs->unscale); cudaFree(bs->packed);
-  delete bs;
+  free_basis(bs);
   return TKBO_OK;
 }
 
@@ -362,33 +422,28 @@ int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
   prep_theta_split_kernel<<<blocks, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Dpad, bs->Salloc,
                                                      bs->unscale, bs->theta_hi, bs->theta_lo);
-  prep_w_kernel<<<(bs->Dpad * bs->WS + 255) / 256, 256, 0, stream>>>(W, b, bs->D, bs->d, bs->Dpad, bs->DT, bs->WS,
-                                                                    bs->Wpack);
+  prep_wproj_kernel<<<(bs->Dpad + 127) / 128, 128, 0, stream>>>(W, b, bs->D, bs->d, bs->Dpad, bs->DT,
+                                                                proj_k_alloc(bs->DT), bs->Wproj);
   h->launches += 3;
   TKBO_CUDA_CHECK(cudaGetLastError());
   bs->is_set = true;
   return TKBO_OK;
 }
 
-template <int DT, int MODE, int TILES, int NPG>
-static int launch_fused_tn(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
-  auto kern = rff_fused_kernel<DT, MODE, TILES, NPG>;
+template <int DT, int MODE, int NPG>
+static int launch_fused_n(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  auto kern = rff_fused_kernel<DT, MODE, NPG>;
   TKBO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs->smem_bytes));
-  kern<<<grid, kNumThreadsFor(NPG), bs->smem_bytes, stream>>>(bs->tm_hi, bs->tm_lo, p);
+  kern<<<grid, kNumThreadsFor(NPG), bs->smem_bytes, stream>>>(bs->tm_hi, bs->tm_lo, bs->tm_w, p);
   h->launches += 1;
   TKBO_CUDA_CHECK(cudaGetLastError());
   return TKBO_OK;
 }
 
-template <int DT, int MODE, int TILES>
-static int launch_fused_t(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
-  return bs->npg == 3 ? launch_fused_tn<DT, MODE, TILES, 3>(h, bs, p, grid, stream)
-                      : launch_fused_tn<DT, MODE, TILES, 2>(h, bs, p, grid, stream);
-}
-
 template <int DT, int MODE>
 static int launch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
-  return bs->tiles == 2 ? launch_fused_t<DT, MODE, 2>(h, bs, p, grid, stream) : launch_fused_t<DT, MODE, 1>(h, bs, p, grid, stream);
+  return bs->npg == 3 ? launch_fused_n<DT, MODE, 3>(h, bs, p, grid, stream)
+                      : launch_fused_n<DT, MODE, 2>(h, bs, p, grid, stream);
 }
 
 template <int MODE>
@@ -411,7 +466,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   TKBO_REQUIRE(h && bs && X, "null pointer");
   TKBO_REQUIRE(bs->is_set, "basis has no data: call tkbo_rff_basis_set first");
   TKBO_REQUIRE(N >= 1 && N < (int64_t(1) << 32) - 256, "N must be in [1, 2^32 - 256)");
-  p->X = X; p->Wpack = bs->Wpack; p->unscale = bs->unscale; p->packed = bs->packed;
+  p->X = X; p->unscale = bs->unscale; p->packed = bs->packed;
   p->done_counter = h->done_counter;
   p->out_val = nullptr; p->out_idx = nullptr; p->out_key = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
   p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
@@ -419,11 +474,12 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   const int64_t mt = (N + kTileM - 1) / kTileM;
   TKBO_REQUIRE(mt * bs->n_chunks < (int64_t(1) << 31), "too many work items");
   p->n_mtiles = static_cast<int>(mt);
-  p->stages = bs->stages; p->acc_bufs = bs->acc_bufs;
+  p->stages = bs->stages; p->ring = bs->ring; p->acc_bufs = bs->acc_bufs; p->xa_bufs = bs->xa_bufs;
+  p->proj_warps = bs->proj_warps;
   p->debug = 0;
   if (const char* env = getenv("TKBO_DEBUG")) p->debug = atoi(env);
   p->trace = h->trace; p->trace_cap = h->trace_cap;
-  *grid = static_cast<int>(std::min<int64_t>(h->sm_count, ((mt + bs->tiles - 1) / bs->tiles) * bs->n_chunks));
+  *grid = static_cast<int>(std::min<int64_t>(h->sm_count, mt * bs->n_chunks));
   return TKBO_OK;
 }
 
@@ -437,7 +493,6 @@ int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int6
   p.out_val = out_val;
   p.out_idx = reinterpret_cast<long long*>(out_idx);
   p.idx_offset = idx_offset;
-  TKBO_CUDA_CHECK(cudaMemsetAsync(bs->packed, 0, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long), stream));
   return dispatch_fused<0>(h, bs, p, grid, stream);
 }
 
@@ -451,7 +506,6 @@ int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, 
   TKBO_REQUIRE(idx_offset >= 0 && idx_offset + N <= (int64_t(1) << 32) - 1, "global index must stay below 2^32 - 1 for the key form");
   p.out_key = reinterpret_cast<long long*>(out_key);
   p.idx_offset = idx_offset;
-  TKBO_CUDA_CHECK(cudaMemsetAsync(bs->packed, 0, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long), stream));
   return dispatch_fused<0>(h, bs, p, grid, stream);
 }
 
@@ -492,8 +546,8 @@ int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg) {
   const int64_t mt = (N + kTileM - 1) / kTileM;
   cfg[0] = bs->SC; cfg[1] = bs->n_chunks; cfg[2] = bs->Dpad / kSlabK; cfg[3] = bs->stages; cfg[4] = bs->acc_bufs;
   cfg[5] = bs->DT; cfg[6] = bs->smem_bytes;
-  cfg[7] = static_cast<int32_t>(std::min<int64_t>(h->sm_count, ((std::max<int64_t>(1, mt) + bs->tiles - 1) / bs->tiles) * bs->n_chunks));
-  cfg[5] = bs->DT * 100 + bs->tiles;              // d_template * 100 + tiles per work item
+  cfg[7] = static_cast<int32_t>(std::min<int64_t>(h->sm_count, std::max<int64_t>(1, mt) * bs->n_chunks));
+  cfg[8] = bs->ring; cfg[9] = kNumThreadsFor(bs->npg); cfg[10] = bs->xa_bufs; cfg[11] = bs->npg; cfg[12] = bs->proj_warps;
   return TKBO_OK;
 }
 

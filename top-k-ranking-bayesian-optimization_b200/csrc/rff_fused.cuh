@@ -2,22 +2,31 @@
 // per-sample (value, index) argmax.  Replaces fourier_features.py:18-21 + ":162-167" (n_init -> N) and the
 // Phi @ theta of acquisitions/dts.py:82-85 for a basis shared by all S samples.
 //
-// Work item = (group of TILES 128-candidate tiles, chunk of SC samples).  Per item and tile the CTA accumulates
+// Work item = (128-candidate tile, chunk of SC samples).  Per item the CTA accumulates
 //     acc[128 x SC] = sum over 64-feature slabs of  Phi_slab[128 x 64] * ThetaScaled_slab[SC x 64]^T
 // with Phi and Theta each split into fp16 hi + lo parts and three tcgen05.mma (hi*hi + hi*lo + lo*hi) per
 // K=16 step, fp32 accumulation in TMEM ("fp32 emulation": ~2^-22 relative per product).
 //
-// TILES = 2 (chosen by the host when SC <= 64, where the feature producers rather than the tensor pipe bound the
-// kernel): every producer thread evaluates TWO candidate rows per W|b value it reads, which halves the
-// shared-memory broadcast traffic and the L2 -> smem Theta traffic per candidate.
+// Both GEMMs of the path run on the tensor pipe.  The projection  arg = X W^T + b  of a slab is itself a small
+// tcgen05.mma: X and (W | b) are split into three bf16 terms each (x = x1 + x2 + x3 exactly) and the six products
+// of order >= 2^-16 are laid side by side along K (K = 6 d + 3 <= 112), so that arg lands in TMEM with fp32
+// accuracy.  The feature producers then only do  TMEM -> cos -> fp16 hi/lo split -> TMEM  in place: five
+// instructions per feature, independent of d, no shared-memory traffic.
 //
 // Warp roles (32 * (6 + 4 NPG) threads, one CTA per SM, persistent over work items):
-//   warps 0-3   epilogue: TMEM accumulator -> per-sample warp max (CREDUX) -> packed atomicMax, or store F
+//   warps 0-3   per item: write the bf16-split candidate rows (projection A operand) into TMEM ahead of time;
+//               epilogue: accumulator -> per-sample warp max (CREDUX) + ballot row -> register best, one atomicMax
+//               per (warp, sample) at the end; or store F
 //   warps 4..   feature producers (NPG groups of four warps; group g takes global slab iterations g, g+NPG, ...):
-//               thread = one candidate row per tile; cos(x.w_j + b_j) for 64 features, hi/lo fp16 split,
-//               tcgen05.st into the TMEM A-operand ring.  Phi never touches shared or global memory.
-//   next warp   TMA: Theta hi/lo slab tiles (128B-swizzled, K-major) + the W|b slab into the smem ring
-//   last warp   TMEM allocation + one elected thread issuing tcgen05.mma / tcgen05.commit
+//               thread = one candidate row: tcgen05.ld 64 projection values, cos, hi/lo split, tcgen05.st back
+//               into the same 64 TMEM columns, which the main MMAs then read as their A operand
+//   next warp   TMA: Theta hi/lo slab tiles (128B-swizzled, K-major) + the bf16 (W | b) slab tile into the smem ring
+//   2 warps     projection MMAs, alternating slabs (1 warp when the smem ring depth is odd): they run ahead of the
+//               main MMAs as far as free TMEM ring slots and landed tiles allow
+//   2 warps     main MMAs, each owning one half of the accumulator columns (N = SC / 2 per instruction).
+//   A lone warp needs ~300 cycles for the waits, commits and address arithmetic of one slab while the tensor
+//   pipe queues only ~4 instructions, so a single issuing warp starves the pipe (tools/probe_mma_chain.cu);
+//   splitting the issue work over warps keeps every accumulator column's MMAs in one program order.
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -27,15 +36,29 @@ namespace tkbo {
 constexpr int kTileM = 128;          // candidates per tile (TMEM lanes)
 constexpr int kSlabK = 64;           // features per slab (= one 128-byte swizzle row of fp16)
 constexpr int kUmmaK = 16;           // K per tcgen05.mma for 16-bit inputs
-constexpr int kNumThreadsFor(int npg) { return 32 * (4 + 4 * npg + 2); }   // epilogue + producers + TMA + MMA warps
+constexpr int kNumThreadsFor(int npg) { return 32 * (4 + 4 * npg + 5); }   // epilogue + producers + TMA + 2 projection + 2 main MMA warps
 constexpr int kTmemCols = 512;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 12;       // smem ring (Theta + W tiles)
+constexpr int kMaxRing = 6;          // TMEM ring (projection result -> Phi hi/lo), 64 columns per slot
+
+// Projection K extent for a template input dimension: 6 split products per dimension + 3 bias terms.
+__host__ __device__ constexpr int proj_k_used(int DT) { return ((6 * DT + 3 + 15) / 16) * 16; }     // K multiplied
+__host__ __device__ constexpr int proj_k_alloc(int DT) {                                            // K stored (pow2)
+  return proj_k_used(DT) <= 16 ? 16 : (proj_k_used(DT) <= 32 ? 32 : (proj_k_used(DT) <= 64 ? 64 : 128));
+}
+__host__ __device__ constexpr int proj_row_bytes(int DT) { return (proj_k_alloc(DT) < 64 ? proj_k_alloc(DT) : 64) * 2; }
+__host__ __device__ constexpr int proj_tiles(int DT) { return proj_k_alloc(DT) > 64 ? 2 : 1; }      // 64-wide K blocks
+__host__ __device__ constexpr int proj_w_bytes(int DT) { return kSlabK * proj_row_bytes(DT) * proj_tiles(DT); }
+// Bytes per smem stage: Theta hi + lo tiles (SC rows x 128 B each) + the projection tile(s), 1024-byte aligned.
+__host__ __device__ constexpr int stage_tx_bytes(int SC, int DT) { return 2 * SC * 128 + proj_w_bytes(DT); }
+__host__ __device__ constexpr int stage_stride_bytes(int SC, int DT) {
+  return ((stage_tx_bytes(SC, DT) + 1023) / 1024) * 1024;
+}
 
 struct RffParams {
   const float* X;            // [N, d] candidates
-  const float* Wpack;        // [Dpad, WS] rows = (w_0..w_{DT-1}, b, 0...) per feature
   const float* unscale;      // [Salloc] 1 / (power-of-two scale folded into Theta)
-  unsigned long long* packed;  // [Salloc] running (orderable value << 32 | ~row), zero-initialised
+  unsigned long long* packed;  // [Salloc] running (orderable value << 32 | ~row); zero between launches
   unsigned int* done_counter;  // last-CTA detection
   float* out_val;            // [S]
   long long* out_idx;        // [S]
@@ -50,9 +73,12 @@ struct RffParams {
   int n_chunks;
   int n_slabs;               // Dpad / 64
   int n_mtiles;              // ceil(N / 128)
-  int stages;                // ring depth (smem B/W ring and TMEM A ring)
-  int acc_bufs;              // 1 or 2 accumulator buffers of TILES * SC columns
-  int debug;                 // timing ablations (TKBO_DEBUG): 1 = issue only the hi*hi MMA, 2 = producers skip the math
+  int stages;                // smem ring depth
+  int ring;                  // TMEM ring depth (64-column slots)
+  int acc_bufs;              // 1 or 2 accumulator buffers of SC columns
+  int xa_bufs;               // 1 or 2 buffers for the split candidate rows
+  int proj_warps;            // 1 or 2 projection-issuing warps (2 needs an even smem ring depth)
+  int debug;                 // timing ablations (TKBO_DEBUG): 1 = hi*hi MMA only, 2 = producers skip the cos, 4 = no Theta TMA
   unsigned long long* trace; // optional clock64() event log of CTA 0 ([kTraceEvents][trace_cap]), tools/trace_k1.py
   int trace_cap;
 };
@@ -60,335 +86,396 @@ struct RffParams {
 // Pipeline trace events (CTA 0, lane 0 of one warp per role); index = that role's own iteration counter.
 enum TraceEvent : int {
   kTrTmaEmpty = 0, kTrTmaIssued = 1,
-  kTrProdBFull = 2 /* + 2 * group */, kTrProdArrived = 3 /* + 2 * group */,
-  kTrMmaBFull = 8, kTrMmaAFull = 9, kTrMmaCommitted = 10,
-  kTrEpiAccFull = 11, kTrEpiDone = 12, kTrMmaAccEmpty = 13, kTraceEvents = 14
+  kTrProdPFull = 2 /* + 2 * group */, kTrProdArrived = 3 /* + 2 * group */,
+  kTrMmaProj = 8, kTrMmaAFull = 9, kTrMmaCommitted = 10,
+  kTrEpiAccFull = 11, kTrEpiDone = 12, kTrMmaAccEmpty = 13, kTrMmaProjIssued = 14, kTraceEvents = 15
 };
+// Compiled in only with -DTKBO_TRACE (libtkbo_trace.so): the issuing warps' loops must stay as short as possible.
 __device__ __forceinline__ void trace_event(const RffParams& p, int ev, int idx) {
+#ifdef TKBO_TRACE
   if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && idx < p.trace_cap)
     p.trace[ev * p.trace_cap + idx] = static_cast<unsigned long long>(clock64());
+#endif
 }
 
-template <int DT> struct WStride { static constexpr int value = (DT == 1) ? 2 : ((DT + 1 + 3) / 4) * 4; };
-
-// bytes one stage receives through its mbarrier, and the 1024-aligned stride between stages
-__host__ __device__ constexpr int stage_tx_bytes(int SC, int WS) { return 2 * SC * 128 + kSlabK * WS * 4; }
-__host__ __device__ constexpr int stage_stride_bytes(int SC, int WS) {
-  return 2 * SC * 128 + ((kSlabK * WS * 4 + 1023) / 1024) * 1024;
-}
-
-// TILES candidate rows x 32 features (half a slab) -> 16 packed fp16x2 hi words + 16 lo words per row.
-// One W|b read serves all TILES rows.
-template <int DT, int TILES>
-__device__ __forceinline__ void produce_half_slab(const float (&x)[TILES][DT], const float* __restrict__ wslab,
-                                                  uint32_t (&hi)[TILES][16], uint32_t (&lo)[TILES][16]) {
-  constexpr int WS = WStride<DT>::value;
+// 16 projection values (fp32 bits) -> 8 packed fp16x2 hi words followed by 8 lo words.
+__device__ __forceinline__ void cos_split16(const uint32_t* __restrict__ arg, uint32_t (&out)[16], bool skip) {
 #pragma unroll
-  for (int jj = 0; jj < 16; ++jj) {
-    float c[TILES][2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float* wr = wslab + (2 * jj + e) * WS;
-      float w[WS];
-      if constexpr (WS == 2) {
-        const float2 v = *reinterpret_cast<const float2*>(wr);
-        w[0] = v.x; w[1] = v.y;
-      } else {
-#pragma unroll
-        for (int q = 0; q < WS / 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(wr + 4 * q);
-          w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < TILES; ++t) {
-        float arg = w[DT];                    // phase b_j
-#pragma unroll
-        for (int i = 0; i < DT; ++i) arg = fmaf(x[t][i], w[i], arg);
-        c[t][e] = __cosf(arg);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < TILES; ++t) {
-      const __half2 h = __floats2half2_rn(c[t][0], c[t][1]);
-      const float2 back = __half22float2(h);
-      const __half2 l = __floats2half2_rn(c[t][0] - back.x, c[t][1] - back.y);
-      hi[t][jj] = *reinterpret_cast<const uint32_t*>(&h);
-      lo[t][jj] = *reinterpret_cast<const uint32_t*>(&l);
-    }
+  for (int jj = 0; jj < 8; ++jj) {
+    float c0, c1;
+    if (skip) { c0 = 1.f; c1 = 1.f; }
+    else { c0 = __cosf(__uint_as_float(arg[2 * jj])); c1 = __cosf(__uint_as_float(arg[2 * jj + 1])); }
+    const __half2 h = __floats2half2_rn(c0, c1);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(c0 - back.x, c1 - back.y);
+    out[jj] = *reinterpret_cast<const uint32_t*>(&h);
+    out[8 + jj] = *reinterpret_cast<const uint32_t*>(&l);
   }
 }
 
-template <int DT, int MODE /* 0 = argmax, 1 = store F */, int TILES /* 1 or 2 */, int NPG /* producer warp groups: 2 or 3 */>
+// x = x1 + x2 + x3 exactly, each term a bf16 (truncating the fp32 bits keeps every step exact).
+__device__ __forceinline__ void bf16_split3(float x, uint32_t& b1, uint32_t& b2, uint32_t& b3) {
+  const uint32_t u = __float_as_uint(x);
+  const float r1 = x - __uint_as_float(u & 0xFFFF0000u);
+  const uint32_t v = __float_as_uint(r1);
+  const float r2 = r1 - __uint_as_float(v & 0xFFFF0000u);      // <= 8 significant bits: exactly a bf16
+  b1 = u >> 16;
+  b2 = v >> 16;
+  b3 = __float_as_uint(r2) >> 16;
+}
+
+template <int DT, int MODE /* 0 = argmax, 1 = store F */, int NPG /* producer warp groups: 2 or 3 */>
 __global__ void __launch_bounds__(kNumThreadsFor(NPG), 1)
 rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                 const RffParams p) {
-  constexpr int WS = WStride<DT>::value;
-  constexpr int kAStage = TILES * kSlabK;            // TMEM columns per A-ring stage: per tile 32 hi + 32 lo
+                 const __grid_constant__ CUtensorMap tm_w, const RffParams p) {
+  constexpr int kPUsed = proj_k_used(DT);
+  constexpr int kPCols = proj_k_alloc(DT) / 2;       // TMEM columns of one split-candidate buffer (2 bf16 per column)
+  constexpr int kPRow = proj_row_bytes(DT);
+  constexpr int kPTile = kSlabK * kPRow;
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for the 128B-swizzled tiles; plain pointer arithmetic keeps the shared address space
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-  __shared__ uint64_t bar_b_full[kMaxStages];   // TMA landed Theta+W slab
-  __shared__ uint64_t bar_a_full[kMaxStages];   // producers wrote the Phi slab into TMEM
-  __shared__ uint64_t bar_empty[kMaxStages];    // MMAs reading stage finished (frees smem + TMEM stage)
-  __shared__ uint64_t bar_acc_full[2];
-  __shared__ uint64_t bar_acc_empty[2];
+  // mbarriers, addressed as bar0 + 8 * index in the hot loops
+  enum : int {
+    kBFull = 0,                        // [kMaxStages] TMA landed the Theta + W tiles of a slab
+    kBEmpty = kBFull + kMaxStages,     // [kMaxStages] main MMAs reading the stage finished
+    kPFull = kBEmpty + kMaxStages,     // [kMaxRing] projection of a slab is in its TMEM ring slot
+    kAFull = kPFull + kMaxRing,        // [kMaxRing] producers replaced it by the Phi hi/lo operand
+    kAccFull = kAFull + kMaxRing,      // [2]
+    kAccEmpty = kAccFull + 2,          // [2]
+    kXaFull = kAccEmpty + 2,           // [2] split candidate rows of an item are in TMEM
+    kNumBars = kXaFull + 2
+  };
+  __shared__ uint64_t bars[kNumBars];
   __shared__ uint32_t tmem_base_smem;
   __shared__ int is_last_cta;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int SC = p.SC;
-  const int sbytes = stage_stride_bytes(SC, WS);
-  const int txbytes = stage_tx_bytes(SC, WS);
-  const int n_groups = (p.n_mtiles + TILES - 1) / TILES;
-  const int n_items = n_groups * p.n_chunks;
+  // kernel parameters used in the loops, as registers
+  const int SC = p.SC, n_slabs = p.n_slabs, n_chunks = p.n_chunks, stages = p.stages, ring = p.ring;
+  const int acc_bufs = p.acc_bufs, xa_bufs = p.xa_bufs;
+  const int sbytes = stage_stride_bytes(SC, DT);
+  const int n_items = p.n_mtiles * n_chunks;
+  const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int total = my_items * n_slabs;              // slab iterations of this CTA
+  const uint32_t bar0 = smem_u32(bars);
+  // 1024-byte alignment for the 128B-swizzled tiles
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&bar_b_full[s], 1);
-      mbar_init(&bar_a_full[s], 4);          // one arrival per producer warp of the owning group
-      mbar_init(&bar_empty[s], 1);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(&bars[kBFull + s], 1);
+      mbar_init(&bars[kBEmpty + s], 2);      // one commit per main MMA warp
+    }
+    for (int s = 0; s < kMaxRing; ++s) {
+      mbar_init(&bars[kPFull + s], 1);
+      mbar_init(&bars[kAFull + s], 4);       // one arrival per producer warp of the owning group
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&bar_acc_full[a], 1);
-      mbar_init(&bar_acc_empty[a], 4);       // one arrival per epilogue warp
+      mbar_init(&bars[kAccFull + a], 2);     // one commit per main MMA warp
+      mbar_init(&bars[kAccEmpty + a], 4);    // one arrival per epilogue warp
+      mbar_init(&bars[kXaFull + a], 4);
     }
     fence_mbar_init();
   }
   constexpr int kTmaWarp = 4 + 4 * NPG;
-  constexpr int kMmaWarp = kTmaWarp + 1;
-  if (warp == kMmaWarp) tmem_alloc(&tmem_base_smem, kTmemCols);
+  constexpr int kProjWarp = kTmaWarp + 1;            // and + 2
+  constexpr int kMainWarp = kTmaWarp + 3;            // and + 4
+  if (warp == kMainWarp) tmem_alloc(&tmem_base_smem, kTmemCols);
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tm_hi);
     tma_prefetch_desc(&tm_lo);
+    tma_prefetch_desc(&tm_w);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t a_col0 = kTmemCols - p.stages * kAStage;   // TMEM A ring occupies the top columns
+  const uint32_t xa_col0 = acc_bufs * SC;                         // split candidate rows follow the accumulators
+  const uint32_t ring_col0 = kTmemCols - ring * kSlabK;           // the ring occupies the top columns
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer (warp-converged, one elected issuer)
     int st = 0, it = 0;
     uint32_t ph = 0;
+    const uint32_t txbytes = (p.debug & 4) ? proj_w_bytes(DT) : stage_tx_bytes(SC, DT);
+    const bool theta = !(p.debug & 4);               // ablation 4: no Theta tile loads
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int chunk = item % p.n_chunks;
-      for (int slab = 0; slab < p.n_slabs; ++slab, ++it) {
-        mbar_wait(&bar_empty[st], ph ^ 1);
+      const int chunk = item % n_chunks;
+      for (int slab = 0; slab < n_slabs; ++slab, ++it) {
+        mbar_wait(bar0 + 8 * (kBEmpty + st), ph ^ 1);
         trace_event(p, kTrTmaEmpty, it);
         if (elect_one()) {
-          uint8_t* sb = smem + st * sbytes;
-          if (p.debug & 4) {               // ablation: no Theta tile loads
-            mbar_arrive_expect_tx(&bar_b_full[st], kSlabK * WS * 4);
-          } else {
-            mbar_arrive_expect_tx(&bar_b_full[st], txbytes);
-            tma_load_2d(sb, &tm_hi, &bar_b_full[st], slab * kSlabK, chunk * SC);
-            tma_load_2d(sb + SC * 128, &tm_lo, &bar_b_full[st], slab * kSlabK, chunk * SC);
+          const uint32_t sb = smem0 + st * sbytes;
+          const uint32_t full = bar0 + 8 * (kBFull + st);
+          mbar_arrive_expect_tx(full, txbytes);
+          if (theta) {
+            tma_load_2d(sb, &tm_hi, full, slab * kSlabK, chunk * SC);
+            tma_load_2d(sb + SC * 128, &tm_lo, full, slab * kSlabK, chunk * SC);
           }
-          bulk_load_1d(sb + 2 * SC * 128, p.Wpack + static_cast<size_t>(slab) * kSlabK * WS, kSlabK * WS * 4,
-                       &bar_b_full[st]);
+#pragma unroll
+          for (int t = 0; t < proj_tiles(DT); ++t)
+            tma_load_2d(sb + 2 * SC * 128 + t * kPTile, &tm_w, full, t * 64, slab * kSlabK);
         }
         __syncwarp();
         trace_event(p, kTrTmaIssued, it);
-        if (++st == p.stages) { st = 0; ph ^= 1; }
+        if (++st == stages) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer (warp-converged, one elected issuer)
-    const uint32_t idesc = idesc_f16_f32(kTileM, SC);
-    // descriptor low words advance by plain adds: (addr >> 4) never carries out of its 14-bit field
-    const uint32_t desc_lo0 = smem_desc_lo(smem_u32(smem));
-    const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
-    const uint32_t desc_lopart = static_cast<uint32_t>(SC * 128) >> 4;     // Theta-lo tile follows the hi tile
-    int st = 0, ab = 0, it = 0, nitem = 0;
-    uint32_t ph = 0, aph = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
-      mbar_wait(&bar_acc_empty[ab], aph ^ 1);
-      trace_event(p, kTrMmaAccEmpty, nitem);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + ab * (TILES * SC);
-      for (int slab = 0; slab < p.n_slabs; ++slab, ++it) {
-        mbar_wait(&bar_b_full[st], ph);
-        trace_event(p, kTrMmaBFull, it);
-        mbar_wait(&bar_a_full[st], ph);
-        trace_event(p, kTrMmaAFull, it);
+  } else if (warp == kProjWarp || warp == kProjWarp + 1) {
+    // ------------------------------------------------------------------ projection MMAs: arg = [x splits | 1] . [w splits | b]^T
+    // Warp h of `npw` takes the slab iterations j = h, h + npw, ...  A ring slot is free again once the main MMAs of
+    // slab j - ring have finished, which is b_empty of that slab's smem stage (stages >= ring, and b_full(j) seen
+    // first implies every earlier phase of that barrier has completed).  The candidate rows of item i+2 (i+1 with
+    // one buffer) are only staged after the epilogue of item i, i.e. after all of item i's projections were consumed.
+    const int npw = p.proj_warps;
+    const int h = warp - kProjWarp;
+    if (h < npw) {
+      constexpr uint32_t idesc_proj = idesc_bf16_f32(kTileM, kSlabK);
+      constexpr uint32_t kWDescHi = smem_desc_hi(8 * kPRow, kPRow == 128 ? 2u : (kPRow == 64 ? 4u : 6u));
+      const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
+      const uint32_t desc_w0 = smem_desc_lo(smem0 + 2 * SC * 128);        // the (W | b) tile(s) follow Theta hi, lo
+      int slab = h % n_slabs, item = h / n_slabs;      // position of j inside this CTA's item sequence
+      int st = h % stages, slot = h % ring;
+      uint32_t ph = (h / stages) & 1;
+      int fst = 0;                                     // smem stage of slab j - ring (valid once j >= ring)
+      uint32_t fph = 0;
+      bool new_item = true;
+      for (int j = h; j < total; j += npw) {
+        mbar_wait(bar0 + 8 * (kBFull + st), ph);
+        if (j >= ring) mbar_wait(bar0 + 8 * (kBEmpty + fst), fph);
+        if (new_item) {
+          const int xb = (xa_bufs == 2) ? (item & 1) : 0;
+          const uint32_t use = (xa_bufs == 2) ? static_cast<uint32_t>(item >> 1) : static_cast<uint32_t>(item);
+          mbar_wait(bar0 + 8 * (kXaFull + xb), use & 1);
+          new_item = false;
+        }
+        trace_event(p, kTrMmaProj, j);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t b_hi = desc_lo0 + st * desc_stage;
-          const uint32_t b_lo = b_hi + desc_lopart;
-          const uint32_t a_st = tmem_base + a_col0 + st * kAStage;
+          const uint32_t d_tmem = tmem_base + ring_col0 + slot * kSlabK;
+          const uint32_t a_tmem = tmem_base + xa_col0 + ((xa_bufs == 2) ? (item & 1) : 0) * kPCols;
+          const uint32_t b_lo = desc_w0 + st * desc_stage;
 #pragma unroll
-          for (int k = 0; k < kSlabK / kUmmaK; ++k) {
-            const uint32_t koff = k * ((kUmmaK * 2) >> 4);               // 32 bytes of K per step, in 16-byte units
-#pragma unroll
-            for (int t = 0; t < TILES; ++t) {
-              const uint32_t a_hi = a_st + t * kSlabK + k * (kUmmaK / 2);
-              const uint32_t a_lo = a_hi + kSlabK / 2;
-              const uint32_t d = d_tmem + t * SC;
-              mma_f16_ts(d, a_hi, smem_desc_from_lo(b_hi + koff), idesc, (slab | k) != 0);
-              if (!(p.debug & 1)) {
-                mma_f16_ts(d, a_hi, smem_desc_from_lo(b_lo + koff), idesc, 1);
-                mma_f16_ts(d, a_lo, smem_desc_from_lo(b_hi + koff), idesc, 1);
-              }
-            }
+          for (int k = 0; k < kPUsed / kUmmaK; ++k) {
+            const uint32_t boff = (k / 4) * (kPTile >> 4) + (k % 4) * ((kUmmaK * 2) >> 4);
+            mma_f16_ts(d_tmem, a_tmem + k * (kUmmaK / 2), (static_cast<uint64_t>(kWDescHi) << 32) | (b_lo + boff),
+                       idesc_proj, k != 0);
           }
-          tc_commit(&bar_empty[st]);
-          if (slab == p.n_slabs - 1) tc_commit(&bar_acc_full[ab]);
+          tc_commit(bar0 + 8 * (kPFull + slot));
         }
         __syncwarp();
-        trace_event(p, kTrMmaCommitted, it);
-        if (++st == p.stages) { st = 0; ph ^= 1; }
+        trace_event(p, kTrMmaProjIssued, j);
+        // advance by npw slab iterations
+        if (j >= ring) { fst += npw; if (fst >= stages) { fst -= stages; fph ^= 1; } }
+        else if (j + npw >= ring) { fst = (j + npw - ring) % stages; fph = 0; }
+        st += npw; if (st >= stages) { st -= stages; ph ^= 1; }
+        slot += npw; if (slot >= ring) slot -= ring;
+        slab += npw;
+        while (slab >= n_slabs) {
+          slab -= n_slabs;
+          ++item;
+          new_item = true;
+          if (slab >= n_slabs && xa_bufs == 1) {         // an item without a slab of this warp: still observe its phase
+            mbar_wait(bar0 + 8 * kXaFull, static_cast<uint32_t>(item) & 1);
+          }
+        }
       }
-      if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
+    }
+  } else if (warp == kMainWarp || warp == kMainWarp + 1) {
+    // ------------------------------------------------------------------ main MMAs: acc += Phi_slab . Theta_slab^T (3 per K step)
+    // Warp h owns accumulator columns [h SC/2, (h+1) SC/2): N = SC/2 per instruction, Theta rows h SC/2 ... of the tile.
+    const int h = warp - kMainWarp;
+    const int NH = SC >> 1;
+    const uint32_t idesc = idesc_f16_f32(kTileM, NH);
+    // descriptor low words advance by plain adds: (addr >> 4) never carries out of its 14-bit field
+    const uint32_t desc_lo0 = smem_desc_lo(smem0 + h * NH * 128);
+    const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
+    const uint32_t desc_lopart = static_cast<uint32_t>(SC * 128) >> 4;     // Theta-lo tile follows the hi tile
+    const bool hi_only = (p.debug & 1) != 0;
+    int st = 0, slot = 0, ab = 0, slab = 0, nitem = 0;
+    uint32_t sph = 0, aph = 0;
+    // a_full implies (through p_full and the projection warp's wait) that the stage's Theta tiles have landed
+    for (int it = 0; it < total; ++it) {
+      if (slab == 0) {
+        mbar_wait(bar0 + 8 * (kAccEmpty + ab), aph ^ 1);
+        if (h == 0) trace_event(p, kTrMmaAccEmpty, nitem);
+      }
+      mbar_wait(bar0 + 8 * (kAFull + slot), sph);
+      if (h == 0) trace_event(p, kTrMmaAFull, it);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + ab * SC + h * NH;
+        const uint32_t b_hi = desc_lo0 + st * desc_stage;
+        const uint32_t b_lo = b_hi + desc_lopart;
+        const uint32_t a_st = tmem_base + ring_col0 + slot * kSlabK;
+#pragma unroll
+        for (int k = 0; k < kSlabK / kUmmaK; ++k) {
+          const uint32_t koff = k * ((kUmmaK * 2) >> 4);               // 32 bytes of K per step, in 16-byte units
+          const uint32_t a_hi = a_st + k * kUmmaK;                     // 16 columns per K step: 8 hi words, 8 lo words
+          const uint32_t a_lo = a_hi + kUmmaK / 2;
+          mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_hi + koff), idesc, (slab | k) != 0);
+          if (!hi_only) {
+            mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_lo + koff), idesc, 1);
+            mma_f16_ts(d_tmem, a_lo, smem_desc_from_lo(b_hi + koff), idesc, 1);
+          }
+        }
+        tc_commit(bar0 + 8 * (kBEmpty + st));
+        if (slab == n_slabs - 1) tc_commit(bar0 + 8 * (kAccFull + ab));
+      }
+      __syncwarp();
+      if (h == 0) trace_event(p, kTrMmaCommitted, it);
+      if (++st == stages) st = 0;
+      if (++slot == ring) { slot = 0; sph ^= 1; }
+      if (++slab == n_slabs) {
+        slab = 0;
+        ++nitem;
+        if (++ab == acc_bufs) { ab = 0; aph ^= 1; }
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ feature producers
-    // group g owns the global slab iterations it = g, g + NPG, g + 2 NPG, ... (across work items), so its ring
-    // position always advances by NPG
+    // group g owns the slab iterations it = g, g + NPG, g + 2 NPG, ... of this CTA, whatever item they belong to
     const int group = (warp - 4) >> 2;               // 0 .. NPG-1
     const int q = warp & 3;                          // TMEM lane quarter of this warp
-    const int r = q * 32 + lane;                     // row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    int st = group % p.stages;
-    uint32_t ph = (group / p.stages) & 1;
-    int slab = group;
-    int item = blockIdx.x;
-    int it = 0;
-    while (slab >= p.n_slabs && item < n_items) { slab -= p.n_slabs; item += gridDim.x; }
-    while (item < n_items) {
-      const int grp = item / p.n_chunks;
-      float x[TILES][DT];
-#pragma unroll
-      for (int t = 0; t < TILES; ++t) {
-        long long row = (static_cast<long long>(grp) * TILES + t) * kTileM + r;
-        if (row >= p.N) row = p.N - 1;               // clamp: tail rows are masked in the epilogue
-#pragma unroll
-        for (int i = 0; i < DT; ++i) x[t][i] = (i < p.d) ? __ldg(p.X + row * p.d + i) : 0.f;
-      }
-      for (; slab < p.n_slabs; slab += NPG, ++it) {
-        mbar_wait(&bar_b_full[st], ph);              // W slab present; also implies the TMEM stage is free
-        if (q == 0) trace_event(p, kTrProdBFull + 2 * group, it);
-        const float* wslab = reinterpret_cast<const float*>(smem + st * sbytes + 2 * SC * 128);
-        const uint32_t a_st = tmem_base + lane_base + a_col0 + st * kAStage;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t hi[TILES][16], lo[TILES][16];
-          if (p.debug & 2) {
-#pragma unroll
-            for (int t = 0; t < TILES; ++t)
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) { hi[t][jj] = 0x3c003c00u; lo[t][jj] = 0u; }
-          } else {
-            produce_half_slab<DT, TILES>(x, wslab + half * 32 * WS, hi, lo);
-          }
-          if (!(p.debug & 8)) {
-#pragma unroll
-            for (int t = 0; t < TILES; ++t) {
-              tmem_st_x16(a_st + t * kSlabK + half * 16, hi[t]);
-              tmem_st_x16(a_st + t * kSlabK + kSlabK / 2 + half * 16, lo[t]);
-            }
-          }
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_a_full[st]);
-        if (q == 0) trace_event(p, kTrProdArrived + 2 * group, it);
-        st += NPG;
-        if (st >= p.stages) { st -= p.stages; ph ^= 1; }
-      }
-      slab -= p.n_slabs;                             // first slab of this group in the next item
-      item += gridDim.x;
-      while (slab >= p.n_slabs && item < n_items) { slab -= p.n_slabs; item += gridDim.x; }   // n_slabs == 1
+    const bool skip = (p.debug & 2) != 0;
+    int slot = group % ring;
+    uint32_t ph = (group / ring) & 1;
+    int n = 0;
+    for (int it = group; it < total; it += NPG, ++n) {
+      mbar_wait(bar0 + 8 * (kPFull + slot), ph);
+      if (q == 0) trace_event(p, kTrProdPFull + 2 * group, n);
+      tc_fence_after();
+      const uint32_t col = tmem_base + lane_base + ring_col0 + slot * kSlabK;
+      // 16 columns at a time, the next load in flight while the current values are converted (keeps the live
+      // registers at two 16-word buffers + one output buffer)
+      uint32_t r0[16], r1[16], out[16];
+      tmem_ld_x16(col, r0);
+      tmem_ld_x16(col + 16, r1);
+      tmem_wait_ld();
+      cos_split16(r0, out, skip);
+      tmem_st_x16(col, out);
+      tmem_ld_x16(col + 32, r0);
+      cos_split16(r1, out, skip);
+      tmem_st_x16(col + 16, out);
+      tmem_ld_x16(col + 48, r1);
+      tmem_wait_ld();
+      cos_split16(r0, out, skip);
+      tmem_st_x16(col + 32, out);
+      cos_split16(r1, out, skip);
+      tmem_st_x16(col + 48, out);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (kAFull + slot));
+      if (q == 0) trace_event(p, kTrProdArrived + 2 * group, n);
+      slot += NPG;
+      if (slot >= ring) { slot -= ring; ph ^= 1; }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ candidate rows + epilogue
     const int q = warp;                              // warps 0..3 <-> TMEM lanes 32q..32q+31
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    int ab = 0, nitem = 0;
-    uint32_t aph = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
-      const int grp = item / p.n_chunks;
-      const int chunk = item % p.n_chunks;
-      const int s_base = chunk * SC;
 
-      unsigned long long bestpk[8];
-      float bestv[8];
-      if constexpr (MODE == 0) {
+    // Write the split rows of this CTA's j-th item into buffer j % xa_bufs; called after the epilogue of item
+    // j - xa_bufs, when every projection that read the buffer has long completed.  K order per input dimension i:
+    // x1 x1 x2 x1 x2 x3 (against w1 w2 w1 w3 w2 w1), then three ones (against b1 b2 b3), zero padding.
+    auto stage_rows = [&](int j) {
+      const int item = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
+      if (item >= n_items) return;
+      const int xb = (xa_bufs == 2) ? (j & 1) : 0;
+      long long row = static_cast<long long>(item / n_chunks) * kTileM + q * 32 + lane;
+      if (row >= p.N) row = p.N - 1;                 // clamp: tail rows are masked in the epilogue
+      uint32_t w[kPCols];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          bestpk[j] = 0ull;
-          bestv[j] = -INFINITY;
-          if (j * 32 < SC) {
-            bestpk[j] = __ldcg(p.packed + s_base + j * 32 + lane);
-            if (bestpk[j] != 0ull) bestv[j] = f32_from_orderable(static_cast<uint32_t>(bestpk[j] >> 32));
-          }
-        }
+      for (int c = 0; c < kPCols; ++c) w[c] = 0u;
+#pragma unroll
+      for (int i = 0; i < DT; ++i) {
+        const float x = (i < p.d) ? __ldg(p.X + row * p.d + i) : 0.f;
+        uint32_t b1, b2, b3;
+        bf16_split3(x, b1, b2, b3);
+        w[3 * i + 0] = b1 | (b1 << 16);              // k = 6i, 6i+1
+        w[3 * i + 1] = b2 | (b1 << 16);              // k = 6i+2, 6i+3
+        w[3 * i + 2] = b2 | (b3 << 16);              // k = 6i+4, 6i+5
       }
-      mbar_wait(&bar_acc_full[ab], aph);
+      constexpr uint32_t kOne = 0x3F80u;             // bf16 1.0 at k = 6 DT, 6 DT + 1, 6 DT + 2
+      w[3 * DT] = kOne | (kOne << 16);
+      w[3 * DT + 1] = kOne;
+      const uint32_t col = tmem_base + lane_base + xa_col0 + xb * kPCols;
+#pragma unroll
+      for (int c = 0; c < kPCols; c += 8) tmem_st_x8(col + c, w + c);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (kXaFull + xb));
+    };
+
+    stage_rows(0);
+    if (xa_bufs == 2) stage_rows(1);
+
+    int ab = 0, nitem = 0, cur_chunk = -1;
+    uint32_t aph = 0;
+    float bestv[8];
+    uint32_t bestrow[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bestv[j] = -INFINITY; bestrow[j] = 0xFFFFFFFFu; }
+    // one atomicMax per (warp, sample) whenever the CTA moves to another sample chunk, and at the end
+    auto flush_best = [&]() {
+      if (cur_chunk < 0) return;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int s = cur_chunk * SC + j * 32 + lane;
+        if (j * 32 < SC && s < p.S && bestrow[j] != 0xFFFFFFFFu)
+          atomicMax(p.packed + s, pack_val_row(bestv[j] + 0.0f, bestrow[j]));
+        bestv[j] = -INFINITY;
+        bestrow[j] = 0xFFFFFFFFu;
+      }
+    };
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
+      const int mtile = item / n_chunks;
+      const int chunk = item % n_chunks;
+      const int s_base = chunk * SC;
+      if constexpr (MODE == 0) {
+        if (chunk != cur_chunk) { flush_best(); cur_chunk = chunk; }
+      }
+      mbar_wait(bar0 + 8 * (kAccFull + ab), aph);
       if (q == 0) trace_event(p, kTrEpiAccFull, nitem);
       tc_fence_after();
-#pragma unroll 1
-      for (int t = 0; t < TILES; ++t) {
-        const long long row0 = (static_cast<long long>(grp) * TILES + t) * kTileM + q * 32;
-        if (row0 >= p.N) continue;                   // whole warp beyond the last candidate (warp-uniform)
-        const long long row = row0 + lane;
-        const bool partial = (row0 + 32 > p.N);
-        const bool row_ok = row < p.N;
-        const uint32_t acc = tmem_base + lane_base + ab * (TILES * SC) + t * SC;
+      const long long row0 = static_cast<long long>(mtile) * kTileM + q * 32;
+      const long long row = row0 + lane;
+      const bool partial = (row0 + 32 > p.N);
+      const bool row_ok = row < p.N;
+      const uint32_t acc = tmem_base + lane_base + ab * SC;
+      if (row0 < p.N) {                              // else: whole warp beyond the last candidate (warp-uniform)
 #pragma unroll 1
         for (int j = 0; j < SC / 32; ++j) {
           uint32_t v[32];
           tmem_ld_x32(acc + j * 32, v);
           tmem_wait_ld();
           if constexpr (MODE == 0) {
+            if (partial) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = row_ok ? v[c] : 0xFF800000u;     // -inf
+            }
             float mine = -INFINITY;
-            if (!partial) {
+            unsigned minehit = 0u;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const float m = warp_max_f32(__uint_as_float(v[c]));
-                mine = (lane == c) ? m : mine;
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const float m = warp_max_f32(row_ok ? __uint_as_float(v[c]) : -INFINITY);
-                mine = (lane == c) ? m : mine;
-              }
+            for (int c = 0; c < 32; ++c) {
+              const float val = __uint_as_float(v[c]);
+              const float m = warp_max_f32(val);
+              const unsigned hit = __ballot_sync(0xffffffffu, val == m);
+              if (lane == c) { mine = m; minehit = hit; }
             }
-            // bestv/bestpk are indexed by j dynamically: select without local-memory indexing
-            float bv = -INFINITY;
-            unsigned long long bp = 0ull;
+            // lane c now holds (max, rows attaining it) of column c; bestv/bestrow are indexed by j dynamically:
+            // select without local-memory indexing.  Strict > keeps the lowest row (items come in row order).
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj)
-              if (jj == j) { bv = bestv[jj]; bp = bestpk[jj]; }
-            const int s = s_base + j * 32 + lane;
-            const bool flag = (s < p.S) && (mine >= bv);
-            unsigned mask = __ballot_sync(0xffffffffu, flag);
-            while (mask) {
-              const int c = __ffs(mask) - 1;
-              mask &= mask - 1;
-              const float mc = __shfl_sync(0xffffffffu, mine, c);
-              float vv = __uint_as_float(tmem_ld_x1(acc + j * 32 + c));
-              tmem_wait_ld();
-              if (!row_ok) vv = -INFINITY;
-              const unsigned hit = __ballot_sync(0xffffffffu, vv == mc);
-              const int l = __ffs(hit) - 1;
-              if (lane == c && hit != 0u) {
-                const unsigned long long pk = pack_val_row(mc + 0.0f, static_cast<uint32_t>(row0 + l));
-                if (pk > bp) {
-                  atomicMax(p.packed + s, pk);
-                  bp = pk;
-                  bv = mc;
-                }
+              if (jj == j && minehit != 0u && mine > bestv[jj]) {
+                bestv[jj] = mine;
+                bestrow[jj] = static_cast<uint32_t>(row0) + (__ffs(minehit) - 1);
               }
-            }
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-              if (jj == j) { bestv[jj] = bv; bestpk[jj] = bp; }
           } else {
             if (row_ok) {
 #pragma unroll
@@ -402,17 +489,19 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_acc_empty[ab]);
+      if (lane == 0) mbar_arrive(bar0 + 8 * (kAccEmpty + ab));
       if (q == 0) trace_event(p, kTrEpiDone, nitem);
-      if (++ab == p.acc_bufs) { ab = 0; aph ^= 1; }
+      if (++ab == acc_bufs) { ab = 0; aph ^= 1; }
+      stage_rows(nitem + xa_bufs);
     }
+    if constexpr (MODE == 0) flush_best();
   }
 
   // ---------------------------------------------------------------------- teardown + final reduce
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kMainWarp) tmem_dealloc(tmem_base, kTmemCols);
   if constexpr (MODE == 0) {
     __threadfence();
     __syncthreads();
@@ -425,6 +514,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       __threadfence();
       for (int s = threadIdx.x; s < p.S; s += blockDim.x) {
         const unsigned long long pk = __ldcg(p.packed + s);
+        p.packed[s] = 0ull;                       // ready for the next launch
         const bool none = (pk == 0ull);           // only NaNs seen for this sample
         const float v = none ? __int_as_float(0x7fc00000)
                              : f32_from_orderable(static_cast<uint32_t>(pk >> 32)) * p.unscale[s];

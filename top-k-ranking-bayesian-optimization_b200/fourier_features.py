@@ -286,13 +286,11 @@ class SharedBasis:
         return rel_feature_error * (self.Theta * float(np.sqrt(2.0 / self.D))).norm(dim=0)
 
     def config(self, N):
-        cfg = (ctypes.c_int32 * 8)()
+        cfg = (ctypes.c_int32 * 16)()
         nat.check(nat.lib().tkbo_rff_basis_config(self._h, self._basis, int(N), cfg), "tkbo_rff_basis_config")
-        keys = ["S_chunk", "n_chunks", "n_slabs", "stages", "acc_bufs", "d_template", "smem_bytes", "grid"]
-        out = dict(zip(keys, list(cfg)))
-        out["tiles_per_item"] = out["d_template"] % 100
-        out["d_template"] //= 100
-        return out
+        keys = ["S_chunk", "n_chunks", "n_slabs", "stages", "acc_bufs", "d_template", "smem_bytes", "grid",
+                "tmem_ring", "threads", "row_bufs", "producer_groups", "proj_warps"]
+        return dict(zip(keys, list(cfg)))
 
     def _candidates(self, X):
         X = _f32(X, self.device)
