@@ -192,6 +192,9 @@ def main():
         for (N, D, d, S) in [(1 << 20, 1024, 2, 64), (1 << 18, 4096, 6, 256), (1 << 16, 2048, 4, 4096)]:
             ms, cs, tf = k1_timing(N, D, d, S)
             print(f"K1 timing N={N} D={D} d={d} S={S}: {ms:.3f} ms  {cs:.3e} cand*samples/s  {tf:.1f} TFLOP/s(alg)", flush=True)
+    if what == "k2time":
+        ms, qs, gbs = k2_timing(1024, 100000, 5, 3, 20)
+        print(f"K2 timing c5: {ms:.3f} ms  {qs:.3e} evals/s  {gbs:.1f} GB/s", flush=True)
     if what in ("k2", "all"):
         for (S, Q, C, k, M, mode) in [(512, 70, 5, 3, 20, 0), (256, 33, 4, 4, 6, 0), (300, 40, 3, 1, 5, 0),
                                       (200, 10, 5, 2, 40, 0), (1000, 12, 2, 1, 20, 1), (128, 9, 6, 3, 4, 0)]:

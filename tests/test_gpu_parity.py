@@ -59,6 +59,12 @@ def _check_argmax(val, idx, X, W, b, Theta, idx_offset=0):
     (2048, 128, 12, 512, 0.0, 1.0, 0.8),      # d=12 (SUSHI duels), two chunks of 256
     (777, 70, 5, 7, 0.0, 1.0, 0.4),           # d padded to the 6-wide template, tiny S
     (20000, 512, 2, 64, -1.5, 1.5, 0.6),      # many tiles per CTA
+    (40000, 64, 2, 64, -1.5, 1.5, 0.6),       # one slab per item: candidate rows staged every slab, 2 items per CTA
+    (40000, 256, 4, 256, 0.0, 1.0, 0.3),      # odd smem ring (3 stages): single projection warp, several items per CTA
+    (6000, 320, 12, 256, 0.0, 1.0, 0.8),      # K = 75 projection (two W tiles), single candidate-row buffer
+    (30000, 128, 16, 32, 0.0, 1.0, 1.0),      # d = 16 (K = 99), 16-column accumulator halves
+    (9000, 192, 8, 40, 0.0, 1.0, 0.7),        # d = 8 (K = 51, one 128-byte W tile)
+    (9000, 192, 3, 130, -1.0, 1.0, 0.5),      # d = 3 (K = 21, 64-byte swizzle), S chunk of 160
 ])
 def test_rff_eval_and_argmax_vs_oracle(pbo, N, D, d, S, lo, hi, ls):
     rng = np.random.default_rng(N + D + S)
