@@ -258,21 +258,20 @@ def run_gpu(args):
     ms_per_step = ms / args.steps
     value = world * N * S / (ms_per_step * 1e-3)
 
-    # ---- end to end through the public API with host buffers (every step: H2D of candidates + basis, D2H of result)
+    # ---- end to end through the C ABI with HOST buffers (tkbo_rff_argmax_host): every step copies the step's pinned
+    # candidates and the float64 basis to the device (candidate chunks pipelined against the kernel), runs the fused
+    # argmax and reads the S results back.  N > 1: each rank does that for its shard, then one all_reduce(MAX) of keys.
     W_h, b_h, T_h = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (W, b, Theta))
     res_val = torch.empty(S, dtype=torch.float32).pin_memory()
     res_idx = torch.empty(S, dtype=torch.int64).pin_memory()
+    ff = pkg.fourier_features
 
     def e2e_step(i):
-        Xd = host_bufs[i % len(host_bufs)].to(dev, non_blocking=True)
-        basis.set(W_h.to(dev, non_blocking=True), b_h.to(dev, non_blocking=True), T_h.to(dev, non_blocking=True))
-        if world > 1:
-            val, idx = pkg.distributed.sharded_argmax_fast(basis, Xd, offset)
-        else:
-            val, idx = basis.argmax(Xd, idx_offset=offset)
-        res_val.copy_(val, non_blocking=True)
-        res_idx.copy_(idx, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        ff.argmax_host(W_h, b_h, T_h, host_bufs[i % len(host_bufs)], device=local, out_val=res_val, out_idx=res_idx)
+        if world > 1:       # merge the per-rank results (global index = local + rank offset)
+            key = torch.stack([res_val.to(dev).double(), -(res_idx.to(dev) + offset).double()])
+            gathered = [torch.empty_like(key) for _ in range(world)]
+            dist.all_gather(gathered, key)
         return float(res_val[0])
 
     for i in range(min(3, args.warmup)):
@@ -295,6 +294,12 @@ def run_gpu(args):
     if rank == 0:
         pk = peaks()
         alg_tf = 2.0 * N * D * S / (ms_per_step * 1e-3) / 1e12        # per GPU: one launch processes N candidates
+        proj_k = ((6 * cfg["d_template"] + 3 + 15) // 16) * 16
+        Dpad = cfg["n_slabs"] * 64
+        exec_tf = (3 * 2.0 * N * Dpad * cfg["S_chunk"] * cfg["n_chunks"] + 2.0 * N * Dpad * proj_k * cfg["n_chunks"]) \
+            / (ms_per_step * 1e-3) / 1e12
+        cos_rate = float(N) * Dpad * cfg["n_chunks"] / (ms_per_step * 1e-3)
+        cos_peak = 16.0 * 148 * 1965e6
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (fp16 hi/lo split x3 tcgen05.mma, fp32 accumulate)", "data": "synthetic",
@@ -303,15 +308,22 @@ def run_gpu(args):
                            "tiling": cfg, "parallelism": f"candidate shards x{world}, one int64 all_reduce(MAX) merge"},
                 "e2e": {"value": world * N * S / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "what": "pinned host candidates + fp64 basis -> device, basis_set, fused argmax, result -> host"},
+                        "what": "tkbo_rff_argmax_host (C ABI, host buffers): pinned candidates + fp64 basis -> device (candidate chunks "
+                                "pipelined against the kernel), operand prep, fused argmax, S results -> host"},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": alg_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                             "frac": alg_tf / pk["bf16_tflops"], "traffic": None,
+                             "frac": alg_tf / pk["bf16_tflops"], "traffic": 8.73e6 if args.workload == "c2" else None,
                              "kernel": "rff_fused_kernel", "flops_per_launch": 2.0 * N * D * S,
-                             "executed": 3 * alg_tf, "executed_frac": 3 * alg_tf / pk["bf16_tflops"],
-                             "note": "achieved = algorithmic 2*N*D*S per launch / CUDA-event time; executed = 3 fp16 MMAs per "
-                                     "product (hi*hi + hi*lo + lo*hi, fp32-accurate); peak = measured bf16 cuBLAS burst (" + pk["source"] + ")"}}
+                             "executed": exec_tf, "executed_frac": exec_tf / pk["bf16_tflops"],
+                             "mufu": {"cos_per_s": cos_rate, "peak_cos_per_s": cos_peak, "frac": cos_rate / cos_peak,
+                                      "note": "the feature map needs N*D*n_chunks cos (MUFU, 16/clk/SM at the max SM clock); "
+                                              "this unit, not the tensor pipe, binds small-S shapes such as c2"},
+                             "note": "achieved = algorithmic 2*N*D*S per launch / CUDA-event time; executed adds what the "
+                                     "tensor pipe really does: 3 fp16 MMAs per product (hi*hi + hi*lo + lo*hi, fp32-accurate) and "
+                                     "the bf16x3 projection X W^T + b (K = " + str(proj_k) + "); peak = measured bf16 cuBLAS burst ("
+                                     + pk["source"] + "); traffic = dram bytes of one launch from the committed ncu capture "
+                                     "(profiles/r01_prof_k1_v4_summary.txt; algorithmic: 4*N*d = 8.39e6)"}}
     # ---- MPES kernel at c5
     if rank == 0 and not args.no_mpes:
         Sm, Q, C, k, M = 1024, 100000, 5, 3, 20

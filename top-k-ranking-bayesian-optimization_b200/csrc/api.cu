@@ -1,6 +1,7 @@
 // extern "C" surface of libtkbo.so (declared in include/tkbo.h).  No torch, no exceptions across the ABI.
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <new>
 #include <string>
 
@@ -22,6 +23,8 @@ int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float*
 int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, int64_t* out_key,
                    cudaStream_t stream);
 int unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, cudaStream_t stream);
+int merge_unpack_keys(tkbo_handle_t h, const int64_t* keys, int G, int S, float* out_val, int64_t* out_idx,
+                      cudaStream_t stream);
 int merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, int G, int S, float* out_val, int64_t* out_idx,
                  cudaStream_t stream);
 int rff_eval_batched(tkbo_handle_t h, const double* X, const double* W, const double* b, const double* theta, int count,
@@ -60,6 +63,25 @@ struct DeviceGuard {
   if (!(h)) { set_error("null handle"); return TKBO_ERR_INVALID; } \
   DeviceGuard _guard(h);                                           \
   if (!_guard.ok) { set_error("cannot select the handle's device"); return TKBO_ERR_CUDA; }
+
+// Host-buffer entry point.  State (basis layout, device staging, two streams) lives on the handle and is reused while
+// (D, d, S) and the sizes fit, so a steady-state call is: basis H2D + prep kernels, then the candidates in up to
+// kHostChunksMax chunks, the H2D copy of chunk k+1 overlapping the fused kernel on chunk k (pass PINNED host memory
+// for that overlap), one merge of the per-chunk keys, and the D2H of the S results.
+constexpr int kHostChunksMax = 8;
+
+static void host_path_release(tkbo_handle_t h) {
+  auto& hp = h->host;
+  if (hp.basis) basis_destroy(h, hp.basis);
+  cudaFree(hp.dbasis); cudaFree(hp.dX[0]); cudaFree(hp.dX[1]); cudaFree(hp.keys); cudaFree(hp.dval); cudaFree(hp.didx);
+  for (int i = 0; i < 2; ++i) {
+    if (hp.copied[i]) cudaEventDestroy(hp.copied[i]);
+    if (hp.consumed[i]) cudaEventDestroy(hp.consumed[i]);
+  }
+  if (hp.copy_stream) cudaStreamDestroy(hp.copy_stream);
+  if (hp.exec_stream) cudaStreamDestroy(hp.exec_stream);
+  hp = tkbo_handle_s::HostPath();
+}
 
 extern "C" {
 
@@ -118,6 +140,7 @@ int tkbo_destroy(tkbo_handle_t h) {
   if (!h) return TKBO_OK;
   {
     DeviceGuard g(h);
+    host_path_release(h);
     cudaFree(h->done_counter);
     cudaFree(h->mpes_scratch);
   }
@@ -180,35 +203,79 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
   TKBO_ENTER(h);
   if (!W || !b || !Theta || !X || !out_val || !out_idx) { set_error("null pointer"); return TKBO_ERR_INVALID; }
   if (N < 1) { set_error("N must be >= 1"); return TKBO_ERR_INVALID; }
-  tkbo_basis_t bs = nullptr;
-  int rc = basis_create(h, &bs, D, d, S);
-  if (rc != TKBO_OK) return rc;
-  double *dW = nullptr, *db = nullptr, *dT = nullptr;
-  float *dX = nullptr, *dval = nullptr;
-  int64_t* didx = nullptr;
-  cudaStream_t st = nullptr;
-  cudaError_t e = cudaSuccess;
-  e = e ? e : cudaMalloc(&dW, sizeof(double) * D * d);
-  e = e ? e : cudaMalloc(&db, sizeof(double) * D);
-  e = e ? e : cudaMalloc(&dT, sizeof(double) * D * S);
-  e = e ? e : cudaMalloc(&dX, sizeof(float) * N * d);
-  e = e ? e : cudaMalloc(&dval, sizeof(float) * S);
-  e = e ? e : cudaMalloc(&didx, sizeof(int64_t) * S);
-  e = e ? e : cudaMemcpyAsync(dW, W, sizeof(double) * D * d, cudaMemcpyHostToDevice, st);
-  e = e ? e : cudaMemcpyAsync(db, b, sizeof(double) * D, cudaMemcpyHostToDevice, st);
-  e = e ? e : cudaMemcpyAsync(dT, Theta, sizeof(double) * D * S, cudaMemcpyHostToDevice, st);
-  e = e ? e : cudaMemcpyAsync(dX, X, sizeof(float) * N * d, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) {
-    rc = basis_set(h, bs, dW, db, dT, 0, st);
-    if (rc == TKBO_OK) rc = rff_argmax(h, bs, dX, N, 0, dval, didx, st);
-    e = e ? e : cudaMemcpyAsync(out_val, dval, sizeof(float) * S, cudaMemcpyDeviceToHost, st);
-    e = e ? e : cudaMemcpyAsync(out_idx, didx, sizeof(int64_t) * S, cudaMemcpyDeviceToHost, st);
-    e = e ? e : cudaStreamSynchronize(st);
+  if (N >= (int64_t(1) << 32) - 256) { set_error("N must be below 2^32 - 256"); return TKBO_ERR_INVALID; }
+  auto& hp = h->host;
+  if (!hp.exec_stream) {
+    TKBO_CUDA_CHECK(cudaStreamCreateWithFlags(&hp.exec_stream, cudaStreamNonBlocking));
+    TKBO_CUDA_CHECK(cudaStreamCreateWithFlags(&hp.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      TKBO_CUDA_CHECK(cudaEventCreateWithFlags(&hp.copied[i], cudaEventDisableTiming));
+      TKBO_CUDA_CHECK(cudaEventCreateWithFlags(&hp.consumed[i], cudaEventDisableTiming));
+    }
   }
-  cudaFree(dW); cudaFree(db); cudaFree(dT); cudaFree(dX); cudaFree(dval); cudaFree(didx);
-  basis_destroy(h, bs);
-  if (e != cudaSuccess) { set_error(std::string("tkbo_rff_argmax_host: ") + cudaGetErrorString(e)); return TKBO_ERR_CUDA; }
-  return rc;
+  if (!hp.basis || hp.D != D || hp.d != d || hp.S != S) {
+    if (hp.basis) { basis_destroy(h, hp.basis); hp.basis = nullptr; }
+    int rc = basis_create(h, &hp.basis, D, d, S);
+    if (rc != TKBO_OK) return rc;
+    hp.D = D; hp.d = d; hp.S = S;
+  }
+  const size_t nb = static_cast<size_t>(D) * d + D + static_cast<size_t>(D) * S;
+  if (hp.dbasis_doubles < nb) {
+    cudaFree(hp.dbasis); hp.dbasis = nullptr; hp.dbasis_doubles = 0;
+    TKBO_CUDA_CHECK(cudaMalloc(&hp.dbasis, nb * sizeof(double)));
+    hp.dbasis_doubles = nb;
+  }
+  if (hp.out_S < S) {
+    cudaFree(hp.keys); cudaFree(hp.dval); cudaFree(hp.didx);
+    hp.keys = nullptr; hp.dval = nullptr; hp.didx = nullptr; hp.out_S = 0;
+    TKBO_CUDA_CHECK(cudaMalloc(&hp.keys, sizeof(long long) * kHostChunksMax * S));
+    TKBO_CUDA_CHECK(cudaMalloc(&hp.dval, sizeof(float) * S));
+    TKBO_CUDA_CHECK(cudaMalloc(&hp.didx, sizeof(long long) * S));
+    hp.out_S = S;
+  }
+  // chunks of whole 128-candidate tiles, at least 2^17 candidates each (below that the kernel's tail dominates)
+  int chunks = static_cast<int>(std::min<int64_t>(kHostChunksMax, std::max<int64_t>(1, N >> 17)));
+  if (chunks > 1) chunks = std::min(chunks, 4);
+  const int64_t per = (((N + chunks - 1) / chunks) + 127) / 128 * 128;
+  chunks = static_cast<int>((N + per - 1) / per);
+  if (hp.dX_floats < static_cast<size_t>(per) * d) {
+    cudaFree(hp.dX[0]); cudaFree(hp.dX[1]); hp.dX[0] = hp.dX[1] = nullptr; hp.dX_floats = 0;
+    TKBO_CUDA_CHECK(cudaMalloc(&hp.dX[0], sizeof(float) * per * d));
+    TKBO_CUDA_CHECK(cudaMalloc(&hp.dX[1], sizeof(float) * per * d));
+    hp.dX_floats = static_cast<size_t>(per) * d;
+  }
+  cudaStream_t sx = hp.exec_stream, sc = hp.copy_stream;
+  double* dW = hp.dbasis;
+  double* db = dW + static_cast<size_t>(D) * d;
+  double* dT = db + D;
+  // first candidate chunk goes out before the basis so that the copy engine is busy while the basis is prepared
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(hp.dX[0], X, sizeof(float) * std::min<int64_t>(per, N) * d, cudaMemcpyHostToDevice, sc));
+  TKBO_CUDA_CHECK(cudaEventRecord(hp.copied[0], sc));
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(dW, W, sizeof(double) * D * d, cudaMemcpyHostToDevice, sx));
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(db, b, sizeof(double) * D, cudaMemcpyHostToDevice, sx));
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(dT, Theta, sizeof(double) * D * S, cudaMemcpyHostToDevice, sx));
+  int rc = basis_set(h, hp.basis, dW, db, dT, 0, sx);
+  for (int k = 0; k < chunks && rc == TKBO_OK; ++k) {
+    const int buf = k & 1;
+    const int64_t n0 = static_cast<int64_t>(k) * per, nk = std::min<int64_t>(per, N - n0);
+    if (k + 1 < chunks) {                 // copy of the next chunk, once its buffer has been consumed
+      const int nb2 = (k + 1) & 1;
+      const int64_t m0 = n0 + per, mk = std::min<int64_t>(per, N - m0);
+      if (k >= 1) TKBO_CUDA_CHECK(cudaStreamWaitEvent(sc, hp.consumed[nb2], 0));
+      TKBO_CUDA_CHECK(cudaMemcpyAsync(hp.dX[nb2], X + m0 * d, sizeof(float) * mk * d, cudaMemcpyHostToDevice, sc));
+      TKBO_CUDA_CHECK(cudaEventRecord(hp.copied[nb2], sc));
+    }
+    TKBO_CUDA_CHECK(cudaStreamWaitEvent(sx, hp.copied[buf], 0));
+    rc = rff_argmax_key(h, hp.basis, hp.dX[buf], nk, n0, reinterpret_cast<int64_t*>(hp.keys) + static_cast<size_t>(k) * S, sx);
+    TKBO_CUDA_CHECK(cudaEventRecord(hp.consumed[buf], sx));
+  }
+  if (rc == TKBO_OK) rc = merge_unpack_keys(h, reinterpret_cast<int64_t*>(hp.keys), chunks, S, hp.dval,
+                                            reinterpret_cast<int64_t*>(hp.didx), sx);
+  if (rc != TKBO_OK) { cudaStreamSynchronize(sx); cudaStreamSynchronize(sc); return rc; }
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(out_val, hp.dval, sizeof(float) * S, cudaMemcpyDeviceToHost, sx));
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(out_idx, hp.didx, sizeof(int64_t) * S, cudaMemcpyDeviceToHost, sx));
+  TKBO_CUDA_CHECK(cudaStreamSynchronize(sx));
+  return TKBO_OK;
 }
 
 int tkbo_rff_eval_batched(tkbo_handle_t h, const double* X, const double* W, const double* b, const double* theta,

@@ -41,6 +41,21 @@ struct tkbo_handle_s {
   // scratch for the MPES kernel (grown on demand)
   void* mpes_scratch = nullptr;
   size_t mpes_scratch_bytes = 0;
+  // persistent state of the host-buffer entry point (tkbo_rff_argmax_host): basis + device staging, reused across calls
+  struct HostPath {
+    tkbo_basis_s* basis = nullptr;
+    int D = 0, d = 0, S = 0;
+    double* dbasis = nullptr;            // W | b | Theta as float64
+    size_t dbasis_doubles = 0;
+    float* dX[2] = {nullptr, nullptr};   // two candidate chunks (copy of chunk k+1 overlaps the kernel on chunk k)
+    size_t dX_floats = 0;                // capacity of each
+    long long* keys = nullptr;           // [kHostChunksMax, S] merge keys
+    float* dval = nullptr;
+    long long* didx = nullptr;
+    int out_S = 0;
+    cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+  } host;
   // optional K1 pipeline trace target (tkbo_debug_set_trace); caller-owned device memory
   unsigned long long* trace = nullptr;
   int trace_cap = 0;

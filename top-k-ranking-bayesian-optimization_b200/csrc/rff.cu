@@ -520,6 +520,30 @@ __global__ void unpack_key_kernel(const long long* __restrict__ key, int S, floa
   out_idx[s] = gi;
 }
 
+// key[s] = max over g of keys[g, s] (largest value, then lowest global index), unpacked.
+__global__ void merge_unpack_keys_kernel(const long long* __restrict__ keys, int G, int S, float* __restrict__ out_val,
+                                         long long* __restrict__ out_idx) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  long long best = keys[s];
+  for (int g = 1; g < G; ++g) best = max(best, keys[static_cast<size_t>(g) * S + s]);
+  float v;
+  long long gi;
+  argmax_unkey(best, &v, &gi);
+  out_val[s] = v;
+  out_idx[s] = gi;
+}
+
+int merge_unpack_keys(tkbo_handle_t h, const int64_t* keys, int G, int S, float* out_val, int64_t* out_idx,
+                      cudaStream_t stream) {
+  TKBO_REQUIRE(h && keys && out_val && out_idx && G >= 1 && S >= 1, "bad merge arguments");
+  merge_unpack_keys_kernel<<<(S + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const long long*>(keys), G, S, out_val,
+                                                              reinterpret_cast<long long*>(out_idx));
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
 int unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, cudaStream_t stream) {
   TKBO_REQUIRE(h && key && out_val && out_idx && S >= 1, "bad unpack arguments");
   unpack_key_kernel<<<(S + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const long long*>(key), S, out_val,

@@ -214,6 +214,35 @@ def sample_maximizers(X, count, n_init, D, model, min_val, max_val, num_steps=30
 # ---------------------------------------------------------------------------------------------------
 # shared-basis fast path
 # ---------------------------------------------------------------------------------------------------
+def argmax_host(W, b, Theta, X, device=0, out_val=None, out_idx=None):
+    """End-to-end host-buffer call (C ABI ``tkbo_rff_argmax_host``): W (D, d), b (D,), Theta (D, S) float64 and the
+    candidates X (N, d) float32 are HOST arrays (NumPy, or CPU torch tensors - pinned memory lets the H2D copy of
+    candidate chunk k+1 overlap the kernel on chunk k); returns (val[S] float32, idx[S] int64) NumPy arrays.
+    Device staging and the basis layout are cached on the handle between calls of the same shape."""
+    def host(a, dtype):
+        if hasattr(a, "data_ptr"):
+            assert a.device.type == "cpu" and a.is_contiguous()
+            return a, a.data_ptr(), tuple(a.shape)
+        a = np.ascontiguousarray(a, dtype=dtype)
+        return a, a.ctypes.data, a.shape
+    Wk, Wp, Ws = host(W, np.float64)
+    bk, bp, bs_ = host(b, np.float64)
+    Tk, Tp, Ts = host(Theta, np.float64)
+    Xk, Xp, Xs = host(X, np.float32)
+    D, d = Ws
+    S = Ts[1]
+    assert Ts[0] == D and int(np.prod(bs_)) == D and Xs[1] == d
+    val = np.empty(S, dtype=np.float32) if out_val is None else out_val
+    idx = np.empty(S, dtype=np.int64) if out_idx is None else out_idx
+    vp = val.data_ptr() if hasattr(val, "data_ptr") else val.ctypes.data
+    ip = idx.data_ptr() if hasattr(idx, "data_ptr") else idx.ctypes.data
+    dev = device if isinstance(device, int) else _device(device).index
+    nat.check(nat.lib().tkbo_rff_argmax_host(nat.handle(dev), ctypes.c_void_p(Wp), ctypes.c_void_p(bp), ctypes.c_void_p(Tp),
+                                             int(D), int(d), int(S), ctypes.c_void_p(Xp), int(Xs[0]), ctypes.c_void_p(vp),
+                                             ctypes.c_void_p(ip)), "tkbo_rff_argmax_host")
+    return val, idx
+
+
 class SharedBasis:
     """One RFF basis (W (D, d), b (D,)) shared by S posterior weight samples Theta (D, S), resident on one GPU in
     the fused kernel's operand layout.  ``argmax`` / ``eval`` stream any number of candidates through it."""
