@@ -53,7 +53,7 @@ int tkbo_sm_count(tkbo_handle_t h);
  *     F[n, s] = sqrt(2/D) * sum_j cos(X[n,:].W[j,:] + b[j]) * Theta[j, s]
  * which is fourier_features(X, W, b) @ theta  (fourier_features.py:18-21 and :162; acquisitions/dts.py:82-85)
  * evaluated for all S samples at once.  The basis object holds the device-side operand layout
- * (fp32 W|b slabs, Theta split into fp16 hi/lo K-major tiles with a per-sample power-of-two scale). */
+ * (bf16-split (W | b) projection rows, Theta split into fp16 hi/lo K-major tiles with a per-sample power-of-two scale). */
 int tkbo_rff_basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S);
 int tkbo_rff_basis_destroy(tkbo_handle_t h, tkbo_basis_t basis);
 /* W [D, d], b [D], Theta [D, S] (theta_is_transposed = 0) or [S, D] (= 1); all float64 device arrays. */
