@@ -69,6 +69,12 @@ int tkbo_rff_argmax(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t
  * acquisitions/dts.py:85 / the f-samples consumed by tkbo_mpes_topk. */
 int tkbo_rff_eval(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, float* out_F,
                   int64_t ldf, void* stream);
+/* Dueling-Thompson soft-Copeland scores without materialising the n^2 duels (acquisitions/dts.py:31-45 combinations,
+ * :71-85 sample_f, :88-97 soft_copeland_maximizer): the basis has d = 2 d_obj, the candidates are all ordered pairs
+ * [x_i, x_j] of the n base points Xbase [n, d_obj]; out_score[s, i] = mean_j sigmoid(f_s([x_i, x_j])) (float32 [S, n],
+ * may be NULL) and out_argmax[s] = lowest i attaining the maximum (may be NULL).  The per-duel values never leave the SM. */
+int tkbo_rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t basis, const float* Xbase, int n, float* out_score,
+                           int64_t* out_argmax, void* stream);
 /* Same as tkbo_rff_argmax but returns one signed 64-bit key per sample whose integer maximum is "largest value, then
  * lowest global index" (idx_offset + N < 2^32): ranks holding candidate shards merge with ONE all-reduce(MAX) over
  * int64 (NCCL), then tkbo_unpack_argmax_key recovers (value, index).  An empty / all-NaN sample has key INT64_MIN. */

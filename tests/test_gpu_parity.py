@@ -463,6 +463,45 @@ def test_dts_sample_f_signature_path(pbo):
     assert dts.soft_copeland_maximizer(f, grid, device="cuda:0").shape == (2,)
 
 
+@pytest.mark.parametrize("n,dobj,D,S", [(300, 2, 256, 40), (128, 1, 128, 300), (257, 3, 192, 8)])
+def test_duel_copeland_fused_matches_oracle_and_unfused_path(pbo, n, dobj, D, S):
+    """Fused duel generation + soft-Copeland epilogue (dts.py:31-45, 71-97 for S samples at once) against the fp64
+    oracle on the explicit n^2 duels, and against the unfused route (store-F kernel + tkbo_soft_copeland)."""
+    rng = np.random.default_rng(n + D + S)
+    Xb = rng.uniform(0.0, 1.0, size=(n, dobj)).astype(np.float32)
+    W = rng.standard_normal((D, 2 * dobj)) / 0.4
+    b = rng.uniform(0, 2 * np.pi, D)
+    Theta = rng.standard_normal((D, S)) * rng.uniform(0.5, 3.0, size=(1, S))
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    score, win = basis.duel_copeland(Xb)
+    combs = pbo.acquisitions.dts.combinations(Xb.astype(np.float64))
+    F = rff_oracle.rff_values_shared(combs, W, b, Theta)                       # (n^2, S)
+    ref = np.stack([mpes_oracle.soft_copeland_scores(F[:, s]) for s in range(S)])   # (S, n)
+    np.testing.assert_allclose(score.cpu().numpy(), ref, rtol=2e-5, atol=1e-6)
+    ref_win = ref.argmax(axis=1)
+    got = win.cpu().numpy()
+    top = np.sort(ref, axis=1)
+    clear = (top[:, -1] - top[:, -2]) > 1e-5                                  # winners with a resolvable margin
+    np.testing.assert_array_equal(got[clear], ref_win[clear])
+    assert np.all(ref[np.arange(S), got] >= top[:, -1] - 1e-5)
+    # deterministic fixed-point sums: bitwise repeatable
+    score2, win2 = basis.duel_copeland(Xb)
+    assert torch.equal(score, score2) and torch.equal(win, win2)
+    # unfused route on the first sample
+    f0 = basis.eval(combs.astype(np.float32))[0].reshape(-1, 1)
+    _, sc0 = pbo.acquisitions.dts.soft_copeland_maximizer(f0, Xb, return_scores=True)
+    np.testing.assert_allclose(score[0].cpu().numpy(), sc0.numpy(), rtol=2e-5, atol=1e-6)
+
+
+def test_dts_thompson_copeland_winners_signature(pbo):
+    dts = pbo.acquisitions.dts
+    mdl = pbo.model.synthetic_model(9, 4, 0.0, 1.0, [0.25, 0.4, 0.25, 0.4], seed=5, product=True)
+    grid = dts.uniform_grid(2, 12, 0, 1)
+    winners, scores = dts.thompson_copeland_winners(mdl, mdl.Z, grid, D=64, count=5, device="cuda:0", return_scores=True)
+    assert winners.shape == (5, 2) and tuple(scores.shape) == (5, 144)
+    assert bool(torch.isfinite(scores).all()) and float(scores.min()) > 0.0 and float(scores.max()) < 1.0
+
+
 def test_rff_joint_sampling_feeds_mpes(pbo):
     """model.predict_f_samples_device (RFF draws through the store-F epilogue) -> K2, nothing leaves the GPU."""
     mdl = pbo.model.synthetic_model(16, 6, 0.0, 1.0, 0.4, seed=8)

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "tkbo_rff_basis_config": (c_i, [c_p, c_p, c_i64, ctypes.POINTER(ctypes.c_int32)]),
     "tkbo_rff_argmax": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p]),
     "tkbo_rff_argmax_key": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "tkbo_rff_duel_copeland": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p]),
     "tkbo_unpack_argmax_key": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p]),
     "tkbo_rff_eval": (c_i, [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p]),
     "tkbo_merge_argmax": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),

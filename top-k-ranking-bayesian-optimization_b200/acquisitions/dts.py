@@ -58,3 +58,15 @@ def soft_copeland_maximizer(f_vals, discrete_space, *, device=None, return_score
                                            nat.current_stream_ptr(dev)), "tkbo_soft_copeland")
     winner = discrete_space[int(win.item())]
     return (winner, score.cpu()) if return_scores else winner
+
+
+def thompson_copeland_winners(m, query_points, discrete_space, D=1000, count=1, *, device=None, return_scores=False):
+    """``count`` independent rounds of sample_f + soft_copeland_maximizer (dts.py:71-97) in one fused launch: the
+    ``count`` posterior samples share one (W, b) draw, the n^2 duels [x, x'] of ``discrete_space`` are generated inside
+    the kernel and reduced to soft-Copeland scores on the fly (never stored).  Returns the (count, d) winners
+    (and the (count, n) scores)."""
+    pts = to_numpy(discrete_space)
+    basis = fourier_features.SharedBasis.sample(to_numpy(query_points), m, D=D, count=count, device=device)
+    score, win = basis.duel_copeland(pts, scores=return_scores)
+    winners = pts[win.cpu().numpy()]
+    return (winners, score.cpu()) if return_scores else winners

@@ -22,6 +22,8 @@ int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int6
 int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float* out_F, int64_t ldf, cudaStream_t stream);
 int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, int64_t* out_key,
                    cudaStream_t stream);
+int rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t bs, const float* Xbase, int n, float* out_score, int64_t* out_argmax,
+                      cudaStream_t stream);
 int unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, cudaStream_t stream);
 int merge_unpack_keys(tkbo_handle_t h, const int64_t* keys, int G, int S, float* out_val, int64_t* out_idx,
                       cudaStream_t stream);
@@ -183,6 +185,11 @@ int tkbo_rff_argmax_key(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int
                         int64_t* out_key, void* stream) {
   TKBO_ENTER(h);
   return rff_argmax_key(h, basis, X, N, idx_offset, out_key, as_stream(stream));
+}
+int tkbo_rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t basis, const float* Xbase, int n, float* out_score,
+                           int64_t* out_argmax, void* stream) {
+  TKBO_ENTER(h);
+  return rff_duel_copeland(h, basis, Xbase, n, out_score, out_argmax, as_stream(stream));
 }
 int tkbo_unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, void* stream) {
   TKBO_ENTER(h);

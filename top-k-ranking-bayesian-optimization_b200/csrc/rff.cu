@@ -449,9 +449,9 @@ static int launch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, in
 template <int MODE>
 static int dispatch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
   switch (bs->DT) {
-    case 1: return launch_fused<1, MODE>(h, bs, p, grid, stream);
+    case 1: if constexpr (MODE != 2) return launch_fused<1, MODE>(h, bs, p, grid, stream); else break;
     case 2: return launch_fused<2, MODE>(h, bs, p, grid, stream);
-    case 3: return launch_fused<3, MODE>(h, bs, p, grid, stream);
+    case 3: if constexpr (MODE != 2) return launch_fused<3, MODE>(h, bs, p, grid, stream); else break;
     case 4: return launch_fused<4, MODE>(h, bs, p, grid, stream);
     case 6: return launch_fused<6, MODE>(h, bs, p, grid, stream);
     case 8: return launch_fused<8, MODE>(h, bs, p, grid, stream);
@@ -469,6 +469,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->X = X; p->unscale = bs->unscale; p->packed = bs->packed;
   p->done_counter = h->done_counter;
   p->out_val = nullptr; p->out_idx = nullptr; p->out_key = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
+  p->duel_n = 0; p->score_fix = nullptr;
   p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
   p->n_slabs = bs->Dpad / kSlabK;
   const int64_t mt = (N + kTileM - 1) / kTileM;
@@ -563,6 +564,72 @@ int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float*
   p.out_F = out_F;
   p.ldf = ldf;
   return dispatch_fused<1>(h, bs, p, grid, stream);
+}
+
+// score[s, i] = fix[s, i] / (2^32 n), argmax over i (lowest index on ties)                 [dts.py:94-97]
+__global__ void copeland_finish_kernel(const unsigned long long* __restrict__ fix, int n, float* __restrict__ score,
+                                       long long* __restrict__ out_arg) {
+  const int s = blockIdx.x;
+  __shared__ unsigned long long bv[256];
+  __shared__ int bi[256];
+  unsigned long long best = 0ull;
+  int idx = 0x7fffffff;
+  const double inv = 1.0 / (4294967296.0 * static_cast<double>(n));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long v = fix[static_cast<size_t>(s) * n + i];
+    if (score) score[static_cast<size_t>(s) * n + i] = static_cast<float>(static_cast<double>(v) * inv);
+    if (idx == 0x7fffffff || v > best) { best = v; idx = i; }       // strided ascending: first maximum of this thread
+  }
+  bv[threadIdx.x] = best; bi[threadIdx.x] = idx;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const unsigned long long v = bv[threadIdx.x + o];
+      const int j = bi[threadIdx.x + o];
+      if (j != 0x7fffffff && (bi[threadIdx.x] == 0x7fffffff || v > bv[threadIdx.x] || (v == bv[threadIdx.x] && j < bi[threadIdx.x]))) {
+        bv[threadIdx.x] = v; bi[threadIdx.x] = j;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && out_arg) out_arg[s] = bi[0];
+}
+
+// Dueling-Thompson soft-Copeland over all ordered pairs of n base points, duels generated on the fly.
+int rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t bs, const float* Xbase, int n, float* out_score, int64_t* out_argmax,
+                      cudaStream_t stream) {
+  TKBO_REQUIRE(h && bs && Xbase, "null pointer");
+  TKBO_REQUIRE(bs->is_set, "basis has no data: call tkbo_rff_basis_set first");
+  TKBO_REQUIRE(bs->d % 2 == 0, "duel mode needs an even input dimension d = 2 d_obj");
+  TKBO_REQUIRE(n >= 1 && n <= (1 << 20), "n must be in [1, 2^20]");
+  TKBO_REQUIRE(out_score || out_argmax, "nothing to compute");
+  RffParams p;
+  const int64_t tpj = (n + kTileM - 1) / kTileM;
+  const int64_t mt = static_cast<int64_t>(n) * tpj;
+  TKBO_REQUIRE(mt * bs->n_chunks < (int64_t(1) << 31), "too many work items");
+  p.X = Xbase; p.unscale = bs->unscale; p.packed = bs->packed; p.done_counter = h->done_counter;
+  p.out_val = nullptr; p.out_idx = nullptr; p.out_key = nullptr; p.out_F = nullptr; p.ldf = 0; p.idx_offset = 0;
+  p.N = mt * kTileM; p.d = bs->d; p.S = bs->S; p.SC = bs->SC; p.n_chunks = bs->n_chunks;
+  p.n_slabs = bs->Dpad / kSlabK; p.n_mtiles = static_cast<int>(mt);
+  p.stages = bs->stages; p.ring = bs->ring; p.acc_bufs = bs->acc_bufs; p.xa_bufs = bs->xa_bufs;
+  p.proj_warps = bs->proj_warps;
+  p.duel_n = n;
+  p.debug = 0;
+  p.trace = nullptr; p.trace_cap = 0;
+  unsigned long long* fix = nullptr;
+  const size_t bytes = sizeof(unsigned long long) * static_cast<size_t>(bs->S) * n;
+  TKBO_CUDA_CHECK(cudaMallocAsync(&fix, bytes, stream));
+  TKBO_CUDA_CHECK(cudaMemsetAsync(fix, 0, bytes, stream));
+  p.score_fix = fix;
+  const int grid = static_cast<int>(std::min<int64_t>(h->sm_count, mt * bs->n_chunks));
+  int rc = dispatch_fused<2>(h, bs, p, grid, stream);
+  if (rc == TKBO_OK) {
+    copeland_finish_kernel<<<bs->S, 256, 0, stream>>>(fix, n, out_score, reinterpret_cast<long long*>(out_argmax));
+    h->launches += 1;
+  }
+  TKBO_CUDA_CHECK(cudaFreeAsync(fix, stream));
+  if (rc == TKBO_OK) TKBO_CUDA_CHECK(cudaGetLastError());
+  return rc;
 }
 
 int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg) {

@@ -78,6 +78,9 @@ struct RffParams {
   int acc_bufs;              // 1 or 2 accumulator buffers of SC columns
   int xa_bufs;               // 1 or 2 buffers for the split candidate rows
   int proj_warps;            // 1 or 2 projection-issuing warps (2 needs an even smem ring depth)
+  int duel_n;                // > 0: the candidates are all ordered pairs [x_i, x_j] of duel_n base points of dimension
+                             // d / 2 held in X (dts.py:31-45), tile = 128 values of i for one j; never materialised
+  unsigned long long* score_fix;   // [S, duel_n] (MODE 2) sum over j of sigmoid(f) in 2^-32 fixed point (deterministic atomics)
   int debug;                 // timing ablations (TKBO_DEBUG): 1 = hi*hi MMA only, 2 = producers skip the cos, 4 = no Theta TMA
   unsigned long long* trace; // optional clock64() event log of CTA 0 ([kTraceEvents][trace_cap]), tools/trace_k1.py
   int trace_cap;
@@ -124,7 +127,7 @@ __device__ __forceinline__ void bf16_split3(float x, uint32_t& b1, uint32_t& b2,
   b3 = __float_as_uint(r2) >> 16;
 }
 
-template <int DT, int MODE /* 0 = argmax, 1 = store F */, int NPG /* producer warp groups: 2 or 3 */>
+template <int DT, int MODE /* 0 = argmax, 1 = store F, 2 = duel soft-Copeland sums */, int NPG /* producer warp groups: 2 or 3 */>
 __global__ void __launch_bounds__(kNumThreadsFor(NPG), 1)
 rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                  const __grid_constant__ CUtensorMap tm_w, const RffParams p) {
@@ -385,14 +388,28 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       const int item = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
       if (item >= n_items) return;
       const int xb = (xa_bufs == 2) ? (j & 1) : 0;
-      long long row = static_cast<long long>(item / n_chunks) * kTileM + q * 32 + lane;
-      if (row >= p.N) row = p.N - 1;                 // clamp: tail rows are masked in the epilogue
+      const int mtile = item / n_chunks;
+      // row of X holding input dimensions [0, dsplit) and the row holding [dsplit, d): the same row for plain
+      // candidates; x_i and x_j for duels (tile = 128 consecutive i of one j)
+      long long row_a, row_b;
+      int dsplit;
+      if (p.duel_n > 0) {
+        const int tpj = (p.duel_n + kTileM - 1) / kTileM;
+        row_a = min(static_cast<long long>(mtile % tpj) * kTileM + q * 32 + lane, static_cast<long long>(p.duel_n) - 1);
+        row_b = mtile / tpj;
+        dsplit = p.d >> 1;
+      } else {
+        row_a = min(static_cast<long long>(mtile) * kTileM + q * 32 + lane, p.N - 1);   // tail rows are masked in the epilogue
+        row_b = row_a;
+        dsplit = p.d;
+      }
+      const int dx = (p.duel_n > 0) ? dsplit : p.d;  // row stride of X
       uint32_t w[kPCols];
 #pragma unroll
       for (int c = 0; c < kPCols; ++c) w[c] = 0u;
 #pragma unroll
       for (int i = 0; i < DT; ++i) {
-        const float x = (i < p.d) ? __ldg(p.X + row * p.d + i) : 0.f;
+        const float x = (i < p.d) ? ((i < dsplit) ? __ldg(p.X + row_a * dx + i) : __ldg(p.X + row_b * dx + (i - dsplit))) : 0.f;
         uint32_t b1, b2, b3;
         bf16_split3(x, b1, b2, b3);
         w[3 * i + 0] = b1 | (b1 << 16);              // k = 6i, 6i+1
@@ -476,12 +493,28 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
                 bestv[jj] = mine;
                 bestrow[jj] = static_cast<uint32_t>(row0) + (__ffs(minehit) - 1);
               }
-          } else {
+          } else if constexpr (MODE == 1) {
             if (row_ok) {
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
                 const int s = s_base + j * 32 + c;
                 if (s < p.S) p.out_F[static_cast<long long>(s) * p.ldf + row] = __uint_as_float(v[c]) * __ldg(p.unscale + s);
+              }
+            }
+          } else {
+            // soft-Copeland partial sums (dts.py:94-96): this tile holds f_s([x_i, x_j]) for 128 values of i and one j;
+            // sigmoid in fp32, summed over j in 2^-32 fixed point so that the atomics commute exactly
+            const int tpj = (p.duel_n + kTileM - 1) / kTileM;
+            const int i = (mtile % tpj) * kTileM + q * 32 + lane;
+            if (i < p.duel_n) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const int s = s_base + j * 32 + c;
+                if (s < p.S) {
+                  const float f = __uint_as_float(v[c]) * __ldg(p.unscale + s);
+                  const float sg = __frcp_rn(1.f + exp2f(-1.4426950408889634f * f));
+                  atomicAdd(p.score_fix + static_cast<long long>(s) * p.duel_n + i, __float2ull_rn(sg * 4294967296.f));
+                }
               }
             }
           }

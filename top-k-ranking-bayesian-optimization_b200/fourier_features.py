@@ -356,6 +356,21 @@ class SharedBasis:
                                                    nat.current_stream_ptr(self.device)), "tkbo_unpack_argmax_key")
         return val, idx
 
+    def duel_copeland(self, X_base, scores=True):
+        """Dueling-Thompson soft-Copeland for all S samples at once: the basis lives on duels [x, x'] (d = 2 d_obj),
+        X_base (n, d_obj) are the base points; returns (score[S, n] float32 or None, winner[S] int64) CUDA tensors with
+        score[s, i] = mean_j sigmoid(f_s([x_i, x_j])) (dts.py:94-96).  The n^2 duels are generated inside the kernel."""
+        torch = self._torch
+        Xb = _f32(X_base, self.device)
+        assert Xb.dim() == 2 and 2 * Xb.shape[1] == self.d, "base points must be (n, d / 2)"
+        n = Xb.shape[0]
+        score = torch.empty((self.S, n), dtype=torch.float32, device=self.device) if scores else None
+        win = torch.empty(self.S, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().tkbo_rff_duel_copeland(self._h, self._basis, nat.ptr(Xb), n,
+                                                   nat.ptr(score) if scores else None, nat.ptr(win),
+                                                   nat.current_stream_ptr(self.device)), "tkbo_rff_duel_copeland")
+        return score, win
+
     def eval(self, X, out=None):
         """(S, N) float32 CUDA tensor, F[s, n] = f_s(X[n])."""
         torch = self._torch
