@@ -493,6 +493,25 @@ def test_duel_copeland_fused_matches_oracle_and_unfused_path(pbo, n, dobj, D, S)
     np.testing.assert_allclose(score[0].cpu().numpy(), sc0.numpy(), rtol=2e-5, atol=1e-6)
 
 
+def test_duel_copeland_shards_add_up_exactly(pbo):
+    """j-shards of the duels (the multi-GPU decomposition) summed as integers == one call, bit for bit."""
+    rng = np.random.default_rng(77)
+    n, dobj, D, S = 200, 2, 128, 24
+    Xb = rng.uniform(0.0, 1.0, size=(n, dobj)).astype(np.float32)
+    basis = pbo.fourier_features.SharedBasis(rng.standard_normal((D, 2 * dobj)) / 0.5, rng.uniform(0, 2 * np.pi, D),
+                                             rng.standard_normal((D, S)), device="cuda:0")
+    score, win = basis.duel_copeland(Xb)
+    fix = None
+    for r in range(3):
+        lo, hi = pbo.distributed.duel_shard(n, r, 3)
+        part = basis.duel_copeland_partial(Xb, lo, hi)
+        fix = part if fix is None else fix + part
+    s2, w2 = basis.copeland_finish(fix)
+    assert torch.equal(score, s2) and torch.equal(win, w2)
+    s3, w3 = pbo.distributed.sharded_duel_copeland(basis, Xb)            # no process group: single shard
+    assert torch.equal(score, s3) and torch.equal(win, w3)
+
+
 def test_dts_thompson_copeland_winners_signature(pbo):
     dts = pbo.acquisitions.dts
     mdl = pbo.model.synthetic_model(9, 4, 0.0, 1.0, [0.25, 0.4, 0.25, 0.4], seed=5, product=True)

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "tkbo_rff_argmax": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p]),
     "tkbo_rff_argmax_key": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "tkbo_rff_duel_copeland": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p]),
+    "tkbo_rff_duel_copeland_partial": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "tkbo_copeland_finish": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
     "tkbo_unpack_argmax_key": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p]),
     "tkbo_rff_eval": (c_i, [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p]),
     "tkbo_merge_argmax": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),

@@ -24,6 +24,10 @@ int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, 
                    cudaStream_t stream);
 int rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t bs, const float* Xbase, int n, float* out_score, int64_t* out_argmax,
                       cudaStream_t stream);
+int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xbase, int n, int j_begin, int j_end,
+                              uint64_t* fix, cudaStream_t stream);
+int copeland_finish(tkbo_handle_t h, const uint64_t* fix, int S, int n, float* out_score, int64_t* out_argmax,
+                    cudaStream_t stream);
 int unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, cudaStream_t stream);
 int merge_unpack_keys(tkbo_handle_t h, const int64_t* keys, int G, int S, float* out_val, int64_t* out_idx,
                       cudaStream_t stream);
@@ -190,6 +194,16 @@ int tkbo_rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t basis, const float* Xba
                            int64_t* out_argmax, void* stream) {
   TKBO_ENTER(h);
   return rff_duel_copeland(h, basis, Xbase, n, out_score, out_argmax, as_stream(stream));
+}
+int tkbo_rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t basis, const float* Xbase, int n, int j_begin, int j_end,
+                                   uint64_t* fix, void* stream) {
+  TKBO_ENTER(h);
+  return rff_duel_copeland_partial(h, basis, Xbase, n, j_begin, j_end, fix, as_stream(stream));
+}
+int tkbo_copeland_finish(tkbo_handle_t h, const uint64_t* fix, int S, int n, float* out_score, int64_t* out_argmax,
+                         void* stream) {
+  TKBO_ENTER(h);
+  return copeland_finish(h, fix, S, n, out_score, out_argmax, as_stream(stream));
 }
 int tkbo_unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, void* stream) {
   TKBO_ENTER(h);

@@ -469,7 +469,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->X = X; p->unscale = bs->unscale; p->packed = bs->packed;
   p->done_counter = h->done_counter;
   p->out_val = nullptr; p->out_idx = nullptr; p->out_key = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
-  p->duel_n = 0; p->score_fix = nullptr;
+  p->duel_n = 0; p->duel_j0 = 0; p->duel_nj = 0; p->score_fix = nullptr;
   p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
   p->n_slabs = bs->Dpad / kSlabK;
   const int64_t mt = (N + kTileM - 1) / kTileM;
@@ -566,7 +566,7 @@ int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float*
   return dispatch_fused<1>(h, bs, p, grid, stream);
 }
 
-// score[s, i] = fix[s, i] / (2^32 n), argmax over i (lowest index on ties)                 [dts.py:94-97]
+// score[s, i] = fix[s, i] / (2^24 n), argmax over i (lowest index on ties)                 [dts.py:94-97]
 __global__ void copeland_finish_kernel(const unsigned long long* __restrict__ fix, int n, float* __restrict__ score,
                                        long long* __restrict__ out_arg) {
   const int s = blockIdx.x;
@@ -574,7 +574,7 @@ __global__ void copeland_finish_kernel(const unsigned long long* __restrict__ fi
   __shared__ int bi[256];
   unsigned long long best = 0ull;
   int idx = 0x7fffffff;
-  const double inv = 1.0 / (4294967296.0 * static_cast<double>(n));
+  const double inv = 1.0 / (16777216.0 * static_cast<double>(n));
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned long long v = fix[static_cast<size_t>(s) * n + i];
     if (score) score[static_cast<size_t>(s) * n + i] = static_cast<float>(static_cast<double>(v) * inv);
@@ -595,17 +595,20 @@ __global__ void copeland_finish_kernel(const unsigned long long* __restrict__ fi
   if (threadIdx.x == 0 && out_arg) out_arg[s] = bi[0];
 }
 
-// Dueling-Thompson soft-Copeland over all ordered pairs of n base points, duels generated on the fly.
-int rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t bs, const float* Xbase, int n, float* out_score, int64_t* out_argmax,
-                      cudaStream_t stream) {
-  TKBO_REQUIRE(h && bs && Xbase, "null pointer");
+// Dueling-Thompson soft-Copeland sums over the ordered pairs (i, j), j in [j_begin, j_end), of n base points; the duels are
+// generated on the fly and fix[s, i] += sum_j round(sigmoid(f_s([x_i, x_j])) * 2^24) (the caller zeroes fix; shards of j held by
+// different ranks add up exactly with an integer all-reduce).
+int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xbase, int n, int j_begin, int j_end,
+                              uint64_t* fix, cudaStream_t stream) {
+  TKBO_REQUIRE(h && bs && Xbase && fix, "null pointer");
   TKBO_REQUIRE(bs->is_set, "basis has no data: call tkbo_rff_basis_set first");
   TKBO_REQUIRE(bs->d % 2 == 0, "duel mode needs an even input dimension d = 2 d_obj");
   TKBO_REQUIRE(n >= 1 && n <= (1 << 20), "n must be in [1, 2^20]");
-  TKBO_REQUIRE(out_score || out_argmax, "nothing to compute");
+  TKBO_REQUIRE(0 <= j_begin && j_begin <= j_end && j_end <= n, "need 0 <= j_begin <= j_end <= n");
+  if (j_begin == j_end) return TKBO_OK;
   RffParams p;
-  const int64_t tpj = (n + kTileM - 1) / kTileM;
-  const int64_t mt = static_cast<int64_t>(n) * tpj;
+  const int64_t tpi = (j_end - j_begin + kTileM - 1) / kTileM;       // tiles per i: 128 consecutive j each
+  const int64_t mt = static_cast<int64_t>(n) * tpi;
   TKBO_REQUIRE(mt * bs->n_chunks < (int64_t(1) << 31), "too many work items");
   p.X = Xbase; p.unscale = bs->unscale; p.packed = bs->packed; p.done_counter = h->done_counter;
   p.out_val = nullptr; p.out_idx = nullptr; p.out_key = nullptr; p.out_F = nullptr; p.ldf = 0; p.idx_offset = 0;
@@ -613,22 +616,36 @@ int rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t bs, const float* Xbase, int 
   p.n_slabs = bs->Dpad / kSlabK; p.n_mtiles = static_cast<int>(mt);
   p.stages = bs->stages; p.ring = bs->ring; p.acc_bufs = bs->acc_bufs; p.xa_bufs = bs->xa_bufs;
   p.proj_warps = bs->proj_warps;
-  p.duel_n = n;
+  p.duel_n = n; p.duel_j0 = j_begin; p.duel_nj = j_end - j_begin;
+  p.score_fix = reinterpret_cast<unsigned long long*>(fix);
   p.debug = 0;
   p.trace = nullptr; p.trace_cap = 0;
-  unsigned long long* fix = nullptr;
-  const size_t bytes = sizeof(unsigned long long) * static_cast<size_t>(bs->S) * n;
+  const int grid = static_cast<int>(std::min<int64_t>(h->sm_count, mt * bs->n_chunks));
+  return dispatch_fused<2>(h, bs, p, grid, stream);
+}
+
+int copeland_finish(tkbo_handle_t h, const uint64_t* fix, int S, int n, float* out_score, int64_t* out_argmax,
+                    cudaStream_t stream) {
+  TKBO_REQUIRE(h && fix && S >= 1 && n >= 1 && (out_score || out_argmax), "bad copeland_finish arguments");
+  copeland_finish_kernel<<<S, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(fix), n, out_score,
+                                                reinterpret_cast<long long*>(out_argmax));
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
+int rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t bs, const float* Xbase, int n, float* out_score, int64_t* out_argmax,
+                      cudaStream_t stream) {
+  TKBO_REQUIRE(h && bs, "null pointer");
+  TKBO_REQUIRE(out_score || out_argmax, "nothing to compute");
+  TKBO_REQUIRE(n >= 1 && n <= (1 << 20), "n must be in [1, 2^20]");
+  uint64_t* fix = nullptr;
+  const size_t bytes = sizeof(uint64_t) * static_cast<size_t>(bs->S) * n;
   TKBO_CUDA_CHECK(cudaMallocAsync(&fix, bytes, stream));
   TKBO_CUDA_CHECK(cudaMemsetAsync(fix, 0, bytes, stream));
-  p.score_fix = fix;
-  const int grid = static_cast<int>(std::min<int64_t>(h->sm_count, mt * bs->n_chunks));
-  int rc = dispatch_fused<2>(h, bs, p, grid, stream);
-  if (rc == TKBO_OK) {
-    copeland_finish_kernel<<<bs->S, 256, 0, stream>>>(fix, n, out_score, reinterpret_cast<long long*>(out_argmax));
-    h->launches += 1;
-  }
+  int rc = rff_duel_copeland_partial(h, bs, Xbase, n, 0, n, fix, stream);
+  if (rc == TKBO_OK) rc = copeland_finish(h, fix, bs->S, n, out_score, out_argmax, stream);
   TKBO_CUDA_CHECK(cudaFreeAsync(fix, stream));
-  if (rc == TKBO_OK) TKBO_CUDA_CHECK(cudaGetLastError());
   return rc;
 }
 

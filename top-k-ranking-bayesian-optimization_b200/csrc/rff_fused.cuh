@@ -78,9 +78,10 @@ struct RffParams {
   int acc_bufs;              // 1 or 2 accumulator buffers of SC columns
   int xa_bufs;               // 1 or 2 buffers for the split candidate rows
   int proj_warps;            // 1 or 2 projection-issuing warps (2 needs an even smem ring depth)
-  int duel_n;                // > 0: the candidates are all ordered pairs [x_i, x_j] of duel_n base points of dimension
-                             // d / 2 held in X (dts.py:31-45), tile = 128 values of i for one j; never materialised
-  unsigned long long* score_fix;   // [S, duel_n] (MODE 2) sum over j of sigmoid(f) in 2^-32 fixed point (deterministic atomics)
+  int duel_n;                // > 0: the candidates are the ordered pairs [x_i, x_j] of duel_n base points of dimension d / 2
+                             // held in X (dts.py:31-45); a tile = one i and 128 consecutive j; never materialised
+  int duel_j0, duel_nj;      // this launch's shard of the second argument: j in [duel_j0, duel_j0 + duel_nj)
+  unsigned long long* score_fix;   // [S, duel_n] (MODE 2) sum over j of sigmoid(f) in 2^-24 fixed point (deterministic atomics)
   int debug;                 // timing ablations (TKBO_DEBUG): 1 = hi*hi MMA only, 2 = producers skip the cos, 4 = no Theta TMA
   unsigned long long* trace; // optional clock64() event log of CTA 0 ([kTraceEvents][trace_cap]), tools/trace_k1.py
   int trace_cap;
@@ -394,9 +395,9 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       long long row_a, row_b;
       int dsplit;
       if (p.duel_n > 0) {
-        const int tpj = (p.duel_n + kTileM - 1) / kTileM;
-        row_a = min(static_cast<long long>(mtile % tpj) * kTileM + q * 32 + lane, static_cast<long long>(p.duel_n) - 1);
-        row_b = mtile / tpj;
+        const int tpi = (p.duel_nj + kTileM - 1) / kTileM;
+        row_a = mtile / tpi;
+        row_b = p.duel_j0 + min((mtile % tpi) * kTileM + q * 32 + lane, p.duel_nj - 1);
         dsplit = p.d >> 1;
       } else {
         row_a = min(static_cast<long long>(mtile) * kTileM + q * 32 + lane, p.N - 1);   // tail rows are masked in the epilogue
@@ -502,21 +503,27 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
               }
             }
           } else {
-            // soft-Copeland partial sums (dts.py:94-96): this tile holds f_s([x_i, x_j]) for 128 values of i and one j;
-            // sigmoid in fp32, summed over j in 2^-32 fixed point so that the atomics commute exactly
-            const int tpj = (p.duel_n + kTileM - 1) / kTileM;
-            const int i = (mtile % tpj) * kTileM + q * 32 + lane;
-            if (i < p.duel_n) {
+            // soft-Copeland partial sums (dts.py:94-96): this tile holds f_s([x_i, x_j]) for one i and 128 values of j.
+            // sigmoid in fp32, rounded to 2^-24 fixed point, summed over the warp's 32 rows with an integer redux and
+            // added to score_fix[s, i] with one 64-bit atomic per (warp, sample): integer sums commute exactly.
+            const int tpi = (p.duel_nj + kTileM - 1) / kTileM;
+            const int i_row = mtile / tpi;
+            const bool j_ok = (mtile % tpi) * kTileM + q * 32 + lane < p.duel_nj;
+            unsigned mine = 0u;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const int s = s_base + j * 32 + c;
-                if (s < p.S) {
-                  const float f = __uint_as_float(v[c]) * __ldg(p.unscale + s);
-                  const float sg = __frcp_rn(1.f + exp2f(-1.4426950408889634f * f));
-                  atomicAdd(p.score_fix + static_cast<long long>(s) * p.duel_n + i, __float2ull_rn(sg * 4294967296.f));
-                }
-              }
+            for (int c = 0; c < 32; ++c) {
+              const int s = min(s_base + j * 32 + c, p.S - 1);
+              const float f = __uint_as_float(v[c]) * __ldg(p.unscale + s);
+              float e, sg;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * f));
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + e));
+              const unsigned u = j_ok ? __float2uint_rn(sg * 16777216.f) : 0u;
+              const unsigned r = __reduce_add_sync(0xffffffffu, u);
+              if (lane == c) mine = r;
             }
+            const int s = s_base + j * 32 + lane;
+            if (s < p.S)
+              atomicAdd(p.score_fix + static_cast<long long>(s) * p.duel_n + i_row, static_cast<unsigned long long>(mine));
           }
         }
       }

@@ -85,6 +85,28 @@ def sharded_argmax(basis, X_local, idx_offset, group=None):
     return allgather_argmax(val, idx, group=group)
 
 
+def duel_shard(n, rank, world_size):
+    """[j_begin, j_end) of the second duel argument x_j handled by ``rank`` (every rank keeps all n values of i)."""
+    per, rem = divmod(n, world_size)
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+def sharded_duel_copeland(basis, X_base, group=None, scores=True):
+    """Dueling-Thompson soft-Copeland with the n^2 duels split over ranks along j: each rank adds its shard's
+    fixed-point sigmoid sums (integers, so the reduction order cannot change the result), ONE all_reduce(SUM) over
+    int64 [S, n] combines them and every rank finishes to (score[S, n], winner[S])."""
+    import torch.distributed as dist
+    n = X_base.shape[0]
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        lo, hi = duel_shard(n, dist.get_rank(group), dist.get_world_size(group))
+        fix = basis.duel_copeland_partial(X_base, lo, hi)
+        dist.all_reduce(fix, op=dist.ReduceOp.SUM, group=group)
+    else:
+        fix = basis.duel_copeland_partial(X_base, 0, n)
+    return basis.copeland_finish(fix, scores=scores)
+
+
 def broadcast_basis_arrays(W, b, Theta, src=0, group=None, device=None):
     """Replicate the host-drawn basis from rank ``src`` (once per BO iteration; <= 34 MB at the c4 shape)."""
     import torch

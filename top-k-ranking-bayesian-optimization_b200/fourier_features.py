@@ -371,6 +371,31 @@ class SharedBasis:
                                                    nat.current_stream_ptr(self.device)), "tkbo_rff_duel_copeland")
         return score, win
 
+    def duel_copeland_partial(self, X_base, j_begin, j_end, fix=None):
+        """Shard of duel_copeland: adds the j in [j_begin, j_end) part of the fixed-point sigmoid sums into ``fix``
+        ((S, n) int64 CUDA tensor, created zeroed when None) and returns it; see distributed.sharded_duel_copeland."""
+        torch = self._torch
+        Xb = _f32(X_base, self.device)
+        assert Xb.dim() == 2 and 2 * Xb.shape[1] == self.d, "base points must be (n, d / 2)"
+        n = Xb.shape[0]
+        if fix is None:
+            fix = torch.zeros((self.S, n), dtype=torch.int64, device=self.device)
+        assert fix.shape == (self.S, n) and fix.dtype == torch.int64 and fix.is_contiguous()
+        nat.check(nat.lib().tkbo_rff_duel_copeland_partial(self._h, self._basis, nat.ptr(Xb), n, int(j_begin), int(j_end),
+                                                           nat.ptr(fix), nat.current_stream_ptr(self.device)),
+                  "tkbo_rff_duel_copeland_partial")
+        return fix
+
+    def copeland_finish(self, fix, scores=True):
+        """(score[S, n] float32 or None, winner[S] int64) from complete fixed-point sums."""
+        torch = self._torch
+        S, n = fix.shape
+        score = torch.empty((S, n), dtype=torch.float32, device=self.device) if scores else None
+        win = torch.empty(S, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().tkbo_copeland_finish(self._h, nat.ptr(fix), int(S), int(n), nat.ptr(score) if scores else None,
+                                                 nat.ptr(win), nat.current_stream_ptr(self.device)), "tkbo_copeland_finish")
+        return score, win
+
     def eval(self, X, out=None):
         """(S, N) float32 CUDA tensor, F[s, n] = f_s(X[n])."""
         torch = self._torch
