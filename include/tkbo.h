@@ -131,6 +131,11 @@ int tkbo_rff_ascent_batched(tkbo_handle_t h, double* X, const double* W, const d
 int tkbo_mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, int S, int64_t Q,
                    int C, int M, const int32_t* perms, int P, int k, int mode, double* out_mi,
                    void* stream);
+/* Top-1 MPES with an indifference outcome (acquisitions/indiff_pes.py:15-130): C + 1 observation types,
+ * P(i) = e^{f_i} / (e^{f_i} + sum_{j != i} e^{f_j + threshold}), P(none) = 1 - sum_i P(i); same inputs / output as
+ * tkbo_mpes_topk, maximisers that win no sample are dropped (indiff_pes.py:68-76).  C <= 8. */
+int tkbo_mpes_indiff(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, int S, int64_t Q, int C, int M,
+                     double threshold, double* out_mi, void* stream);
 /* out[s] = argmax_m fstar[s, m] (lowest index), fstar [S, M] float32 — rank_pes.py:39 / pes.py:108. */
 int tkbo_argmax_rows(tkbo_handle_t h, const float* fstar, int S, int M, int32_t* out, void* stream);
 

@@ -201,3 +201,38 @@ def dts_sample_f(W, b, query_points, q_mu, q_sqrt, z, combs):
     phi_y = fourier_features(np.asarray(query_points)[None], W, b)
     theta = sample_theta_variational(phi_y, q_mu, q_sqrt, z=z)
     return np.squeeze(phi @ theta, axis=0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# top-1 MPES with an indifference outcome (acquisitions/indiff_pes.py)
+# ---------------------------------------------------------------------------------------------------
+def indiff_log_likelihood(fx, normalizer=None, indifference_threshold=0.0):
+    """(C + 1, Q): log (1/normalizer) sum_s P_s(z), z = "choice i is the most preferred" (i < C) or "none".
+    fx (S, Q, C).                                                                       [indiff_pes.py:95-130]"""
+    fx = np.asarray(fx, dtype=np.float64)
+    S, Q, C = fx.shape
+    normalizer = S if normalizer is None else normalizer
+    indiff = (1.0 - np.eye(C)) * indifference_threshold                                 # :105-106
+    base = fx[..., :, None] + indiff                                                    # :108, :111 (S, Q, C, C)
+    ll_pref = fx - _logsumexp(base, axis=-2)                                            # :110-113
+    p_ind = np.clip(1.0 - np.exp(ll_pref).sum(axis=-1, keepdims=True), 1e-100, 1.0 - 1e-100)   # :116-117
+    ll = np.concatenate([ll_pref, np.log(p_ind)], axis=-1)                              # :121
+    return _logsumexp(ll - np.log(normalizer), axis=0).T                                # :126-129
+
+
+def indiff_mpes_from_samples(fchi, fstar, indifference_threshold=0.1):
+    """MI (Q,) of indiff_pes.I_batch given the joint samples fchi (S, Q, C), fstar (S, M).  [indiff_pes.py:41-92]"""
+    fchi = np.asarray(fchi, dtype=np.float64)
+    fstar = np.asarray(fstar, dtype=np.float64)
+    S, M = fstar.shape
+    arg = np.argmax(fstar, axis=1)                                                      # :42
+    count = np.bincount(arg, minlength=M)                                               # :43 (minlength: see rank_pes note)
+    p_xstar = count / count.sum()                                                       # :44
+    log_p_obs = indiff_log_likelihood(fchi, S, indifference_threshold)                  # :48-50
+    mi = np.zeros(fchi.shape[1])
+    for m in range(M):
+        if p_xstar[m] <= 0:                                                             # :58, :68-76
+            continue
+        ll = indiff_log_likelihood(fchi[arg == m], S, indifference_threshold)           # :60-65 (C + 1, Q)
+        mi += np.sum(np.exp(ll) * (ll - np.log(p_xstar[m]) - log_p_obs), axis=0)        # :80-90
+    return mi

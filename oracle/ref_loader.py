@@ -35,7 +35,7 @@ def _load(modname, relpath, package):
 def load():
     """-> namespace(fourier_features, pes, rank_pes, dts) of reference modules.
 
-    ``rank_pes.py`` needs NumPy/SciPy only.  The other three import tensorflow / tfp / gpflow at
+    ``rank_pes.py`` and ``indiff_pes.py`` need NumPy/SciPy only.  The other three import tensorflow / tfp / gpflow at
     module scope, which resolve to ``tf_shim`` (the package ``__init__`` chain is bypassed because it
     pulls in the training code and EI, which are outside the hot path)."""
     if not available():
@@ -45,6 +45,7 @@ def load():
         return types.SimpleNamespace(fourier_features=m[_PKG + ".fourier_features"],
                                      pes=m[_PKG + ".acquisitions.pes"],
                                      rank_pes=m[_PKG + ".acquisitions.rank_pes"],
+                                     indiff_pes=m[_PKG + ".acquisitions.indiff_pes"],
                                      dts=m[_PKG + ".acquisitions.dts"])
     tf_shim.install()
     pkg = types.ModuleType(_PKG)
@@ -56,6 +57,7 @@ def load():
     ff = _load(_PKG + ".fourier_features", "fourier_features.py", _PKG)
     pkg.fourier_features = ff
     rank_pes = _load(_PKG + ".acquisitions.rank_pes", "acquisitions/rank_pes.py", _PKG + ".acquisitions")
+    indiff_pes = _load(_PKG + ".acquisitions.indiff_pes", "acquisitions/indiff_pes.py", _PKG + ".acquisitions")
     pes = _load(_PKG + ".acquisitions.pes", "acquisitions/pes.py", _PKG + ".acquisitions")
     dts = _load(_PKG + ".acquisitions.dts", "acquisitions/dts.py", _PKG + ".acquisitions")   # `from .. import fourier_features`
-    return types.SimpleNamespace(fourier_features=ff, pes=pes, rank_pes=rank_pes, dts=dts)
+    return types.SimpleNamespace(fourier_features=ff, pes=pes, rank_pes=rank_pes, indiff_pes=indiff_pes, dts=dts)

@@ -122,6 +122,27 @@ def golden_rank_pes(ref):
     np.savez_compressed(os.path.join(OUT, "rank_pes.npz"), **out)
 
 
+def golden_indiff_pes(ref):
+    """indiff_pes.I_batch as shipped (indiff_pes.py:15-92) on fixed fp32-representable samples."""
+    out = {}
+    for tag, (S, Q, C, M, thr) in {"c3": (400, 16, 3, 8, 0.1), "c5": (256, 10, 5, 12, 0.5), "c2_t0": (300, 12, 2, 6, 0.0)}.items():
+        rng = np.random.default_rng({"c3": 11, "c5": 12, "c2_t0": 13}[tag])
+        d = 4
+        chi = rng.uniform(0, 1, size=(Q, C, d))
+        x_star = rng.uniform(0, 1, size=(M, d))
+        basis = rng.standard_normal((Q * C + M, 5))
+        fs = (rng.standard_normal((S, 5)) @ basis.T + 0.3 * rng.standard_normal((S, Q * C + M)))
+        # indiff_pes.py:43 also calls np.bincount without minlength: let the last maximiser win sample 0
+        fs[0, Q * C + M - 1] = fs[0, Q * C:].max() + 1.0
+        fs = fs.astype(np.float32).astype(np.float64)
+        model = tf_shim.StubModel(fixed_samples=fs)
+        mi = ref.indiff_pes.I_batch(chi, x_star, model, num_samples=S, indifference_threshold=thr)
+        ll = ref.indiff_pes.get_log_likelihood(fs[:, :Q * C].reshape(S, Q, C), normalizer=S, indifference_threshold=thr)
+        out.update({f"{tag}_fsample_all": fs.astype(np.float32), f"{tag}_mi": mi, f"{tag}_loglik": ll,
+                    f"{tag}_meta": np.array([S, Q, C, M]), f"{tag}_threshold": np.array(thr)})
+    np.savez_compressed(os.path.join(OUT, "indiff_pes.npz"), **out)
+
+
 def golden_pes(ref):
     """pes.I / pes.I_batch (pes.py:92-132) with one fixed sample matrix per query. c1 sizes:
     S=1000, M=20, C=2 (MPES_Forr.py:70-79) plus a C=3 case."""
@@ -188,6 +209,7 @@ def main():
     golden_fourier_features(ref)
     golden_sample_maximizers(ref)
     golden_rank_pes(ref)
+    golden_indiff_pes(ref)
     golden_pes(ref)
     golden_dts(ref)
     for f in sorted(os.listdir(OUT)):

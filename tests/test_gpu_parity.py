@@ -401,6 +401,37 @@ def test_rank_pes_properties(pbo):
         assert abs(p - mi1[q]) < 1e-5
 
 
+@pytest.mark.parametrize("tag", ["c3", "c5", "c2_t0"])
+def test_indiff_pes_matches_reference_golden(pbo, golden, tag):
+    """indiff_pes.I_batch (tkbo_mpes_indiff) on the samples the reference consumed -> the reference's MI."""
+    g = golden("indiff_pes.npz")
+    S, Q, C, M = (int(v) for v in g[f"{tag}_meta"])
+    thr = float(g[f"{tag}_threshold"])
+    fs = g[f"{tag}_fsample_all"]
+    rng = np.random.default_rng(0)
+    chi, x_star = rng.uniform(0, 1, (Q, C, 4)), rng.uniform(0, 1, (M, 4))          # only their shapes matter with f_samples
+    mi = pbo.acquisitions.indiff_pes.I_batch(chi, x_star, None, num_samples=S, indifference_threshold=thr,
+                                             f_samples=fs, device="cuda:0")
+    ref = g[f"{tag}_mi"]
+    assert mi.dtype == torch.float64 and tuple(mi.shape) == (Q,)
+    np.testing.assert_allclose(mi.numpy(), ref, rtol=VAL_RTOL, atol=2e-6)
+    ll = pbo.acquisitions.indiff_pes.get_log_likelihood(fs[:, :Q * C].reshape(S, Q, C), S, thr, device="cuda:0")
+    rows = C + 1 if thr > 0 else C            # threshold 0: P(none) is pure rounding noise in the reference as well
+    np.testing.assert_allclose(ll.numpy()[:rows], g[f"{tag}_loglik"][:rows], rtol=1e-9, atol=1e-10)
+
+
+def test_indiff_pes_large_batch_matches_oracle(pbo):
+    rng = np.random.default_rng(21)
+    S, Q, C, M = 512, 3000, 4, 10
+    basis = rng.standard_normal((Q * C + M, 6))
+    fs = (rng.standard_normal((S, 6)) @ basis.T + 0.3 * rng.standard_normal((S, Q * C + M))).astype(np.float32)
+    mi = pbo.acquisitions.indiff_pes.I_batch(np.zeros((Q, C, 2)), np.zeros((M, 2)), None, num_samples=S,
+                                             indifference_threshold=0.2, f_samples=fs, device="cuda:0").numpy()
+    ref = mpes_oracle.indiff_mpes_from_samples(fs[:, :Q * C].reshape(S, Q, C).astype(np.float64), fs[:, Q * C:].astype(np.float64), 0.2)
+    np.testing.assert_allclose(mi, ref, rtol=VAL_RTOL, atol=2e-6)
+    assert mi.min() > -1e-6
+
+
 @pytest.mark.parametrize("tag", ["c1", "c3"])
 def test_pes_I_matches_reference_golden(pbo, golden, tag):
     """pes.I / pes.I_batch executed from the reference source (golden) vs K2 in PES mode, c1 sizes S=1000, M=20, C=2."""

@@ -51,6 +51,20 @@ def test_rank_mpes(golden, tag):
     assert np.all(ref > -1e-12)                          # MI >= 0
 
 
+@pytest.mark.parametrize("tag", ["c3", "c5", "c2_t0"])
+def test_indiff_mpes(golden, tag):
+    """Restatement of indiff_pes.I_batch / get_log_likelihood against the reference's own output."""
+    g = golden("indiff_pes.npz")
+    S, Q, C, M = (int(v) for v in g[f"{tag}_meta"])
+    thr = float(g[f"{tag}_threshold"])
+    fs = g[f"{tag}_fsample_all"].astype(np.float64)
+    fchi, fstar = fs[:, :Q * C].reshape(S, Q, C), fs[:, Q * C:]
+    ll, ll_ref = mpes_oracle.indiff_log_likelihood(fchi, S, thr), g[f"{tag}_loglik"]
+    rows = C + 1 if thr > 0 else C            # threshold 0: P(none) = 1 - sum_i P(i) is pure rounding noise (~1e-16)
+    np.testing.assert_allclose(ll[:rows], ll_ref[:rows], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(mpes_oracle.indiff_mpes_from_samples(fchi, fstar, thr), g[f"{tag}_mi"], rtol=1e-9, atol=1e-12)
+
+
 def test_permutation_tables(golden):
     g = golden("rank_pes.npz")
     np.testing.assert_array_equal(mpes_oracle.all_permutations_k_in_n(5, 3), g["perms_5_3"])

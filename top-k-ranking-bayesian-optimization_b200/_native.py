@@ -52,6 +52,7 @@ _SIGNATURES = {
     "tkbo_rff_ascent_batched": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, c_i, c_d, c_d, c_d,
                                       ctypes.POINTER(c_i), c_p]),
     "tkbo_mpes_topk": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "tkbo_mpes_indiff": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i, c_i, c_d, c_p, c_p]),
     "tkbo_argmax_rows": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p]),
     "tkbo_soft_copeland": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p]),
 }

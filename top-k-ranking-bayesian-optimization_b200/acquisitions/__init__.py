@@ -1,3 +1,3 @@
 """Acquisition functions on the hot path (same sub-module names as the reference's acquisitions/__init__.py:1;
-``ei`` and ``indiff_pes`` are outside this package's scope)."""
-from . import pes, dts, rank_pes  # noqa: F401
+``ei`` is outside this package's scope)."""
+from . import pes, dts, rank_pes, indiff_pes  # noqa: F401

@@ -42,6 +42,8 @@ int rff_features_batched(tkbo_handle_t h, const double* X, const double* W, cons
                          int d, double* out_phi, cudaStream_t stream);
 int mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, int S, int64_t Q, int C, int M,
               const int32_t* perms, int P, int k, int mode, double* out_mi, cudaStream_t stream);
+int mpes_indiff(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, int S, int64_t Q, int C, int M,
+                double threshold, double* out_mi, cudaStream_t stream);
 int argmax_rows(tkbo_handle_t h, const float* fstar, int S, int M, int32_t* out, cudaStream_t stream);
 int soft_copeland(tkbo_handle_t h, const float* f, int n, float* out_score, int64_t* out_argmax, cudaStream_t stream);
 
@@ -321,6 +323,11 @@ int tkbo_mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argm
                    const int32_t* perms, int P, int k, int mode, double* out_mi, void* stream) {
   TKBO_ENTER(h);
   return mpes_topk(h, fchi, fstar_argmax, S, Q, C, M, perms, P, k, mode, out_mi, as_stream(stream));
+}
+int tkbo_mpes_indiff(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, int S, int64_t Q, int C, int M,
+                     double threshold, double* out_mi, void* stream) {
+  TKBO_ENTER(h);
+  return mpes_indiff(h, fchi, fstar_argmax, S, Q, C, M, threshold, out_mi, as_stream(stream));
 }
 int tkbo_argmax_rows(tkbo_handle_t h, const float* fstar, int S, int M, int32_t* out, void* stream) {
   TKBO_ENTER(h);

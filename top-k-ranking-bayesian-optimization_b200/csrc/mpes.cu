@@ -367,6 +367,70 @@ mpes_table_kernel(const float* __restrict__ fchi, const int* __restrict__ order,
 }
 
 // ------------------------------------------------------------------------------------------------
+// top-1 MPES with an indifference outcome (acquisitions/indiff_pes.py:15-130): C + 1 observation types,
+//   P(i) = e^{f_i} / (e^{f_i} + sum_{j != i} e^{f_j + t}),   P(none) = clip(1 - sum_i P(i))        [:107-118]
+// same grouped Monte-Carlo MI as rank_pes (:44-92).  One thread per query, fp32 probabilities summed per group,
+// fp64 fold (C + 1 <= 9 logs per group).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+mpes_indiff_kernel(const float* __restrict__ fchi, const int* __restrict__ order, const int* __restrict__ group_start,
+                   int S, long long Q, int C, int M, float tau /* e^threshold */, double* __restrict__ out_mi) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const float* base = fchi + q * C;
+  const long long rowstride = Q * C;
+  const double invS = 1.0 / static_cast<double>(S);
+  float acc[kGenMaxC + 1], tot[kGenMaxC + 1];
+#pragma unroll
+  for (int z = 0; z <= kGenMaxC; ++z) { acc[z] = 0.f; tot[z] = 0.f; }
+  double mi = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const int lo = group_start[m], hi = group_start[m + 1];
+    if (hi == lo) continue;                                // indiff_pes.py:68-76 drops maximisers that win no sample
+    for (int i = lo; i < hi; ++i) {
+      const float* r = base + static_cast<long long>(order[i]) * rowstride;
+      float e[kGenMaxC];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kGenMaxC; ++c)
+        if (c < C) { e[c] = __ldg(r + c); mx = fmaxf(mx, e[c]); }
+      float T = 0.f;
+#pragma unroll
+      for (int c = 0; c < kGenMaxC; ++c)
+        if (c < C) { e[c] = __expf(e[c] - mx); T += e[c]; }
+      float psum = 0.f;
+#pragma unroll
+      for (int c = 0; c < kGenMaxC; ++c)
+        if (c < C) {
+          const float pc = e[c] / (e[c] + tau * (T - e[c]));
+          acc[c] += pc;
+          psum += pc;
+        }
+      acc[kGenMaxC] += fminf(fmaxf(1.f - psum, 0.f), 1.f);
+    }
+    const double pm = static_cast<double>(hi - lo) * invS;
+    const double log_pm = log(pm);
+#pragma unroll
+    for (int z = 0; z <= kGenMaxC; ++z) {
+      if (z < C || z == kGenMaxC) {
+        const double J = static_cast<double>(acc[z]) * invS;
+        if (J > 0.0) mi += J * (log(J) - log_pm);
+        tot[z] += acc[z];
+      }
+      acc[z] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int z = 0; z <= kGenMaxC; ++z) {
+    if (z < C || z == kGenMaxC) {
+      const double pz = static_cast<double>(tot[z]) * invS;
+      if (pz > 0.0) mi -= pz * log(pz);
+    }
+  }
+  out_mi[q] = mi;
+}
+
+// ------------------------------------------------------------------------------------------------
 // DTS tail: soft-Copeland score and its argmax                               (acquisitions/dts.py:94-97)
 // ------------------------------------------------------------------------------------------------
 __global__ void soft_copeland_rows_kernel(const float* __restrict__ f, int n, float* __restrict__ score) {
@@ -505,6 +569,29 @@ int mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, i
         fchi, order, gs, S, Q, C, M, table, Pt, k, mode, out_mi);
   }
   h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
+}
+
+int mpes_indiff(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, int S, int64_t Q, int C, int M,
+                double threshold, double* out_mi, cudaStream_t stream) {
+  TKBO_REQUIRE(h && fchi && fstar_argmax && out_mi, "null pointer");
+  TKBO_REQUIRE(S >= 1 && Q >= 1 && Q < (int64_t(1) << 31) && M >= 1, "S, Q, M must be >= 1 and Q < 2^31");
+  TKBO_REQUIRE(C >= 1 && C <= kGenMaxC, "need 1 <= C <= 8");
+  TKBO_REQUIRE(threshold >= 0.0 && threshold < 80.0, "indifference threshold must be in [0, 80)");
+  const size_t need = sizeof(int) * (static_cast<size_t>(S) + M + 1) + sizeof(int) * kGenMaxP * kGenMaxC;
+  if (h->mpes_scratch_bytes < need) {
+    if (h->mpes_scratch) TKBO_CUDA_CHECK(cudaFree(h->mpes_scratch));
+    h->mpes_scratch = nullptr; h->mpes_scratch_bytes = 0;
+    TKBO_CUDA_CHECK(cudaMalloc(&h->mpes_scratch, need));
+    h->mpes_scratch_bytes = need;
+  }
+  int* order = static_cast<int*>(h->mpes_scratch);
+  int* gs = order + S;
+  group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs);
+  mpes_indiff_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, stream>>>(fchi, order, gs, S, Q, C, M,
+                                                                            static_cast<float>(exp(threshold)), out_mi);
+  h->launches += 2;
   TKBO_CUDA_CHECK(cudaGetLastError());
   return TKBO_OK;
 }
