@@ -166,6 +166,18 @@ def golden_pes(ref):
     np.savez_compressed(os.path.join(OUT, "pes.npz"), **out)
 
 
+def golden_pes_inputs(ref):
+    """pes.sample_inputs / sample_inputs_discrete (pes.py:135-189) under a fixed np.random seed."""
+    rng = np.random.default_rng(31)
+    cur = rng.uniform(0, 1, size=(4, 3))
+    data = rng.uniform(0, 1, size=(25, 3))
+    np.random.seed(1234)
+    a = np.asarray(ref.pes.sample_inputs(cur, 6, 3, -1.0, 2.0))
+    np.random.seed(4321)
+    b = np.asarray(ref.pes.sample_inputs_discrete(cur, data, 5, 4))
+    np.savez_compressed(os.path.join(OUT, "pes_inputs.npz"), cur=cur, data=data, uniform=a, discrete=b)
+
+
 def golden_dts(ref):
     """dts.sample_f (dts.py:71-85) with a Product kernel, and soft_copeland_maximizer (dts.py:88-97)."""
     import gpflow
@@ -211,6 +223,7 @@ def main():
     golden_rank_pes(ref)
     golden_indiff_pes(ref)
     golden_pes(ref)
+    golden_pes_inputs(ref)
     golden_dts(ref)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):

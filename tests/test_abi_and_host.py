@@ -177,3 +177,17 @@ def test_allgather_merge_world2_gloo():
         np.testing.assert_array_equal(i, np.argmax(F, axis=0))
         np.testing.assert_array_equal(v, F.max(axis=0))
     assert res[0][2][3] == 100
+
+
+def test_query_set_generators_reproduce_reference_under_seed(golden):
+    """pes.sample_inputs / sample_inputs_discrete: same np.random stream as pes.py:135-189 -> identical query sets."""
+    import importlib
+    pes = importlib.import_module("top-k-ranking-bayesian-optimization_b200.acquisitions.pes")
+    g = golden("pes_inputs.npz")
+    np.random.seed(1234)
+    a = pes.sample_inputs(g["cur"], 6, 3, -1.0, 2.0)
+    np.random.seed(4321)
+    b = pes.sample_inputs_discrete(g["cur"], g["data"], 5, 4)
+    assert tuple(a.shape) == (24, 3, 3) and tuple(b.shape) == (20, 4, 3)
+    np.testing.assert_array_equal(a.numpy(), g["uniform"])
+    np.testing.assert_array_equal(b.numpy(), g["discrete"])

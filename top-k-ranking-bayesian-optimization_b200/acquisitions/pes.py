@@ -62,3 +62,32 @@ def sample_maximizers_discrete(model, count, data, batch_size=1000, *, D=1024, d
     basis = ff.SharedBasis.sample(model.Z if hasattr(model, "Z") else to_numpy(model.inducing_variable.Z), model, D=D,
                                   count=count, device=device)
     return basis.maximizers(data)
+
+
+def sample_inputs(current_inputs, num_samples, num_choices, min_val, max_val):
+    """Query sets for the next observation: every existing input paired with the same ``num_samples`` uniform draws
+    of the other ``num_choices - 1`` choices -> (num_samples * num_inputs, num_choices, input_dims) CPU float64
+    tensor, row i * num_samples + j = [current_inputs[i], draw j].  Same ``np.random.uniform`` call as the
+    reference, so a seeded run reproduces its query sets bit for bit.                       [pes.py:135-161]"""
+    import torch                                           # host-side bookkeeping: no GPU involved
+    cur = to_numpy(current_inputs)
+    num_inputs, input_dims = cur.shape
+    uniform_samples = np.random.uniform(low=min_val, high=max_val, size=(num_samples, num_choices - 1, input_dims))
+    samples = np.empty((num_inputs, num_samples, num_choices, input_dims))
+    samples[:, :, 0, :] = cur[:, None, :]
+    samples[:, :, 1:, :] = uniform_samples[None]
+    return torch.from_numpy(samples.reshape(num_inputs * num_samples, num_choices, input_dims))
+
+
+def sample_inputs_discrete(current_inputs, data, num_samples, num_choices):
+    """As sample_inputs with the other choices drawn (with replacement) from the rows of ``data``.   [pes.py:164-189]"""
+    import torch
+    cur = to_numpy(current_inputs)
+    data = to_numpy(data)
+    num_inputs, input_dims = cur.shape
+    random_indices = np.random.choice(data.shape[0], (num_samples, num_choices - 1))
+    data_samples = np.take(data, random_indices, axis=0)
+    samples = np.empty((num_inputs, num_samples, num_choices, input_dims))
+    samples[:, :, 0, :] = cur[:, None, :]
+    samples[:, :, 1:, :] = data_samples[None]
+    return torch.from_numpy(samples.reshape(num_inputs * num_samples, num_choices, input_dims))
