@@ -154,7 +154,7 @@ int64_t tkbo_launch_count(tkbo_handle_t h);
 int tkbo_rff_basis_config(tkbo_handle_t h, tkbo_basis_t basis, int64_t N, int32_t* cfg);
 /* Diagnostics: while `trace` (device, uint64 [TKBO_TRACE_EVENTS][cap]) is set, CTA 0 of every K1 launch logs
  * clock64() at its pipeline events (rff_fused.cuh TraceEvent); pass NULL to switch it off. */
-#define TKBO_TRACE_EVENTS 15
+#define TKBO_TRACE_EVENTS 17
 int tkbo_debug_set_trace(tkbo_handle_t h, uint64_t* trace, int cap);
 
 #ifdef __cplusplus

@@ -19,7 +19,9 @@ pkg = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
 nat = pkg._native
 
 EV = ["tma_empty", "tma_issued", "p0_pfull", "p0_arrived", "p1_pfull", "p1_arrived", "p2_pfull", "p2_arrived",
-      "mma_proj", "mma_afull", "mma_committed", "epi_accfull", "epi_done", "mma_accempty", "mma_proj_issued"]
+      "p3_pfull", "p3_arrived", "mma_proj", "mma_afull", "mma_committed", "epi_accfull", "epi_done", "mma_accempty",
+      "mma_proj_issued"]
+E_PROJ, E_AFULL, E_COMMIT, E_EPIFULL, E_EPIDONE, E_ACCEMPTY, E_PROJISS = 10, 11, 12, 13, 14, 15, 16
 
 
 def main():
@@ -47,9 +49,9 @@ def main():
     nat.check(nat.lib().tkbo_debug_set_trace(h, None, 0), "set_trace")
     t = trace.cpu().numpy().astype(np.int64)
     t0 = t[t > 0].min()
-    npg = 3 if t[6].any() else 2
-    n_it = int((t[10] > 0).sum())
-    n_items = int((t[11] > 0).sum())
+    npg = cfg["producer_groups"]
+    n_it = int(np.nonzero(t[E_COMMIT] > 0)[0].max()) + 1
+    n_items = int((t[E_EPIFULL] > 0).sum())
     total = t.max() - t0
     print(f"CTA 0: {n_it} slab iterations, {n_items} items, {total} cycles total, {total / max(n_it, 1):.0f} cycles/slab")
     rel = lambda v: int(v - t0) if v > 0 else -1
@@ -58,18 +60,19 @@ def main():
     for it in range(first, min(first + count, n_it)):
         g, k = it % npg, it // npg
         pb, pa = t[2 + 2 * g][k], t[3 + 2 * g][k]
-        dc = t[10][it] - t[10][it - 1] if it > 0 else 0
-        print(f"{it:>5} {rel(t[0][it]):>10} {rel(t[1][it]):>8} {rel(t[8][it]):>9} {rel(pb):>10} {rel(pa):>9} {int(pa - pb):>8} "
-              f"{rel(t[9][it]):>10} {rel(t[10][it]):>10} {int(dc):>8}")
+        dc = t[E_COMMIT][it] - t[E_COMMIT][it - 1] if it > 0 else 0
+        print(f"{it:>5} {rel(t[0][it]):>10} {rel(t[1][it]):>8} {rel(t[E_PROJ][it]):>9} {rel(pb):>10} {rel(pa):>9} {int(pa - pb):>8} "
+              f"{rel(t[E_AFULL][it]):>10} {rel(t[E_COMMIT][it]):>10} {int(dc):>8}")
     print("items: epi_accfull, epi_done (dur), mma_accempty")
     for i in range(min(n_items, 6)):
-        print(f"{i:>5} {rel(t[11][i]):>10} {rel(t[12][i]):>10} ({int(t[12][i] - t[11][i])}) {rel(t[13][i]):>10}")
+        print(f"{i:>5} {rel(t[E_EPIFULL][i]):>10} {rel(t[E_EPIDONE][i]):>10} ({int(t[E_EPIDONE][i] - t[E_EPIFULL][i])}) {rel(t[E_ACCEMPTY][i]):>10}")
     ii = np.arange(1, n_it)
-    print(f"proj warp per slab: waits {(t[8][ii] - t[14][ii - 1]).mean():.0f} | issue {(t[14][ii] - t[8][ii]).mean():.0f};  "
-          f"main warp per slab: waits {(t[9][ii] - t[10][ii - 1]).mean():.0f} | issue {(t[10][ii] - t[9][ii]).mean():.0f}")
-    print(f"proj runs ahead of main by {(t[9][ii] - t[14][ii]).mean():.0f} cycles")
-    wait_a = (t[9][1:n_it] - t[10][:n_it - 1]).clip(min=0)
-    issue = t[10][:n_it] - t[9][:n_it]
+    ii = ii[(t[E_AFULL][ii] > 0) & (t[E_COMMIT][ii - 1] > 0) & (t[E_PROJISS][ii] > 0)]   # paired bursts log their first slab only
+    print(f"proj warp per slab: waits {(t[E_PROJ][ii] - t[E_PROJISS][ii - 1]).mean():.0f} | issue {(t[E_PROJISS][ii] - t[E_PROJ][ii]).mean():.0f};  "
+          f"main warp per slab: waits {(t[E_AFULL][ii] - t[E_COMMIT][ii - 1]).mean():.0f} | issue {(t[E_COMMIT][ii] - t[E_AFULL][ii]).mean():.0f}")
+    print(f"proj runs ahead of main by {(t[E_AFULL][ii] - t[E_PROJISS][ii]).mean():.0f} cycles")
+    wait_a = (t[E_AFULL][ii] - t[E_COMMIT][ii - 1]).clip(min=0)
+    issue = t[E_COMMIT][ii] - t[E_AFULL][ii]
     print(f"MMA warp per slab: from previous commit to a_full seen (projection issue + waiting) {wait_a.mean():.0f}, "
           f"main issue+commit {issue.mean():.0f}")
     for g in range(npg):
@@ -82,9 +85,9 @@ def main():
     lat = []
     for it in range(k):
         g, kk = it % npg, it // npg
-        lat.append(t[2 + 2 * g][kk] - t[8][it])
+        lat.append(t[2 + 2 * g][kk] - t[E_PROJ][it])
     print(f"projection issue -> producer sees p_full: mean {np.mean(lat):.0f}, min {np.min(lat)}, max {np.max(lat)}")
-    lat2 = [t[9][it] - t[3 + 2 * (it % npg)][it // npg] for it in range(k)]
+    lat2 = [t[E_AFULL][it] - t[3 + 2 * (it % npg)][it // npg] for it in range(k) if t[E_AFULL][it] > 0]
     print(f"producer arrival -> MMA warp sees a_full: mean {np.mean(lat2):.0f}, min {np.min(lat2)}, max {np.max(lat2)}")
 
 

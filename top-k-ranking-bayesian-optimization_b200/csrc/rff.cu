@@ -379,12 +379,22 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
   if (bs->stages % 2 == 1 && bs->stages >= 5) bs->stages -= 1;
   bs->proj_warps = (bs->stages % 2 == 0) ? 2 : 1;
   bs->ring = std::min(bs->ring, bs->stages);
-  bs->npg = bs->ring >= 5 ? 3 : 2;       // producer groups that can be busy at once: ring slots ahead of the main MMAs
+  bs->npg = bs->ring >= 5 ? 3 : 2;
+  // Small sample chunks are bound by the SFU (cos), not the tensor pipe: a fourth producer group pays off if a sixth ring
+  // slot is available, which needs the split candidate rows out of TMEM (two smem buffers) and a deep smem ring.
+  {
+    const int ring6 = (kTmemCols - 2 * bs->SC) / kSlabK;
+    const int st6 = std::min(kMaxStages, (smem_limit - 2 * proj_x_bytes(DT)) / stride) & ~1;
+    const bool off = getenv("TKBO_NPG") != nullptr && atoi(getenv("TKBO_NPG")) != 4;
+    if (bs->acc_bufs == 2 && ring6 >= 6 && st6 >= 6 && !off) {
+      bs->npg = 4; bs->ring = std::min(kMaxRing, ring6); bs->stages = st6; bs->proj_warps = 2; bs->xa_bufs = 2;
+    }
+  }       // producer groups that can be busy at once: ring slots ahead of the main MMAs
   if (const char* env = getenv("TKBO_NPG")) {
     const int t = atoi(env);
-    if (t == 2 || t == 3) bs->npg = t;
+    if ((t == 2 || t == 3) && bs->npg != 4) bs->npg = t;
   }
-  bs->smem_bytes = bs->stages * stride + 1024;
+  bs->smem_bytes = bs->stages * stride + 1024 + (bs->npg == 4 ? 2 * proj_x_bytes(DT) : 0);
   cudaError_t e = cudaSuccess;
   e = e ? e : cudaMalloc(&bs->Wproj, static_cast<size_t>(bs->Dpad) * proj_k_alloc(DT) * sizeof(uint16_t));
   e = e ? e : cudaMalloc(&bs->theta_hi, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
@@ -442,8 +452,9 @@ static int launch_fused_n(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, 
 
 template <int DT, int MODE>
 static int launch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
-  return bs->npg == 3 ? launch_fused_n<DT, MODE, 3>(h, bs, p, grid, stream)
-                      : launch_fused_n<DT, MODE, 2>(h, bs, p, grid, stream);
+  return bs->npg == 4 ? launch_fused_n<DT, MODE, 4>(h, bs, p, grid, stream)
+         : bs->npg == 3 ? launch_fused_n<DT, MODE, 3>(h, bs, p, grid, stream)
+                        : launch_fused_n<DT, MODE, 2>(h, bs, p, grid, stream);
 }
 
 template <int MODE>

@@ -23,10 +23,11 @@
 //   next warp   TMA: Theta hi/lo slab tiles (128B-swizzled, K-major) + the bf16 (W | b) slab tile into the smem ring
 //   2 warps     projection MMAs, alternating slabs (1 warp when the smem ring depth is odd): they run ahead of the
 //               main MMAs as far as free TMEM ring slots and landed tiles allow
-//   2 warps     main MMAs, each owning one half of the accumulator columns (N = SC / 2 per instruction).
+//   2 warps     main MMAs, each owning one half of the accumulator columns (N = SC / 2 per instruction), two slabs
+//               per burst when the operands are ready, the two warps' bursts offset by one slab.
 //   A lone warp needs ~300 cycles for the waits, commits and address arithmetic of one slab while the tensor
 //   pipe queues only ~4 instructions, so a single issuing warp starves the pipe (tools/probe_mma_chain.cu);
-//   splitting the issue work over warps keeps every accumulator column's MMAs in one program order.
+//   splitting the issue work by columns keeps every accumulator column's MMAs in one program order.
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -36,7 +37,9 @@ namespace tkbo {
 constexpr int kTileM = 128;          // candidates per tile (TMEM lanes)
 constexpr int kSlabK = 64;           // features per slab (= one 128-byte swizzle row of fp16)
 constexpr int kUmmaK = 16;           // K per tcgen05.mma for 16-bit inputs
-constexpr int kNumThreadsFor(int npg) { return 32 * (4 + 4 * npg + 5); }   // epilogue + producers + TMA + 2 projection + 2 main MMA warps
+// epilogue + producers + TMA + 2 projection + 2 main MMA warps
+constexpr int kProjWarpsFor(int npg) { return 2; }
+constexpr int kNumThreadsFor(int npg) { return 32 * (4 + 4 * npg + 1 + kProjWarpsFor(npg) + 2); }
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 12;       // smem ring (Theta + W tiles)
 constexpr int kMaxRing = 6;          // TMEM ring (projection result -> Phi hi/lo), 64 columns per slot
@@ -54,6 +57,11 @@ __host__ __device__ constexpr int stage_tx_bytes(int SC, int DT) { return 2 * SC
 __host__ __device__ constexpr int stage_stride_bytes(int SC, int DT) {
   return ((stage_tx_bytes(SC, DT) + 1023) / 1024) * 1024;
 }
+
+// With four producer groups (small sample chunks, where the SFU binds) the split candidate rows live in shared memory
+// instead of TMEM, which frees the columns of a sixth ring slot: 128 rows in the same K-major swizzled tile format as
+// the (W | b) tile, two buffers after the stage ring; the projection MMA then takes both operands from shared memory.
+__host__ __device__ constexpr int proj_x_bytes(int DT) { return kTileM * proj_row_bytes(DT) * proj_tiles(DT); }
 
 struct RffParams {
   const float* X;            // [N, d] candidates
@@ -91,8 +99,8 @@ struct RffParams {
 enum TraceEvent : int {
   kTrTmaEmpty = 0, kTrTmaIssued = 1,
   kTrProdPFull = 2 /* + 2 * group */, kTrProdArrived = 3 /* + 2 * group */,
-  kTrMmaProj = 8, kTrMmaAFull = 9, kTrMmaCommitted = 10,
-  kTrEpiAccFull = 11, kTrEpiDone = 12, kTrMmaAccEmpty = 13, kTrMmaProjIssued = 14, kTraceEvents = 15
+  kTrMmaProj = 10, kTrMmaAFull = 11, kTrMmaCommitted = 12,
+  kTrEpiAccFull = 13, kTrEpiDone = 14, kTrMmaAccEmpty = 15, kTrMmaProjIssued = 16, kTraceEvents = 17
 };
 // Compiled in only with -DTKBO_TRACE (libtkbo_trace.so): the issuing warps' loops must stay as short as possible.
 __device__ __forceinline__ void trace_event(const RffParams& p, int ev, int idx) {
@@ -128,12 +136,14 @@ __device__ __forceinline__ void bf16_split3(float x, uint32_t& b1, uint32_t& b2,
   b3 = __float_as_uint(r2) >> 16;
 }
 
-template <int DT, int MODE /* 0 = argmax, 1 = store F, 2 = duel soft-Copeland sums */, int NPG /* producer warp groups: 2 or 3 */>
+template <int DT, int MODE /* 0 = argmax, 1 = store F, 2 = duel soft-Copeland sums */, int NPG /* producer warp groups: 2, 3 or 4 */>
 __global__ void __launch_bounds__(kNumThreadsFor(NPG), 1)
 rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                  const __grid_constant__ CUtensorMap tm_w, const RffParams p) {
   constexpr int kPUsed = proj_k_used(DT);
-  constexpr int kPCols = proj_k_alloc(DT) / 2;       // TMEM columns of one split-candidate buffer (2 bf16 per column)
+  constexpr int kPCols = proj_k_alloc(DT) / 2;       // 32-bit words of one split candidate row = TMEM columns of one buffer
+  constexpr bool kXSmem = (NPG == 4);                // split candidate rows in shared memory (else in TMEM)
+  constexpr int kXBytes = proj_x_bytes(DT);
   constexpr int kPRow = proj_row_bytes(DT);
   constexpr int kPTile = kSlabK * kPRow;
   extern __shared__ uint8_t smem_raw[];
@@ -183,8 +193,9 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     fence_mbar_init();
   }
   constexpr int kTmaWarp = 4 + 4 * NPG;
-  constexpr int kProjWarp = kTmaWarp + 1;            // and + 2
-  constexpr int kMainWarp = kTmaWarp + 3;            // and + 4
+  constexpr int kProjWarp = kTmaWarp + 1;            // kProjWarps of them
+  constexpr int kProjWarps = kProjWarpsFor(NPG);
+  constexpr int kMainWarp = kProjWarp + kProjWarps;  // and + 1
   if (warp == kMainWarp) tmem_alloc(&tmem_base_smem, kTmemCols);
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tm_hi);
@@ -195,7 +206,8 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t xa_col0 = acc_bufs * SC;                         // split candidate rows follow the accumulators
+  const uint32_t xa_col0 = acc_bufs * SC;                         // split candidate rows follow the accumulators (TMEM form)
+  const uint32_t xa_smem0 = smem0 + stages * sbytes;              // or two buffers after the stage ring (smem form)
   const uint32_t ring_col0 = kTmemCols - ring * kSlabK;           // the ring occupies the top columns
 
   if (warp == kTmaWarp) {
@@ -226,13 +238,13 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         if (++st == stages) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == kProjWarp || warp == kProjWarp + 1) {
+  } else if (warp >= kProjWarp && warp < kProjWarp + kProjWarps) {
     // ------------------------------------------------------------------ projection MMAs: arg = [x splits | 1] . [w splits | b]^T
     // Warp h of `npw` takes the slab iterations j = h, h + npw, ...  A ring slot is free again once the main MMAs of
     // slab j - ring have finished, which is b_empty of that slab's smem stage (stages >= ring, and b_full(j) seen
     // first implies every earlier phase of that barrier has completed).  The candidate rows of item i+2 (i+1 with
     // one buffer) are only staged after the epilogue of item i, i.e. after all of item i's projections were consumed.
-    const int npw = p.proj_warps;
+    const int npw = p.proj_warps < kProjWarps ? p.proj_warps : kProjWarps;
     const int h = warp - kProjWarp;
     if (h < npw) {
       constexpr uint32_t idesc_proj = idesc_bf16_f32(kTileM, kSlabK);
@@ -258,13 +270,20 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + ring_col0 + slot * kSlabK;
-          const uint32_t a_tmem = tmem_base + xa_col0 + ((xa_bufs == 2) ? (item & 1) : 0) * kPCols;
+          const int xb = (xa_bufs == 2) ? (item & 1) : 0;
+          const uint32_t a_tmem = tmem_base + xa_col0 + xb * kPCols;
+          const uint32_t a_lo = smem_desc_lo(xa_smem0 + xb * kXBytes);
           const uint32_t b_lo = desc_w0 + st * desc_stage;
 #pragma unroll
           for (int k = 0; k < kPUsed / kUmmaK; ++k) {
-            const uint32_t boff = (k / 4) * (kPTile >> 4) + (k % 4) * ((kUmmaK * 2) >> 4);
-            mma_f16_ts(d_tmem, a_tmem + k * (kUmmaK / 2), (static_cast<uint64_t>(kWDescHi) << 32) | (b_lo + boff),
-                       idesc_proj, k != 0);
+            const uint32_t koff = (k % 4) * ((kUmmaK * 2) >> 4);
+            const uint64_t b_desc = (static_cast<uint64_t>(kWDescHi) << 32) | (b_lo + (k / 4) * (kPTile >> 4) + koff);
+            if constexpr (kXSmem) {
+              mma_f16_ss(d_tmem, (static_cast<uint64_t>(kWDescHi) << 32) | (a_lo + (k / 4) * ((kTileM * kPRow) >> 4) + koff),
+                         b_desc, idesc_proj, k != 0);
+            } else {
+              mma_f16_ts(d_tmem, a_tmem + k * (kUmmaK / 2), b_desc, idesc_proj, k != 0);
+            }
           }
           tc_commit(bar0 + 8 * (kPFull + slot));
         }
@@ -286,9 +305,14 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         }
       }
     }
-  } else if (warp == kMainWarp || warp == kMainWarp + 1) {
+  } else if (warp >= kMainWarp) {
     // ------------------------------------------------------------------ main MMAs: acc += Phi_slab . Theta_slab^T (3 per K step)
-    // Warp h owns accumulator columns [h SC/2, (h+1) SC/2): N = SC/2 per instruction, Theta rows h SC/2 ... of the tile.
+    // Warp h owns accumulator columns [h SC/2, (h+1) SC/2): N = SC/2 per instruction, Theta rows h SC/2 ... of the tile,
+    // so every column's MMAs come from one thread in slab order (deterministic fp32 accumulation; MMAs issued by
+    // different threads are NOT ordered against each other, even across an mbarrier hand-off).  A warp needs ~300
+    // cycles of waits / commits / address arithmetic per burst, so when the next slab's operand is already there it
+    // issues two slabs per burst; warp 0 pairs (0,1)(2,3).., warp 1 pairs (1,2)(3,4).., which keeps the two warps'
+    // bookkeeping phases apart instead of idling the tensor pipe together.
     const int h = warp - kMainWarp;
     const int NH = SC >> 1;
     const uint32_t idesc = idesc_f16_f32(kTileM, NH);
@@ -297,41 +321,55 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
     const uint32_t desc_lopart = static_cast<uint32_t>(SC * 128) >> 4;     // Theta-lo tile follows the hi tile
     const bool hi_only = (p.debug & 1) != 0;
+    const bool pairing = ring >= 5 && !(p.debug & 8);  // a pair holds two ring slots while its MMAs run
     int st = 0, slot = 0, ab = 0, slab = 0, nitem = 0;
     uint32_t sph = 0, aph = 0;
     // a_full implies (through p_full and the projection warp's wait) that the stage's Theta tiles have landed
-    for (int it = 0; it < total; ++it) {
+    for (int it = 0; it < total;) {
       if (slab == 0) {
         mbar_wait(bar0 + 8 * (kAccEmpty + ab), aph ^ 1);
         if (h == 0) trace_event(p, kTrMmaAccEmpty, nitem);
       }
       mbar_wait(bar0 + 8 * (kAFull + slot), sph);
+      // second slab of the burst: same item, pair alignment of this warp, operand already produced
+      int st2 = st + 1, slot2 = slot + 1;
+      uint32_t sph2 = sph;
+      if (st2 == stages) st2 = 0;
+      if (slot2 == ring) { slot2 = 0; sph2 ^= 1; }
+      const bool two = pairing && ((it & 1) == h) && (slab + 1 < n_slabs) && mbar_test_wait(bar0 + 8 * (kAFull + slot2), sph2);
       if (h == 0) trace_event(p, kTrMmaAFull, it);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + ab * SC + h * NH;
-        const uint32_t b_hi = desc_lo0 + st * desc_stage;
-        const uint32_t b_lo = b_hi + desc_lopart;
-        const uint32_t a_st = tmem_base + ring_col0 + slot * kSlabK;
+        auto issue_slab = [&](int st_, int slot_, int sl) {
+          const uint32_t b_hi = desc_lo0 + st_ * desc_stage;
+          const uint32_t b_lo = b_hi + desc_lopart;
+          const uint32_t a_st = tmem_base + ring_col0 + slot_ * kSlabK;
 #pragma unroll
-        for (int k = 0; k < kSlabK / kUmmaK; ++k) {
-          const uint32_t koff = k * ((kUmmaK * 2) >> 4);               // 32 bytes of K per step, in 16-byte units
-          const uint32_t a_hi = a_st + k * kUmmaK;                     // 16 columns per K step: 8 hi words, 8 lo words
-          const uint32_t a_lo = a_hi + kUmmaK / 2;
-          mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_hi + koff), idesc, (slab | k) != 0);
-          if (!hi_only) {
-            mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_lo + koff), idesc, 1);
-            mma_f16_ts(d_tmem, a_lo, smem_desc_from_lo(b_hi + koff), idesc, 1);
+          for (int k = 0; k < kSlabK / kUmmaK; ++k) {
+            const uint32_t koff = k * ((kUmmaK * 2) >> 4);               // 32 bytes of K per step, in 16-byte units
+            const uint32_t a_hi = a_st + k * kUmmaK;                     // 16 columns per K step: 8 hi words, 8 lo words
+            const uint32_t a_lo = a_hi + kUmmaK / 2;
+            mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_hi + koff), idesc, (sl | k) != 0);
+            if (!hi_only) {
+              mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_lo + koff), idesc, 1);
+              mma_f16_ts(d_tmem, a_lo, smem_desc_from_lo(b_hi + koff), idesc, 1);
+            }
           }
-        }
-        tc_commit(bar0 + 8 * (kBEmpty + st));
-        if (slab == n_slabs - 1) tc_commit(bar0 + 8 * (kAccFull + ab));
+          tc_commit(bar0 + 8 * (kBEmpty + st_));
+          if (sl == n_slabs - 1) tc_commit(bar0 + 8 * (kAccFull + ab));
+        };
+        issue_slab(st, slot, slab);
+        if (two) issue_slab(st2, slot2, slab + 1);
       }
       __syncwarp();
       if (h == 0) trace_event(p, kTrMmaCommitted, it);
-      if (++st == stages) st = 0;
-      if (++slot == ring) { slot = 0; sph ^= 1; }
-      if (++slab == n_slabs) {
+      const int adv = two ? 2 : 1;
+      it += adv;
+      st += adv; if (st >= stages) st -= stages;
+      slot += adv; if (slot >= ring) { slot -= ring; sph ^= 1; }
+      slab += adv;
+      if (slab == n_slabs) {
         slab = 0;
         ++nitem;
         if (++ab == acc_bufs) { ab = 0; aph ^= 1; }
@@ -420,11 +458,29 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       constexpr uint32_t kOne = 0x3F80u;             // bf16 1.0 at k = 6 DT, 6 DT + 1, 6 DT + 2
       w[3 * DT] = kOne | (kOne << 16);
       w[3 * DT + 1] = kOne;
-      const uint32_t col = tmem_base + lane_base + xa_col0 + xb * kPCols;
+      if constexpr (kXSmem) {
+        // row r of a K-major tile with kPRow-byte rows and the matching swizzle (what TMA writes for the (W | b)
+        // tile): 16-byte chunk c of the row lands at chunk c ^ f(r), f = r & 7 / (r >> 1) & 3 / (r >> 2) & 1 for
+        // 128 / 64 / 32-byte rows
+        const int r = q * 32 + lane;
+        const uint32_t sw = (kPRow == 128) ? (r & 7) : ((kPRow == 64) ? ((r >> 1) & 3) : ((r >> 2) & 1));
+        const uint32_t rowaddr = xa_smem0 + xb * kXBytes + r * kPRow;
 #pragma unroll
-      for (int c = 0; c < kPCols; c += 8) tmem_st_x8(col + c, w + c);
-      tmem_wait_st();
-      tc_fence_before();
+        for (int c = 0; c < kPCols / 4; ++c) {
+          constexpr int kChunksPerRow = kPRow / 16;
+          const uint32_t tile = c / kChunksPerRow, cc = c % kChunksPerRow;
+          const uint32_t addr = rowaddr + tile * (kTileM * kPRow) + ((cc ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * c]), "r"(w[4 * c + 1]),
+                       "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
+        }
+        fence_proxy_async_smem();
+      } else {
+        const uint32_t col = tmem_base + lane_base + xa_col0 + xb * kPCols;
+#pragma unroll
+        for (int c = 0; c < kPCols; c += 8) tmem_st_x8(col + c, w + c);
+        tmem_wait_st();
+        tc_fence_before();
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar0 + 8 * (kXaFull + xb));
     };
