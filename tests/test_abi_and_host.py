@@ -191,3 +191,41 @@ def test_query_set_generators_reproduce_reference_under_seed(golden):
     assert tuple(a.shape) == (24, 3, 3) and tuple(b.shape) == (20, 4, 3)
     np.testing.assert_array_equal(a.numpy(), g["uniform"])
     np.testing.assert_array_equal(b.numpy(), g["discrete"])
+
+
+def test_dts_gauss_hermite_helpers_match_numerical_integration():
+    """dts.expected_integral / variance_integral / variance_logistic_f (dts.py:48-68) against scipy quadrature."""
+    from scipy import integrate
+    dts = importlib.import_module("top-k-ranking-bayesian-optimization_b200.acquisitions.dts")
+    means = np.array([[-2.0], [0.0], [0.7], [3.0]])
+    variances = np.array([[[0.01]], [[1.0]], [[4.0]], [[0.5]]])
+    sig = lambda t: 1.0 / (1.0 + np.exp(-t))   # noqa: E731
+    for fn, g in ((dts.expected_integral, sig), (dts.variance_integral, lambda t: sig(t) ** 2)):
+        got = fn(means, variances).numpy()[:, 0]
+        ref = [integrate.quad(lambda t, m=m, v=v: g(t) * np.exp(-0.5 * (t - m) ** 2 / v) / np.sqrt(2 * np.pi * v), m - 12 * np.sqrt(v),
+                              m + 12 * np.sqrt(v))[0] for m, v in zip(means[:, 0], variances[:, 0, 0])]
+        np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-9)        # H = 50 nodes on a non-polynomial integrand
+
+    class M:
+        def predict_f(self, x):
+            return means, variances[:, 0]
+    v = dts.variance_logistic_f(M(), np.zeros((4, 2))).numpy()
+    assert v.shape == (4, 1) and np.all(v > 0) and np.all(v < 0.25)
+
+
+def test_pes_building_blocks_reassemble_to_I():
+    """pes.samples_likelihood / log_p_x_star_cond_D / log_p_z_cond_D_x_star (pes.py:44-89) combined as pes.I does
+    (pes.py:108-123) equal the oracle's restatement of I."""
+    pes = importlib.import_module("top-k-ranking-bayesian-optimization_b200.acquisitions.pes")
+    rng = np.random.default_rng(5)
+    S, M, C = 400, 6, 3
+    samples = rng.standard_normal((S, 3)) @ rng.standard_normal((3, M + C)) + 0.3 * rng.standard_normal((S, M + C))
+    arg = samples[:, :M].argmax(axis=1)
+    log_px = pes.log_p_x_star_cond_D(M, arg)
+    total = 0.0
+    for i in range(C):
+        z = (i, None)
+        log_pz_x = pes.log_p_z_cond_D_x_star(M, samples, arg, z, log_px)
+        log_pz = torch.logsumexp(log_px + log_pz_x, dim=0)                      # pes.py:115-118
+        total += float((torch.exp(log_px) * torch.exp(log_pz_x) * (log_pz_x - log_pz)).sum())
+    np.testing.assert_allclose(total, mpes_oracle.pes_I_from_samples(samples, M), rtol=1e-9)

@@ -1,6 +1,6 @@
 """Dueling-Thompson sampling (Gonzalez et al. 2017) — the hot-path half of the reference's acquisitions/dts.py:
 ``sample_f`` (dts.py:71-85) and ``soft_copeland_maximizer`` (dts.py:88-97), plus the two grid helpers the
-scripts call (dts.py:12-45).  The Gauss-Hermite variance helpers (dts.py:48-68) are outside this package's scope.
+scripts call (dts.py:12-45) and the Gauss-Hermite variance helpers (dts.py:48-68; small host-side torch code).
 """
 from __future__ import annotations
 
@@ -32,6 +32,44 @@ def combinations(points):
     out[:, :, :d] = points[:, None, :]
     out[:, :, d:] = points[None, :, :]
     return out.reshape(n * n, 2 * d)
+
+
+def logistic(x):
+    """[dts.py:48-49]"""
+    import torch
+    return 1 / (1 + torch.exp(-torch.as_tensor(x)))
+
+
+def logistic_square(x):
+    """[dts.py:52-53]"""
+    return logistic(x) ** 2
+
+
+def _gauss_hermite_1d(func, means, variances, H=50):
+    """E_{f ~ N(mean, var)}[func(f)] with H-point Gauss-Hermite quadrature: what gpflow.quadrature.mvnquad(func,
+    means, variances, H, Din=1) computes.  means (N, 1), variances (N, 1, 1) or (N, 1) -> (N, 1) float64."""
+    import torch
+    xn, wn = np.polynomial.hermite.hermgauss(H)
+    mu = torch.as_tensor(to_numpy(means), dtype=torch.float64).reshape(-1, 1)
+    var = torch.as_tensor(to_numpy(variances), dtype=torch.float64).reshape(-1, 1)
+    X = mu + torch.sqrt(2.0 * var) * torch.from_numpy(xn)[None, :]              # (N, H)
+    return (func(X) * torch.from_numpy(wn / np.sqrt(np.pi))[None, :]).sum(dim=1, keepdim=True)
+
+
+def variance_integral(means, variances):
+    """E[sigmoid(f)^2]                                                                    [dts.py:56-57]"""
+    return _gauss_hermite_1d(logistic_square, means, variances, H=50)
+
+
+def expected_integral(means, variances):
+    """E[sigmoid(f)]                                                                      [dts.py:60-61]"""
+    return _gauss_hermite_1d(logistic, means, variances, H=50)
+
+
+def variance_logistic_f(m, x):
+    """Var[sigmoid(f(x))] under the posterior marginals of ``m.predict_f`` -> (N, 1).        [dts.py:64-68]"""
+    means, variances = m.predict_f(to_numpy(x))
+    return variance_integral(means, variances) - expected_integral(means, variances) ** 2
 
 
 def sample_f(m, query_points, combs, D=1000, *, device=None, device_output=False):

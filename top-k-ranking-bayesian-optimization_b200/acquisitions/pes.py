@@ -64,6 +64,43 @@ def sample_maximizers_discrete(model, count, data, batch_size=1000, *, D=1024, d
     return basis.maximizers(data)
 
 
+def sample_maximizers_simple(model, count, num_discrete_points, *, D=1024, device=None):
+    """Grid-argmax maximiser sampling on ``num_discrete_points`` points of [0, 1] -> (count, 1).     [pes.py:9-21]"""
+    xx = np.linspace(0.0, 1.0, num_discrete_points).reshape(num_discrete_points, 1)
+    return sample_maximizers_discrete(model, count, xx, D=D, device=device)
+
+
+# ---- the building blocks of I (pes.py:44-89): kept for API parity, plain torch float64 on the tensors' device; the
+# ---- fused path (tkbo_mpes_topk, mode TKBO_MPES_PES) computes the same quantities without materialising them
+EPSILON = 1e-7                 # tf.keras.backend.epsilon()
+
+
+def samples_likelihood(z, f_z):
+    """P(choice x is the most preferred given f) per sample, un-stabilised softmax as in the reference. [pes.py:45-53]"""
+    import torch
+    f_z = torch.as_tensor(f_z, dtype=torch.float64) if not isinstance(f_z, torch.Tensor) else f_z.to(torch.float64)
+    x = int(z[0])
+    return torch.exp(f_z[:, x]) / torch.exp(f_z).sum(dim=1)
+
+
+def log_p_x_star_cond_D(num_max, samples_argmax):
+    """log of the eps-smoothed fraction of samples each maximiser wins -> (num_max,).                 [pes.py:57-70]"""
+    import torch
+    arg = torch.as_tensor(samples_argmax).to(torch.int64)
+    count = torch.bincount(arg, minlength=int(num_max)).to(torch.float64) + EPSILON
+    return torch.log(count / (arg.shape[0] + num_max * EPSILON))
+
+
+def log_p_z_cond_D_x_star(num_max, samples, samples_x_star_argmax, z, log_p_x_star_cond):
+    """log p(z | D, x*) for every maximiser -> (num_max,).                                             [pes.py:74-89]"""
+    import torch
+    samples = torch.as_tensor(samples).to(torch.float64)
+    arg = torch.as_tensor(samples_x_star_argmax).to(torch.int64).to(samples.device)
+    lik = samples_likelihood(z, samples[:, num_max:])
+    p = torch.zeros(int(num_max), dtype=torch.float64, device=samples.device).index_add_(0, arg, lik) + EPSILON
+    return torch.log(p / samples.shape[0]) - torch.as_tensor(log_p_x_star_cond).to(samples.device)
+
+
 def sample_inputs(current_inputs, num_samples, num_choices, min_val, max_val):
     """Query sets for the next observation: every existing input paired with the same ``num_samples`` uniform draws
     of the other ``num_choices - 1`` choices -> (num_samples * num_inputs, num_choices, input_dims) CPU float64
