@@ -182,6 +182,28 @@ def test_rff_argmax_key_form_and_merge(pbo):
     assert torch.equal(v3, val) and torch.equal(i3, idx)
 
 
+def test_rff_argmax_ignores_nan_candidates(pbo):
+    """Candidates with a NaN coordinate produce NaN samples; they are never selected (np.nanargmax semantics), a
+    sample whose candidates are all NaN returns (NaN, -1)."""
+    rng = np.random.default_rng(23)
+    X, W, b, Theta = _basis_inputs(rng, 3000, 128, 2, 40, -1.5, 1.5, 0.6)
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    _, idx0 = basis.argmax(X)
+    Xn = X.copy()
+    bad = np.unique(np.concatenate([idx0.cpu().numpy()[:20], np.arange(64, 128), rng.integers(0, 3000, 200)]))
+    Xn[bad, rng.integers(0, 2, bad.shape[0])] = np.nan        # includes current winners and one whole 32-row warp slice
+    val, idx = basis.argmax(Xn)
+    keep = np.setdiff1d(np.arange(3000), bad)
+    ref_val, ref_idx, second, absmax = rff_oracle.rff_argmax_shared(X[keep].astype(np.float64), W, b, Theta, return_absmax=True)
+    got = idx.cpu().numpy()
+    assert not np.isin(got, bad).any() and np.isfinite(val.cpu().numpy()).all()
+    mism = got != keep[ref_idx]
+    assert not np.any(mism & ((ref_val - second) / absmax > VAL_RTOL))
+    assert np.max(np.abs(val.cpu().numpy() - ref_val) / absmax) < VAL_RTOL
+    v2, i2 = basis.argmax(np.full((300, 2), np.nan, dtype=np.float32))
+    assert bool((i2 == -1).all()) and bool(torch.isnan(v2).all())
+
+
 def test_rff_argmax_host_entry_point(pbo):
     """tkbo_rff_argmax_host: the pure C-ABI end-to-end call with host buffers (no torch memory involved)."""
     rng = np.random.default_rng(8)
