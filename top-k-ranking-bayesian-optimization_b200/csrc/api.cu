@@ -151,6 +151,7 @@ int tkbo_destroy(tkbo_handle_t h) {
     host_path_release(h);
     cudaFree(h->done_counter);
     cudaFree(h->mpes_scratch);
+    cudaFree(h->mpes_parts);
   }
   delete h;
   return TKBO_OK;

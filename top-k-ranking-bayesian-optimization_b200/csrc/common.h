@@ -41,6 +41,8 @@ struct tkbo_handle_s {
   // scratch for the MPES kernel (grown on demand)
   void* mpes_scratch = nullptr;
   size_t mpes_scratch_bytes = 0;
+  void* mpes_parts = nullptr;             // per-chunk partial sums of the all-permutations kernel
+  size_t mpes_parts_bytes = 0;
   // persistent state of the host-buffer entry point (tkbo_rff_argmax_host): basis + device staging, reused across calls
   struct HostPath {
     tkbo_basis_s* basis = nullptr;

@@ -27,8 +27,10 @@ constexpr double kPesEps = 1e-7;   // tf.keras.backend.epsilon(), pes.py:68,87
 // stable counting sort of the sample indices by winning maximiser
 // ------------------------------------------------------------------------------------------------
 // order[group_start[m] .. group_start[m+1]) = samples with fstar_argmax == m, ascending.
+// chunk_group[0 .. J]: the groups split into J contiguous chunks of roughly equal sample counts (work units of the
+// all-permutations kernel; a chunk may be empty).
 __global__ void group_samples_kernel(const int* __restrict__ arg, int S, int M, int* __restrict__ order,
-                                     int* __restrict__ group_start) {
+                                     int* __restrict__ group_start, int J = 0, int* __restrict__ chunk_group = nullptr) {
   extern __shared__ int cnt[];           // [M + 1]
   for (int m = threadIdx.x; m <= M; m += blockDim.x) cnt[m] = 0;
   __syncthreads();
@@ -41,6 +43,16 @@ __global__ void group_samples_kernel(const int* __restrict__ arg, int S, int M, 
     for (int m = 0; m < M; ++m) cnt[m + 1] += cnt[m];
   __syncthreads();
   for (int m = threadIdx.x; m <= M; m += blockDim.x) group_start[m] = cnt[m];
+  if (threadIdx.x == 0 && chunk_group != nullptr) {
+    int m = 0;
+    chunk_group[0] = 0;
+    for (int j = 1; j < J; ++j) {
+      const long long target = static_cast<long long>(cnt[M]) * j / J;
+      while (m < M && cnt[m + 1] <= target) ++m;       // groups wholly below the j-th cut
+      chunk_group[j] = m;
+    }
+    chunk_group[J] = M;
+  }
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     int w = cnt[m];
     for (int s = 0; s < S; ++s)
@@ -136,32 +148,39 @@ struct PermWalk {
 // ------------------------------------------------------------------------------------------------
 constexpr int kRing = 4;
 constexpr int kMpesWarps = 4;
+constexpr int kMaxChunks = 8;
 __host__ __device__ constexpr int mpes_warp_smem_bytes(int C, int P) {
-  return ((kRing * 32 * C * 4 + 2 * P * 32 * 4 + kRing * 8 + 127) / 128) * 128;
+  return ((kRing * 32 * C * 4 + P * 32 * 4 + kRing * 8 + 127) / 128) * 128;
 }
 
+// Work unit = (tile of 32 queries, chunk j of the maximiser groups), fetched dynamically from a global counter: a
+// whole tile (all S samples) is ~0.5 ms of work for one warp, far too coarse for a few thousand persistent warps.
+// For its chunk a unit produces
+//     A_j  = sum_{m in j} p_m sum_z c_zm log c_zm      (t1buf[j, q], float64)
+//     tot_j[z] = sum_{m in j} sum_{s in m} P_s(z)       (totbuf[j, z, q], float32)
+// and mpes_finish_kernel assembles  MI = sum_j A_j - sum_z p_z log p_z,  p_z = (sum_j tot_j[z] + M eps) / S.
+// Per group the entropy-like sum over the P orderings runs in float32 (two interleaved partial sums, logf), the
+// weighting by p_m and the sum over groups in float64; measured |dMI| stays below 1e-6 absolute.
 template <int C, int K, bool STAGED>
-__global__ void __launch_bounds__(32 * kMpesWarps, 3)
+__global__ void __launch_bounds__(32 * kMpesWarps, 4)
 mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ order, const int* __restrict__ group_start,
-                      int S, long long Q, int M, int mode, int tile_begin, int tile_end, double* __restrict__ out_mi) {
+                      const int* __restrict__ chunk_group, int J, int S, long long Q, long long Qpad, int M, int mode,
+                      int tile_begin, int tile_end, unsigned int* __restrict__ unit_counter, float* __restrict__ totbuf,
+                      double* __restrict__ t1buf) {
   constexpr int P = perm_count(C, K);
   constexpr float kLog2e = 1.4426950408889634f;
-  // dynamic shared memory, one private slice per warp: ring | tot | ruz | mbarriers (see mpes_warp_smem_bytes)
+  // dynamic shared memory, one private slice per warp: ring | tot | mbarriers (see mpes_warp_smem_bytes)
   extern __shared__ __align__(128) unsigned char mpes_smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;                        // warps never synchronise with each other
   unsigned char* slice = mpes_smem + static_cast<size_t>(wib) * mpes_warp_smem_bytes(C, P);
   float (*ring)[32 * C] = reinterpret_cast<float (*)[32 * C]>(slice);
-  float (*tot)[32] = reinterpret_cast<float (*)[32]>(slice + kRing * 32 * C * 4);      // sum over groups of acc
-  float (*ruz)[32] = tot + P;                              // 1 / u_z, the reference distribution of the MI fold
-  uint64_t* full = reinterpret_cast<uint64_t*>(ruz + P);
-  const int warp_gid = blockIdx.x * kMpesWarps + wib;
-  const int warp_total = gridDim.x * kMpesWarps;
+  float (*tot)[32] = reinterpret_cast<float (*)[32]>(slice + kRing * 32 * C * 4);      // sum over the chunk's groups of acc
+  uint64_t* full = reinterpret_cast<uint64_t*>(tot + P);
   const double invS = 1.0 / static_cast<double>(S);
   const double eps = (mode == TKBO_MPES_PES) ? kPesEps : 0.0;
   const float epsf = static_cast<float>(eps);
   const long long rowstride = Q * C;
-  const int n_used = group_start[M];                       // samples with a valid group (all of them normally)
   if constexpr (STAGED) {
     if (lane == 0)
       for (int i = 0; i < kRing; ++i) mbar_init(&full[i], 1);
@@ -169,8 +188,17 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
     __syncwarp();
   }
   uint32_t ring_phase = 0;                                 // bit i = parity to wait for on slot i
+  const unsigned n_units = static_cast<unsigned>(tile_end - tile_begin) * static_cast<unsigned>(J);
 
-  for (int tile = tile_begin + warp_gid; tile < tile_end; tile += warp_total) {
+  for (;;) {
+    unsigned unit = 0;
+    if (lane == 0) unit = atomicAdd(unit_counter, 1u);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    if (unit >= n_units) break;
+    const int tile = tile_begin + static_cast<int>(unit / J);
+    const int j = static_cast<int>(unit % J);
+    const int m0 = chunk_group[j], m1 = chunk_group[j + 1];
+    const int i0 = group_start[m0], i1 = group_start[m1];  // this unit's range of the grouped sample order
     const long long q = static_cast<long long>(tile) * 32 + lane;
     const bool valid = q < Q;
     const float* base = fchi + (valid ? q : Q - 1) * C;                          // direct path
@@ -180,36 +208,35 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
     float acc[P];
 #pragma unroll
     for (int z = 0; z < P; ++z) acc[z] = 0.f;
-    float t1 = 0.f;
-    bool have_ref = false;
+    double A = 0.0;
 
-    if constexpr (STAGED) {                                // prime the ring with the first kRing rows of this tile
+    if constexpr (STAGED) {                                // prime the ring with the unit's first kRing rows
       if (lane == 0) {
-        for (int j = 0; j < kRing && j < n_used; ++j) {
-          mbar_arrive_expect_tx(&full[j], 32 * C * 4);
-          bulk_load_1d(ring[j], tile_base + static_cast<long long>(order[j]) * rowstride, 32 * C * 4, &full[j]);
+        for (int r = 0; r < kRing && i0 + r < i1; ++r) {
+          mbar_arrive_expect_tx(&full[r], 32 * C * 4);
+          bulk_load_1d(ring[r], tile_base + static_cast<long long>(order[i0 + r]) * rowstride, 32 * C * 4, &full[r]);
         }
       }
       __syncwarp();
     }
     float fnext[C];
     if constexpr (!STAGED) {
-      if (n_used > 0) {
-        const float* r = base + static_cast<long long>(order[0]) * rowstride;
+      if (i0 < i1) {
+        const float* r = base + static_cast<long long>(order[i0]) * rowstride;
 #pragma unroll
         for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
       }
     }
 
-    int i = 0;                                             // position in the grouped sample order
-    for (int m = 0; m < M; ++m) {
+    int i = i0;                                            // position in the grouped sample order
+    for (int m = m0; m < m1; ++m) {
       const int hi = group_start[m + 1];
       const int cnt = hi - group_start[m];
       if (cnt == 0 && mode == TKBO_MPES_RANK) continue;    // rank_pes.py:86-93 drops empty groups
       for (; i < hi; ++i) {
         float f[C];
         if constexpr (STAGED) {
-          const int slot = i % kRing;
+          const int slot = (i - i0) % kRing;
           mbar_wait(&full[slot], (ring_phase >> slot) & 1u);
           ring_phase ^= 1u << slot;
 #pragma unroll
@@ -217,7 +244,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
         } else {
 #pragma unroll
           for (int c = 0; c < C; ++c) f[c] = fnext[c];
-          if (i + 1 < n_used) {
+          if (i + 1 < i1) {
             const float* r = base + static_cast<long long>(order[i + 1]) * rowstride;
 #pragma unroll
             for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
@@ -232,8 +259,8 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
         for (int c = 0; c < C; ++c) e[c] = fast_ex2(fmaf(f[c], kLog2e, -mxs));
         if constexpr (STAGED) {
           __syncwarp();                                    // every lane has consumed its slot values
-          if (lane == 0 && i + kRing < n_used) {
-            const int slot = i % kRing;
+          if (lane == 0 && i + kRing < i1) {
+            const int slot = (i - i0) % kRing;
             mbar_arrive_expect_tx(&full[slot], 32 * C * 4);
             bulk_load_1d(ring[slot], tile_base + static_cast<long long>(order[i + kRing]) * rowstride, 32 * C * 4, &full[slot]);
           }
@@ -243,41 +270,44 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
         int leaf = 0;
         PermWalk<C, K, 0>::run(e, rs, 0u, 1.f, acc, leaf);
       }
-      // fold group m.  MI = sum_{m,z} p_m c_{zm} log(c_{zm} / p_z), c_{zm} = p(z | m).  Written against a fixed
-      // reference distribution u_z (= c_{z,m0} of the first folded group):
-      //   MI = sum_m p_m sum_z c_{zm} log(c_{zm} / u_z)  -  sum_z p_z log(p_z / u_z)
-      // both sums are small KL-type quantities whose log arguments sit near 1, so float32 logf is accurate to
-      // ~1e-8 absolute and nothing of the size of the entropies (~log P) is ever subtracted.
+      // fold group m:  A += p_m sum_z c_zm log c_zm  with c_zm = p(z | m)
       const double pm = (mode == TKBO_MPES_PES)
                             ? (static_cast<double>(cnt) + kPesEps) / (static_cast<double>(S) + M * kPesEps)
                             : static_cast<double>(cnt) * invS;
       const float cm = static_cast<float>(invS / pm);              // (acc + eps) * cm = p(z | m)
-      const float pmf = static_cast<float>(pm);
-      if (!have_ref) {
-#pragma unroll
-        for (int z = 0; z < P; ++z) ruz[z][lane] = 1.f / fmaxf((acc[z] + epsf) * cm, 1e-30f);
-        have_ref = true;
-      }
-      float tg = 0.f;
+      float tg0 = 0.f, tg1 = 0.f;
 #pragma unroll
       for (int z = 0; z < P; ++z) {
         const float c = (acc[z] + epsf) * cm;
-        if (c > 0.f) tg = fmaf(c, logf(c * ruz[z][lane]), tg);
+        const float t = (c > 0.f) ? c * __logf(c) : 0.f;          // lg2.approx: ~2e-7 relative
+        if (z & 1) tg1 += t; else tg0 += t;
         tot[z][lane] += acc[z];
         acc[z] = 0.f;
       }
-      t1 = fmaf(pmf, tg, t1);
+      A += pm * (static_cast<double>(tg0) + static_cast<double>(tg1));
     }
-    float t2 = 0.f;
-    const float meps = static_cast<float>(M * eps);
-    const float invSf = static_cast<float>(invS);
 #pragma unroll
-    for (int z = 0; z < P; ++z) {
-      const float pz = (tot[z][lane] + meps) * invSf;
-      if (pz > 0.f) t2 = fmaf(pz, logf(pz * ruz[z][lane]), t2);
-    }
-    if (valid) out_mi[q] = static_cast<double>(t1) - static_cast<double>(t2);
+    for (int z = 0; z < P; ++z) totbuf[(static_cast<size_t>(j) * P + z) * Qpad + q] = tot[z][lane];
+    t1buf[static_cast<size_t>(j) * Qpad + q] = A;
   }
+}
+
+// MI[q] = sum_j A_j[q] - sum_z p_z log p_z                                            (rank_pes.py:97-105, pes.py:115-123)
+__global__ void mpes_finish_kernel(const float* __restrict__ totbuf, const double* __restrict__ t1buf, int J, int P,
+                                   long long Q, long long Qpad, int S, int M, int mode, double* __restrict__ out_mi) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const double invS = 1.0 / static_cast<double>(S);
+  const double meps = (mode == TKBO_MPES_PES) ? M * kPesEps : 0.0;
+  double mi = 0.0;
+  for (int j = 0; j < J; ++j) mi += t1buf[static_cast<size_t>(j) * Qpad + q];
+  for (int z = 0; z < P; ++z) {
+    double t = 0.0;
+    for (int j = 0; j < J; ++j) t += static_cast<double>(totbuf[(static_cast<size_t>(j) * P + z) * Qpad + q]);
+    const double pz = (t + meps) * invS;
+    if (pz > 0.0) mi -= pz * log(pz);
+  }
+  out_mi[q] = mi;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -472,34 +502,52 @@ __global__ void argmax_vec_kernel(const float* __restrict__ v, int n, long long*
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
+// Partial results of the all-permutations kernel (one slab per sample chunk) and its two unit counters.
+struct MpesParts {
+  const int* chunk_group;   // [J + 1]
+  int J;
+  long long Qpad;           // queries rounded up to whole 32-query tiles
+  float* totbuf;            // [J, P, Qpad]
+  double* t1buf;            // [J, Qpad]
+  unsigned int* counters;   // [2], zeroed before the launches
+};
+
 template <int C, int K>
 static void launch_all_perms(const float* fchi, const int* order, const int* gs, int S, int64_t Q, int M, int mode,
-                             int sm_count, double* out, cudaStream_t stream) {
+                             int sm_count, const MpesParts& pt, double* out, cudaStream_t stream) {
   const int64_t tiles = (Q + 31) / 32;
   // the bulk-copy path needs 16-byte aligned rows (Q*C % 4 == 0, base aligned) and full 32-query tiles
   const bool aligned = ((Q * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(fchi) & 15) == 0);
   const int64_t staged_tiles = aligned ? Q / 32 : 0;
   const int threads = 32 * kMpesWarps;
-  const int smem = kMpesWarps * mpes_warp_smem_bytes(C, perm_count(C, K));
+  constexpr int P = perm_count(C, K);
+  const int smem = kMpesWarps * mpes_warp_smem_bytes(C, P);
   cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaMemsetAsync(pt.counters, 0, 2 * sizeof(unsigned int), stream);
   if (staged_tiles > 0) {
-    const int grid = static_cast<int>(std::min<int64_t>(3 * sm_count, (staged_tiles + kMpesWarps - 1) / kMpesWarps));
-    mpes_all_perms_kernel<C, K, true><<<grid, threads, smem, stream>>>(fchi, order, gs, S, Q, M, mode, 0,
-                                                                   static_cast<int>(staged_tiles), out);
+    const int64_t units = staged_tiles * pt.J;
+    const int grid = static_cast<int>(std::min<int64_t>(4 * sm_count, (units + kMpesWarps - 1) / kMpesWarps));
+    mpes_all_perms_kernel<C, K, true><<<grid, threads, smem, stream>>>(fchi, order, gs, pt.chunk_group, pt.J, S, Q, pt.Qpad, M,
+                                                                   mode, 0, static_cast<int>(staged_tiles), pt.counters,
+                                                                   pt.totbuf, pt.t1buf);
   }
   if (staged_tiles < tiles) {
-    const int64_t rest = tiles - staged_tiles;
-    const int grid = static_cast<int>(std::min<int64_t>(3 * sm_count, (rest + kMpesWarps - 1) / kMpesWarps));
-    mpes_all_perms_kernel<C, K, false><<<grid, threads, smem, stream>>>(fchi, order, gs, S, Q, M, mode,
-                                                                    static_cast<int>(staged_tiles), static_cast<int>(tiles), out);
+    const int64_t units = (tiles - staged_tiles) * pt.J;
+    const int grid = static_cast<int>(std::min<int64_t>(4 * sm_count, (units + kMpesWarps - 1) / kMpesWarps));
+    mpes_all_perms_kernel<C, K, false><<<grid, threads, smem, stream>>>(fchi, order, gs, pt.chunk_group, pt.J, S, Q, pt.Qpad, M,
+                                                                    mode, static_cast<int>(staged_tiles),
+                                                                    static_cast<int>(tiles), pt.counters + 1, pt.totbuf,
+                                                                    pt.t1buf);
   }
+  mpes_finish_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, stream>>>(pt.totbuf, pt.t1buf, pt.J, P, Q, pt.Qpad, S, M,
+                                                                            mode, out);
 }
 
 static bool dispatch_all_perms(int C, int K, const float* fchi, const int* order, const int* gs, int S, int64_t Q, int M,
-                               int mode, int sm, double* out, cudaStream_t st) {
+                               int mode, int sm, const MpesParts& pt, double* out, cudaStream_t st) {
 #define TKBO_CASE(c, k) \
-  if (C == c && K == k) { launch_all_perms<c, k>(fchi, order, gs, S, Q, M, mode, sm, out, st); return true; }
+  if (C == c && K == k) { launch_all_perms<c, k>(fchi, order, gs, S, Q, M, mode, sm, pt, out, st); return true; }
   TKBO_CASE(2, 1) TKBO_CASE(2, 2)
   TKBO_CASE(3, 1) TKBO_CASE(3, 2) TKBO_CASE(3, 3)
   TKBO_CASE(4, 1) TKBO_CASE(4, 2) TKBO_CASE(4, 3) TKBO_CASE(4, 4)
@@ -507,6 +555,10 @@ static bool dispatch_all_perms(int C, int K, const float* fchi, const int* order
   TKBO_CASE(6, 1) TKBO_CASE(6, 2)
 #undef TKBO_CASE
   return false;
+}
+
+static bool has_all_perms_kernel(int C, int K) {
+  return (C == 2 && K <= 2) || (C == 3 && K <= 3) || (C == 4 && K <= 4) || (C == 5 && K <= 3) || (C == 6 && K <= 2);
 }
 
 static void full_table(int C, int k, std::vector<int>* out) {
@@ -544,10 +596,34 @@ int mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, i
   int* order = static_cast<int*>(h->mpes_scratch);
   int* gs = order + S;
   int* dperm = gs + M + 1;
-  group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs);
-  h->launches += 1;
   bool done = false;
-  if (perms == nullptr) done = dispatch_all_perms(C, k, fchi, order, gs, S, Q, M, mode, h->sm_count, out_mi, stream);
+  if (perms == nullptr && has_all_perms_kernel(C, k)) {
+    // sample chunks: as many as keep the partial buffers below 256 MiB, at most kMaxChunks and one per group
+    const int Pn = perm_count(C, k);
+    MpesParts pt;
+    pt.Qpad = ((Q + 31) / 32) * 32;
+    const size_t per_chunk = static_cast<size_t>(pt.Qpad) * (static_cast<size_t>(Pn) * sizeof(float) + sizeof(double));
+    pt.J = static_cast<int>(std::max<size_t>(1, std::min<size_t>(std::min(kMaxChunks, M), (size_t(256) << 20) / per_chunk)));
+    const size_t need2 = per_chunk * pt.J + sizeof(int) * (kMaxChunks + 2) + 64;
+    if (h->mpes_parts_bytes < need2) {
+      if (h->mpes_parts) TKBO_CUDA_CHECK(cudaFree(h->mpes_parts));
+      h->mpes_parts = nullptr; h->mpes_parts_bytes = 0;
+      TKBO_CUDA_CHECK(cudaMalloc(&h->mpes_parts, need2));
+      h->mpes_parts_bytes = need2;
+    }
+    pt.t1buf = static_cast<double*>(h->mpes_parts);
+    pt.totbuf = reinterpret_cast<float*>(pt.t1buf + static_cast<size_t>(pt.J) * pt.Qpad);
+    pt.counters = reinterpret_cast<unsigned int*>(pt.totbuf + static_cast<size_t>(pt.J) * Pn * pt.Qpad);
+    int* chunk_group = reinterpret_cast<int*>(pt.counters + 2);
+    pt.chunk_group = chunk_group;
+    group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs, pt.J, chunk_group);
+    h->launches += 1;
+    done = dispatch_all_perms(C, k, fchi, order, gs, S, Q, M, mode, h->sm_count, pt, out_mi, stream);
+    h->launches += 1;                                     // + the finishing kernel (the main one is counted below)
+  } else {
+    group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs);
+    h->launches += 1;
+  }
   if (!done) {
     const int32_t* table = perms;
     int Pt = P;
