@@ -179,6 +179,61 @@ def test_allgather_merge_world2_gloo():
     assert res[0][2][3] == 100
 
 
+def _gloo_key_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    pkg = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    F = rng.standard_normal((900, 12)).astype(np.float32)
+    F[700, 5] = F[40, 5] = F[:, 5].max() + 1.0                       # exact tie across shards -> lowest index wins
+    F[:, 7] = -np.abs(F[:, 7])                                       # an all-negative sample (sign handling of the key)
+    lo, hi = pkg.distributed.shard_range(900, rank, world)
+    val = torch.from_numpy(F[lo:hi].max(axis=0))
+    idx = torch.from_numpy(np.argmax(F[lo:hi], axis=0).astype(np.int64)) + lo
+    key = pkg.distributed.pack_argmax_key(val, idx)
+    dist.all_reduce(key, op=dist.ReduceOp.MAX)                       # what allreduce_argmax does with NCCL
+    v, i = pkg.distributed.unpack_argmax_key(key)
+    # duel shards: integer partial sums add up exactly
+    jlo, jhi = pkg.distributed.duel_shard(101, rank, world)
+    part = torch.arange(jlo, jhi, dtype=torch.int64).sum().reshape(1)
+    dist.all_reduce(part, op=dist.ReduceOp.SUM)
+    q.put((rank, v.numpy(), i.numpy(), int(part)))
+    dist.destroy_process_group()
+
+
+def test_key_merge_and_duel_shards_world2_gloo():
+    """The one-collective merges of the multi-GPU paths (int64 all_reduce MAX of packed keys; SUM of integer duel
+    sums) on two gloo ranks, with the torch restatement of the device-side key."""
+    import torch.multiprocessing as mp
+    pkg = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
+    v0 = torch.tensor([3.5, -2.25, 0.0, -0.0, float("-inf"), 1e-30], dtype=torch.float32)
+    i0 = torch.tensor([7, 123456789, 0, 5, 2, -1])
+    v1, i1 = pkg.distributed.unpack_argmax_key(pkg.distributed.pack_argmax_key(v0, i0))
+    assert torch.equal(v1[:5], v0[:5]) and torch.equal(i1[:5], i0[:5]) and int(i1[5]) == -1 and bool(torch.isnan(v1[5]))
+    ks = pkg.distributed.pack_argmax_key(torch.tensor([1.0, 1.0, -1.0, 2.0]), torch.tensor([9, 4, 0, 100]))
+    assert ks[1] > ks[0] > ks[2] and ks[3] > ks[1]                   # value first, then the lower index
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_key_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(1)
+    F = rng.standard_normal((900, 12)).astype(np.float32)
+    F[700, 5] = F[40, 5] = F[:, 5].max() + 1.0
+    F[:, 7] = -np.abs(F[:, 7])
+    for _, v, i, part in res:
+        np.testing.assert_array_equal(i, np.argmax(F, axis=0))
+        np.testing.assert_array_equal(v, F.max(axis=0))
+        assert part == sum(range(101))
+    assert res[0][2][5] == 40
+
+
 def test_query_set_generators_reproduce_reference_under_seed(golden):
     """pes.sample_inputs / sample_inputs_discrete: same np.random stream as pes.py:135-189 -> identical query sets."""
     import importlib

@@ -174,6 +174,10 @@ def test_rff_argmax_key_form_and_merge(pbo):
     merged = torch.stack(keys).max(dim=0).values
     v2, i2 = basis.unpack_key(merged)
     assert torch.equal(v2, val) and torch.equal(i2, idx)
+    # the torch restatement of the key (used by the gloo tests of the merge) is bit-identical to the device's
+    assert torch.equal(pbo.distributed.pack_argmax_key(val, idx), merged)
+    v2b, i2b = pbo.distributed.unpack_argmax_key(merged)
+    assert torch.equal(v2b, val) and torch.equal(i2b, idx)
     assert int(idx.max()) < 6000                           # ties resolved to the first copy
     ve, ie = basis.unpack_key(keys[-1])
     assert bool((ie == -1).all()) and bool(torch.isnan(ve).all())

@@ -54,6 +54,33 @@ def allgather_argmax(val, idx, group=None):
 EMPTY_KEY = -(1 << 63)
 
 
+def pack_argmax_key(val, idx):
+    """Torch restatement of the device-side merge key (csrc/ptx.cuh ``argmax_key``): signed int64 whose maximum is
+    "largest float32 value, then lowest index"; idx < 0 -> EMPTY_KEY.  Any device; used by the CPU tests of the merge."""
+    import torch
+    bits = val.to(torch.float32).contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    neg = (bits >> 31) & 1
+    orderable = torch.where(neg == 1, (~bits) & 0xFFFFFFFF, bits | 0x80000000)        # larger float <-> larger unsigned
+    hi = orderable ^ 0x80000000                                                      # signed order in the high word
+    hi = torch.where(hi >= (1 << 31), hi - (1 << 32), hi)
+    key = hi * (1 << 32) + (0xFFFFFFFF - idx.to(torch.int64))
+    return torch.where(idx < 0, torch.full_like(key, EMPTY_KEY), key)
+
+
+def unpack_argmax_key(key):
+    """Inverse of pack_argmax_key -> (val float32, idx int64; NaN / -1 for EMPTY_KEY)."""
+    import torch
+    hi = key >> 32                                                                   # arithmetic shift: signed high word
+    lo = key & 0xFFFFFFFF
+    orderable = (hi & 0xFFFFFFFF) ^ 0x80000000
+    bits = torch.where(orderable >= (1 << 31), orderable & 0x7FFFFFFF, (~orderable) & 0xFFFFFFFF)
+    bits = torch.where(bits >= (1 << 31), bits - (1 << 32), bits)
+    val = bits.to(torch.int32).view(torch.float32)
+    idx = 0xFFFFFFFF - lo
+    empty = key == EMPTY_KEY
+    return torch.where(empty, torch.full_like(val, float("nan")), val), torch.where(empty, torch.full_like(idx, -1), idx)
+
+
 def allreduce_argmax(basis, key, group=None):
     """Merge per-rank key vectors (SharedBasis.argmax_key) with ONE all_reduce(MAX) over int64 and unpack:
     the whole exchange is 8*S bytes per rank, one NCCL launch + one unpack launch."""
