@@ -54,6 +54,8 @@ int tkbo_sm_count(tkbo_handle_t h);
  * which is fourier_features(X, W, b) @ theta  (fourier_features.py:18-21 and :162; acquisitions/dts.py:82-85)
  * evaluated for all S samples at once.  The basis object holds the device-side operand layout
  * (bf16-split (W | b) projection rows, Theta split into fp16 hi/lo K-major tiles with a per-sample power-of-two scale). */
+/* Calls that use the same basis object must be stream-ordered (it owns the argmax workspace); calls on different basis
+ * objects may run concurrently on different streams. */
 int tkbo_rff_basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S);
 int tkbo_rff_basis_destroy(tkbo_handle_t h, tkbo_basis_t basis);
 /* W [D, d], b [D], Theta [D, S] (theta_is_transposed = 0) or [S, D] (= 1); all float64 device arrays. */

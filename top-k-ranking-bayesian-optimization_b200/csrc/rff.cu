@@ -400,8 +400,10 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
   e = e ? e : cudaMalloc(&bs->theta_hi, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
   e = e ? e : cudaMalloc(&bs->theta_lo, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
   e = e ? e : cudaMalloc(&bs->unscale, static_cast<size_t>(bs->Salloc) * sizeof(float));
-  e = e ? e : cudaMalloc(&bs->packed, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long));
-  e = e ? e : cudaMemset(bs->packed, 0, static_cast<size_t>(bs->Salloc) * sizeof(unsigned long long));
+  // + one word behind the keys: the last-CTA counter of this basis' launches (launches on different bases may
+  // overlap on different streams; launches on the same basis must be stream-ordered)
+  e = e ? e : cudaMalloc(&bs->packed, static_cast<size_t>(bs->Salloc + 1) * sizeof(unsigned long long));
+  e = e ? e : cudaMemset(bs->packed, 0, static_cast<size_t>(bs->Salloc + 1) * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     set_error(std::string("cudaMalloc (basis): ") + cudaGetErrorString(e));
     free_basis(bs);
@@ -478,7 +480,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   TKBO_REQUIRE(bs->is_set, "basis has no data: call tkbo_rff_basis_set first");
   TKBO_REQUIRE(N >= 1 && N < (int64_t(1) << 32) - 256, "N must be in [1, 2^32 - 256)");
   p->X = X; p->unscale = bs->unscale; p->packed = bs->packed;
-  p->done_counter = h->done_counter;
+  p->done_counter = reinterpret_cast<unsigned int*>(bs->packed + bs->Salloc);
   p->out_val = nullptr; p->out_idx = nullptr; p->out_key = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
   p->duel_n = 0; p->duel_j0 = 0; p->duel_nj = 0; p->score_fix = nullptr;
   p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
@@ -621,7 +623,8 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   const int64_t tpi = (j_end - j_begin + kTileM - 1) / kTileM;       // tiles per i: 128 consecutive j each
   const int64_t mt = static_cast<int64_t>(n) * tpi;
   TKBO_REQUIRE(mt * bs->n_chunks < (int64_t(1) << 31), "too many work items");
-  p.X = Xbase; p.unscale = bs->unscale; p.packed = bs->packed; p.done_counter = h->done_counter;
+  p.X = Xbase; p.unscale = bs->unscale; p.packed = bs->packed;
+  p.done_counter = reinterpret_cast<unsigned int*>(bs->packed + bs->Salloc);
   p.out_val = nullptr; p.out_idx = nullptr; p.out_key = nullptr; p.out_F = nullptr; p.ldf = 0; p.idx_offset = 0;
   p.N = mt * kTileM; p.d = bs->d; p.S = bs->S; p.SC = bs->SC; p.n_chunks = bs->n_chunks;
   p.n_slabs = bs->Dpad / kSlabK; p.n_mtiles = static_cast<int>(mt);
