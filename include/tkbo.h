@@ -125,6 +125,7 @@ int tkbo_rff_ascent_batched(tkbo_handle_t h, double* X, const double* W, const d
  *   mode TKBO_MPES_RANK: acquisitions/rank_pes.py:58-105 (empty maximiser groups dropped).
  *   mode TKBO_MPES_PES : acquisitions/pes.py:66-123 (k must be 1, perms NULL; eps = 1e-7 added to the
  *                        group counts and likelihood sums, all M groups kept).
+ * Calls on one handle share its scratch buffers and must be stream-ordered.
  * perms == NULL means "all k-permutations of C" (P ignored; rank_pes.py:55): register-resident fast path
  * for the common (C, k); an explicit table (P <= 1024 rows, e.g. the random 1000-row subset of
  * rank_pes.py:49-53) takes the table-driven kernel.  C <= 8, Q < 2^31. */

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 : > gpurun_out/ablate_k1.log
 for dbg in 0 1 2 3 4 6 7 8 10 15; do
-  echo "== TILES=${TKBO_TILES:-auto} NPG=${TKBO_NPG:-2} DEBUG=$dbg" >> gpurun_out/ablate_k1.log
+  echo "== NPG=${TKBO_NPG:-2} DEBUG=$dbg" >> gpurun_out/ablate_k1.log
   TKBO_DEBUG=$dbg timeout 300 python tests/gpu_probe.py k1time >> gpurun_out/ablate_k1.log 2>&1
 done
 cat gpurun_out/ablate_k1.log
