@@ -65,6 +65,8 @@ def _check_argmax(val, idx, X, W, b, Theta, idx_offset=0):
     (30000, 128, 16, 32, 0.0, 1.0, 1.0),      # d = 16 (K = 99), 16-column accumulator halves
     (9000, 192, 8, 40, 0.0, 1.0, 0.7),        # d = 8 (K = 51, one 128-byte W tile)
     (9000, 192, 3, 130, -1.0, 1.0, 0.5),      # d = 3 (K = 21, 64-byte swizzle), S chunk of 160
+    (31, 1, 12, 128, 0.0, 1.0, 0.8),          # one slab, one row buffer, two projection warps: the second owns nothing
+    (40000, 40, 12, 128, 0.0, 1.0, 0.8),      # same, 3 items per CTA: each projection warp skips every other item
 ])
 def test_rff_eval_and_argmax_vs_oracle(pbo, N, D, d, S, lo, hi, ls):
     rng = np.random.default_rng(N + D + S)

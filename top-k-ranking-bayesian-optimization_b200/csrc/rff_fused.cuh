@@ -257,6 +257,11 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       int fst = 0;                                     // smem stage of slab j - ring (valid once j >= ring)
       uint32_t fph = 0;
       bool new_item = true;
+      // One row buffer = one barrier whose phases are the items in order; a parity wait only tells adjacent phases
+      // apart, so a warp that owns no slab of an item (n_slabs < npw) still observes that item's phase, but never
+      // the phase of an item beyond its own last slab iteration (it would not arrive).
+      if (xa_bufs == 1 && h < total)
+        for (int i = 0; i < item; ++i) mbar_wait(bar0 + 8 * kXaFull, static_cast<uint32_t>(i) & 1);
       for (int j = h; j < total; j += npw) {
         mbar_wait(bar0 + 8 * (kBFull + st), ph);
         if (j >= ring) mbar_wait(bar0 + 8 * (kBEmpty + fst), fph);
@@ -299,7 +304,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           slab -= n_slabs;
           ++item;
           new_item = true;
-          if (slab >= n_slabs && xa_bufs == 1) {         // an item without a slab of this warp: still observe its phase
+          if (slab >= n_slabs && xa_bufs == 1 && j + npw < total) {   // an item without a slab of this warp
             mbar_wait(bar0 + 8 * kXaFull, static_cast<uint32_t>(item) & 1);
           }
         }
