@@ -296,13 +296,18 @@ def run_gpu(args):
         alg_tf = 2.0 * N * D * S / (ms_per_step * 1e-3) / 1e12        # per GPU: one launch processes N candidates
         proj_k = ((6 * cfg["d_template"] + 3 + 15) // 16) * 16
         Dpad = cfg["n_slabs"] * 64
-        exec_tf = (3 * 2.0 * N * Dpad * cfg["S_chunk"] * cfg["n_chunks"] + 2.0 * N * Dpad * proj_k * cfg["n_chunks"]) \
+        # tensor-pipe time in 16-bit-MMA equivalents per product: 3 (fp16 hi*hi + hi*lo + lo*hi) or 2 (fp16 hi*hi + one e4m3 MMA
+        # of twice the K at twice the rate, carrying both corrections)
+        mma_eq = 2 if cfg.get("e4m3_corrections") else 3
+        exec_tf = (mma_eq * 2.0 * N * Dpad * cfg["S_chunk"] * cfg["n_chunks"] + 2.0 * N * Dpad * proj_k * cfg["n_chunks"]) \
             / (ms_per_step * 1e-3) / 1e12
         cos_rate = float(N) * Dpad * cfg["n_chunks"] / (ms_per_step * 1e-3)
         cos_peak = 16.0 * 148 * 1965e6
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (fp16 hi/lo split x3 tcgen05.mma, fp32 accumulate)", "data": "synthetic",
+                "dtype": ("f32 (fp16 hi*hi + e4m3 correction tcgen05.mma, fp32 accumulate; <= 1e-4 of max|f|)"
+                          if cfg.get("e4m3_corrections") else "f32 (fp16 hi/lo split x3 tcgen05.mma, fp32 accumulate)"),
+                "data": "synthetic",
                 "config": {"workload": desc, "N_per_gpu": N, "d": d, "D": D, "S": S,
                            "l2": f"{n_rot} rotating candidate buffers ({n_rot * N * d * 4 >> 20} MiB > 126 MiB L2)",
                            "tiling": cfg, "parallelism": f"candidate shards x{world}, one int64 all_reduce(MAX) merge"},
@@ -320,7 +325,9 @@ def run_gpu(args):
                                       "note": "the feature map needs N*D*n_chunks cos (MUFU, 16/clk/SM at the max SM clock); "
                                               "this unit, not the tensor pipe, binds small-S shapes such as c2"},
                              "note": "achieved = algorithmic 2*N*D*S per launch / CUDA-event time; executed adds what the "
-                                     "tensor pipe really does: 3 fp16 MMAs per product (hi*hi + hi*lo + lo*hi, fp32-accurate) and "
+                                     "tensor pipe really does, in 16-bit-MMA equivalents: " + str(mma_eq) + " per product ("
+                                     + ("fp16 hi*hi + one e4m3 MMA for both corrections" if mma_eq == 2 else
+                                        "hi*hi + hi*lo + lo*hi, fp32-accurate") + ") and "
                                      "the bf16x3 projection X W^T + b (K = " + str(proj_k) + "); peak = measured bf16 cuBLAS burst ("
                                      + pk["source"] + "); traffic = dram bytes of one launch from the committed ncu capture "
                                      "(profiles/r01_prof_k1_v6_summary.txt; algorithmic: 4*N*d = 8.39e6)"}}
@@ -489,12 +496,14 @@ def run_gpu_duel(args):
         pk = peaks()
         alg_tf = 2.0 * N_rank * D * S / (ms_per_step * 1e-3) / 1e12
         proj_k = ((6 * cfg["d_template"] + 3 + 15) // 16) * 16
-        exec_tf = (3 * 2.0 * N_rank * D * cfg["S_chunk"] * cfg["n_chunks"] + 2.0 * N_rank * D * proj_k * cfg["n_chunks"]) \
+        mma_eq = 2 if cfg.get("e4m3_corrections") else 3
+        exec_tf = (mma_eq * 2.0 * N_rank * D * cfg["S_chunk"] * cfg["n_chunks"] + 2.0 * N_rank * D * proj_k * cfg["n_chunks"]) \
             / (ms_per_step * 1e-3) / 1e12
         line = {"metric": METRIC, "value": world * N_rank * S / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (fp16 hi/lo split x3 tcgen05.mma, fp32 accumulate; sigmoid sums in 2^-24 fixed point)",
+                "dtype": ("f32 (fp16 hi*hi + e4m3 correction tcgen05.mma" if mma_eq == 2 else "f32 (fp16 hi/lo split x3 tcgen05.mma")
+                         + ", fp32 accumulate; sigmoid sums in 2^-24 fixed point)",
                 "data": "synthetic",
                 "config": {"workload": "c4d: DTS batch Thompson, n=2048 base points (d_obj=2), duels [x_i, x_j] generated in the "
                                        "kernel, D=2048, S=4096, soft-Copeland winners; per rank the j-shard of n/8 = 2^19 duels "
@@ -510,7 +519,7 @@ def run_gpu_duel(args):
                              "frac": alg_tf / pk["bf16_tflops"], "traffic": None, "kernel": "rff_fused_kernel<4, 2, *>",
                              "flops_per_launch": 2.0 * N_rank * D * S, "executed": exec_tf,
                              "executed_frac": exec_tf / pk["bf16_tflops"],
-                             "note": "algorithmic 2*N*D*S over the rank's duels; executed = 3 fp16 MMAs per product + projection; "
+                             "note": "algorithmic 2*N*D*S over the rank's duels; executed = " + str(mma_eq) + " 16-bit-MMA equivalents per product + projection; "
                                      "peak = measured bf16 cuBLAS burst (" + pk["source"] + ")"},
                 "cpu_baseline": None, "checksum": int(win.sum().item())}
         print(json.dumps(line), flush=True)

@@ -57,6 +57,16 @@ int tkbo_sm_count(tkbo_handle_t h);
 /* Calls that use the same basis object must be stream-ordered (it owns the argmax workspace); calls on different basis
  * objects may run concurrently on different streams. */
 int tkbo_rff_basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S);
+/* Same with an explicit contraction precision.  Phi and Theta are each split into an fp16 hi part and a remainder:
+ *   TKBO_PRECISION_FP32  hi*hi + hi*lo + lo*hi as three fp16 tcgen05.mma (fp32 emulation, ~2e-6 of max|F|);
+ *   TKBO_PRECISION_FAST  hi*hi in fp16 + both correction terms in ONE e4m3 tcgen05.mma (K = 32): two thirds of the
+ *                        tensor work, ~3e-5 of max|F| -- inside the 1e-4 parity tolerance of the path;
+ *   TKBO_PRECISION_AUTO  (what tkbo_rff_basis_create uses) FAST where the tensor pipe binds (sample chunks >= 128),
+ *                        FP32 otherwise; the environment variable TKBO_PRECISION=fp32|fast overrides AUTO. */
+#define TKBO_PRECISION_AUTO 0
+#define TKBO_PRECISION_FP32 1
+#define TKBO_PRECISION_FAST 2
+int tkbo_rff_basis_create_ex(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int precision);
 int tkbo_rff_basis_destroy(tkbo_handle_t h, tkbo_basis_t basis);
 /* W [D, d], b [D], Theta [D, S] (theta_is_transposed = 0) or [S, D] (= 1); all float64 device arrays. */
 int tkbo_rff_basis_set(tkbo_handle_t h, tkbo_basis_t basis, const double* W, const double* b,
@@ -151,9 +161,11 @@ int tkbo_soft_copeland(tkbo_handle_t h, const float* f, int n, float* out_score,
 /* ---- introspection used by bench.py / tests --------------------------------------------------------
  * Number of kernel launches issued through this handle since creation. */
 int64_t tkbo_launch_count(tkbo_handle_t h);
-/* Describes the tiling chosen for a basis: fills cfg[0..12] = {S_chunk, n_chunks, n_slabs, smem stages,
+/* Describes the tiling chosen for a basis: fills cfg[0..15] = {S_chunk, n_chunks, n_slabs, smem stages,
  * accumulator buffers, d_template, smem_bytes, grid, TMEM ring slots, threads per CTA, candidate-row
- * buffers, producer warp groups, projection-issuing warps}; cfg must have room for 16 int32. */
+ * buffers, producer warp groups, projection-issuing warps,
+ * 1 if the e4m3 correction form is used, depth of the separate (W | b) tile ring or 0,
+ * 1 if both producer groups convert every slab}; cfg must have room for 16 int32. */
 int tkbo_rff_basis_config(tkbo_handle_t h, tkbo_basis_t basis, int64_t N, int32_t* cfg);
 /* Diagnostics: while `trace` (device, uint64 [TKBO_TRACE_EVENTS][cap]) is set, CTA 0 of every K1 launch logs
  * clock64() at its pipeline events (rff_fused.cuh TraceEvent); pass NULL to switch it off. */

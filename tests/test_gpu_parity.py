@@ -89,6 +89,31 @@ def test_rff_eval_and_argmax_vs_oracle(pbo, N, D, d, S, lo, hi, ls):
     assert torch.equal(basis.eval(X), basis.eval(X))
 
 
+@pytest.mark.parametrize("N,D,d,S", [(20000, 512, 6, 256), (9000, 320, 4, 300), (30000, 256, 2, 64), (5000, 192, 12, 128)])
+def test_rff_precision_modes(pbo, N, D, d, S):
+    """"fp32" (three fp16 MMAs per product) holds ~1e-5 of max|f|; "fast" (fp16 hi*hi + one e4m3 MMA carrying both
+    correction terms) holds the path's 1e-4; "auto" picks fast exactly for sample chunks >= 128.  Theta columns span a
+    wide dynamic range inside each sample (the e4m3 tile keeps 8 octaves below the column maximum in its normal range)."""
+    rng = np.random.default_rng(N + S)
+    X, W, b, Theta = _basis_inputs(rng, N, D, d, S, 0.0, 1.0, 0.4)
+    Theta = Theta * np.exp(2.0 * rng.standard_normal((D, 1)))
+    Fref = rff_oracle.rff_values_shared(X.astype(np.float64), W, b, Theta)
+    scale = np.abs(Fref).max(axis=0)
+    errs = {}
+    for precision in ("fp32", "fast", "auto"):
+        basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0", precision=precision)
+        cfg = basis.config(N)
+        assert cfg["e4m3_corrections"] == {"fp32": 0, "fast": 1, "auto": int(cfg["S_chunk"] >= 128)}[precision]
+        F = basis.eval(X).cpu().numpy().T.astype(np.float64)
+        errs[precision] = float(np.max(np.abs(F - Fref) / scale))
+        val, idx = basis.argmax(X)
+        _check_argmax(val, idx, X, W, b, Theta)
+        val2, idx2 = basis.argmax(X)
+        assert torch.equal(val, val2) and torch.equal(idx, idx2)
+    assert errs["fp32"] < 1e-5 and errs["fast"] < VAL_RTOL, errs
+    assert errs["fast"] > errs["fp32"]                     # the modes really differ
+
+
 def test_rff_argmax_wide_dynamic_range_theta(pbo):
     """Per-sample power-of-two scaling keeps tiny and huge weight samples equally accurate."""
     rng = np.random.default_rng(5)

@@ -50,6 +50,8 @@ def main():
     t = trace.cpu().numpy().astype(np.int64)
     t0 = t[t > 0].min()
     npg = cfg["producer_groups"]
+    coop = bool(cfg.get("producers_share_slab"))
+    grp = (lambda it: (0, it)) if coop else (lambda it: (it % npg, it // npg))    # producer group 0's log stands for the slab
     n_it = int(np.nonzero(t[E_COMMIT] > 0)[0].max()) + 1
     n_items = int((t[E_EPIFULL] > 0).sum())
     total = t.max() - t0
@@ -58,10 +60,10 @@ def main():
     print(f"{'it':>5} {'tma_empty':>10} {'tma_iss':>8} {'mma_proj':>9} {'prod_pfull':>10} {'prod_arr':>9} {'prod_dur':>8} "
           f"{'mma_afull':>10} {'mma_commit':>10} {'d_commit':>8}")
     for it in range(first, min(first + count, n_it)):
-        g, k = it % npg, it // npg
+        g, k = grp(it)
         pb, pa = t[2 + 2 * g][k], t[3 + 2 * g][k]
         dc = t[E_COMMIT][it] - t[E_COMMIT][it - 1] if it > 0 else 0
-        print(f"{it:>5} {rel(t[0][it]):>10} {rel(t[1][it]):>8} {rel(t[E_PROJ][it]):>9} {rel(pb):>10} {rel(pa):>9} {int(pa - pb):>8} "
+        print(f"{it:>5} {rel(t[0][it]):>10} {rel(t[1][it]):>8} {rel(t[E_PROJ][it]):>9}/{rel(t[E_PROJISS][it]) - rel(t[E_PROJ][it]):<4} {rel(pb):>10} {rel(pa):>9} {int(pa - pb):>8} "
               f"{rel(t[E_AFULL][it]):>10} {rel(t[E_COMMIT][it]):>10} {int(dc):>8}")
     print("items: epi_accfull, epi_done (dur), mma_accempty")
     for i in range(min(n_items, 6)):
@@ -84,10 +86,10 @@ def main():
     print(f"TMA warp per slab: wait b_empty {(t[0][1:k] - t[1][:k - 1]).mean():.0f}, issue {(t[1][:k] - t[0][:k]).mean():.0f}")
     lat = []
     for it in range(k):
-        g, kk = it % npg, it // npg
-        lat.append(t[2 + 2 * g][kk] - t[E_PROJ][it])
-    print(f"projection issue -> producer sees p_full: mean {np.mean(lat):.0f}, min {np.min(lat)}, max {np.max(lat)}")
-    lat2 = [t[E_AFULL][it] - t[3 + 2 * (it % npg)][it // npg] for it in range(k) if t[E_AFULL][it] > 0]
+        g, kk = grp(it)
+        lat.append(t[2 + 2 * g][kk] - t[E_PROJISS][it])
+    print(f"projection issued -> producer sees p_full: mean {np.mean(lat):.0f}, min {np.min(lat)}, max {np.max(lat)}")
+    lat2 = [t[E_AFULL][it] - t[3 + 2 * grp(it)[0]][grp(it)[1]] for it in range(k) if t[E_AFULL][it] > 0]
     print(f"producer arrival -> MMA warp sees a_full: mean {np.mean(lat2):.0f}, min {np.min(lat2)}, max {np.max(lat2)}")
 
 

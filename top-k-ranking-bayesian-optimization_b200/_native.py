@@ -35,6 +35,7 @@ _SIGNATURES = {
     "tkbo_launch_count": (c_i64, [c_p]),
     "tkbo_debug_set_trace": (c_i, [c_p, c_p, c_i]),
     "tkbo_rff_basis_create": (c_i, [c_p, ctypes.POINTER(c_p), c_i, c_i, c_i]),
+    "tkbo_rff_basis_create_ex": (c_i, [c_p, ctypes.POINTER(c_p), c_i, c_i, c_i, c_i]),
     "tkbo_rff_basis_destroy": (c_i, [c_p, c_p]),
     "tkbo_rff_basis_set": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p]),
     "tkbo_rff_basis_config": (c_i, [c_p, c_p, c_i64, ctypes.POINTER(ctypes.c_int32)]),

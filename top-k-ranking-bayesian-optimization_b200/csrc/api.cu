@@ -12,7 +12,7 @@ namespace tkbo {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
-int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S);
+int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int precision);
 int basis_destroy(tkbo_handle_t h, tkbo_basis_t bs);
 int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b, const double* Theta, int transposed,
               cudaStream_t stream);
@@ -168,7 +168,12 @@ int tkbo_debug_set_trace(tkbo_handle_t h, uint64_t* trace, int cap) {
 
 int tkbo_rff_basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
   TKBO_ENTER(h);
-  return basis_create(h, out, D, d, S);
+  return basis_create(h, out, D, d, S, TKBO_PRECISION_AUTO);
+}
+int tkbo_rff_basis_create_ex(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int precision) {
+  TKBO_ENTER(h);
+  TKBO_REQUIRE(precision >= TKBO_PRECISION_AUTO && precision <= TKBO_PRECISION_FAST, "unknown precision");
+  return basis_create(h, out, D, d, S, precision);
 }
 int tkbo_rff_basis_destroy(tkbo_handle_t h, tkbo_basis_t basis) {
   TKBO_ENTER(h);
@@ -239,7 +244,7 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
   }
   if (!hp.basis || hp.D != D || hp.d != d || hp.S != S) {
     if (hp.basis) { basis_destroy(h, hp.basis); hp.basis = nullptr; }
-    int rc = basis_create(h, &hp.basis, D, d, S);
+    int rc = basis_create(h, &hp.basis, D, d, S, TKBO_PRECISION_AUTO);
     if (rc != TKBO_OK) return rc;
     hp.D = D; hp.d = d; hp.S = S;
   }

@@ -75,11 +75,15 @@ struct tkbo_basis_s {
   int acc_bufs = 0;
   int xa_bufs = 0;
   int proj_warps = 1;
-  int npg = 2;       // producer warp groups (2 or 3)
+  int coop = 0;      // 1: the two producer groups share every slab (32 columns each)
+  int wstages = 0;   // depth of the separate (W | b) tile ring (0: the tile travels in the Theta stage)
+  int npg = 2;       // producer warp groups (2, 3 or 4)
+  int corr8 = 0;     // 1: correction terms as one e4m3 MMA (fp16 hi*hi + fp8 [hi*lo | lo*hi]); 0: three fp16 MMAs
   int smem_bytes = 0;
   uint16_t* Wproj = nullptr;         // [Dpad, proj_k_alloc(DT)] bf16 split (W | b) rows, K order of rff_fused.cuh
   __half* theta_hi = nullptr;        // [Salloc, Dpad]
-  __half* theta_lo = nullptr;        // [Salloc, Dpad]
+  __half* theta_lo = nullptr;        // [Salloc, Dpad] fp16 lo parts, or (corr8) [Salloc, 2 Dpad] e4m3 bytes: per 16
+                                     // features 16 lo parts then 16 hi parts scaled by 2^-12
   float* unscale = nullptr;          // [Salloc]
   unsigned long long* packed = nullptr;  // [Salloc], zero between launches
   CUtensorMap tm_hi, tm_lo, tm_w;

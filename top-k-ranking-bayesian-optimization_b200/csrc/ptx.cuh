@@ -132,6 +132,16 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with 8-bit inputs (kind::f8f6f4, K = 32 per instruction): A holds four elements per 32-bit TMEM column.
+__device__ __forceinline__ void mma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Makes this thread's generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma / TMA reads).
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -187,6 +197,11 @@ __device__ __forceinline__ bool elect_one() {
 
 // Instruction descriptor, kind::f16: fp16 A and B (K-major), fp32 D, M x N tile.
 __host__ __device__ constexpr uint32_t idesc_f16_f32(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// kind::f8f6f4 with e4m3 A and B (format code 0), fp32 accumulation.
+__host__ __device__ constexpr uint32_t idesc_e4m3_f32(uint32_t M, uint32_t N) {
   return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 

@@ -2,9 +2,11 @@
 // plus the small float64 kernels for the reference-exact per-sample-basis shapes.
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <math.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -24,10 +26,13 @@ __device__ __forceinline__ double theta_at(const double* T, int transposed, int 
   return transposed ? T[static_cast<size_t>(s) * D + j] : T[static_cast<size_t>(j) * S + s];
 }
 
-// unscale[s] = 2^-e_s with e_s chosen so that max_j |sqrt(2/D) Theta[j,s]| 2^e_s lies in [2^9, 2^10):
-// keeps the fp16 hi part far from overflow and the lo part (<= 2^-11 of hi) far above fp16's subnormal step.
+// e_s is chosen so that max_j |sqrt(2/D) Theta[j,s]| 2^e_s lies in [2^top, 2^(top+1)); unscale[s] = 2^(-e_s - post) is what
+// the epilogue multiplies the accumulator by (post = the power of two the feature operand carries).
+// top = 9, post = 0 (three-fp16 form) keeps the fp16 hi part far from overflow and the lo part (<= 2^-11 of hi) far above
+// fp16's subnormal step; top = 7, post = 12 (e4m3 correction form, features scaled by 2^12) puts the entries themselves
+// (< 2^8) and the 2^12-scaled lo parts (<= 2^8) into e4m3's normal range [2^-6, 448] down to 2^-14 of the column maximum.
 __global__ void prep_theta_scale_kernel(const double* __restrict__ Theta, int transposed, int D, int S, int Salloc,
-                                        float* __restrict__ unscale) {
+                                        int top, int post, float* __restrict__ unscale) {
   const int s = blockIdx.x;
   __shared__ double red[256];
   double m = 0.0;
@@ -42,9 +47,9 @@ __global__ void prep_theta_scale_kernel(const double* __restrict__ Theta, int tr
   if (threadIdx.x == 0) {
     const double amax = red[0] * sqrt(2.0 / D);
     int e = 0;
-    if (amax > 0.0 && isfinite(amax)) e = 9 - ilogb(amax);
+    if (amax > 0.0 && isfinite(amax)) e = top - ilogb(amax);
     e = max(-100, min(100, e));
-    unscale[s] = static_cast<float>(ldexp(1.0, -e));
+    unscale[s] = static_cast<float>(ldexp(1.0, -e - post));
   }
 }
 
@@ -63,6 +68,28 @@ __global__ void prep_theta_split_kernel(const double* __restrict__ Theta, int tr
     const __half l = __double2half(v - static_cast<double>(__half2float(h)));
     hi[i] = h;
     lo[i] = l;
+  }
+}
+
+// e4m3 correction tile (rff_fused.cuh, C8): row s = per 16 features 16 bytes e4m3(2^12 lo part) then 16 bytes
+// e4m3(value), i.e. 128 bytes per 64-feature slab; hi = the fp16 tile as in the three-MMA form.
+__global__ void prep_theta_split8_kernel(const double* __restrict__ Theta, int transposed, int D, int S, int Dpad,
+                                         int Salloc, const float* __restrict__ unscale, __half* __restrict__ hi,
+                                         uint8_t* __restrict__ c8) {
+  const size_t total = static_cast<size_t>(Salloc) * Dpad;
+  const double root = sqrt(2.0 / D);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(i / Dpad);
+    const int j = static_cast<int>(i % Dpad);
+    double v = 0.0;
+    if (s < S && j < D) v = theta_at(Theta, transposed, D, S, j, s) * root / (static_cast<double>(unscale[s]) * 4096.0);
+    const __half h = __double2half(v);
+    hi[i] = h;
+    const float lo = static_cast<float>(v - static_cast<double>(__half2float(h)));
+    uint8_t* row = c8 + static_cast<size_t>(s) * 2 * Dpad + (j >> 4) * 32 + (j & 15);
+    row[0] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(lo * 4096.f, __NV_SATFINITE, __NV_E4M3));
+    row[16] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(static_cast<float>(v), __NV_SATFINITE, __NV_E4M3));
   }
 }
 
@@ -284,13 +311,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_theta_map(tkbo_handle_t h, CUtensorMap* map, __half* base, int Salloc, int Dpad, int SC) {
+// [Salloc, Dpad] fp16 (or, bytes = true, the [Salloc, 2 Dpad] e4m3 correction tile); box = SC rows x 128 bytes.
+static int make_theta_map(tkbo_handle_t h, CUtensorMap* map, void* base, int Salloc, int Dpad, int SC, bool bytes = false) {
   auto fn = reinterpret_cast<EncodeTiledFn>(h->encode_tiled);
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(Dpad), static_cast<cuuint64_t>(Salloc)};
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(bytes ? 2 * Dpad : Dpad), static_cast<cuuint64_t>(Salloc)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Dpad) * sizeof(__half)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kSlabK), static_cast<cuuint32_t>(SC)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(bytes ? 2 * kSlabK : kSlabK), static_cast<cuuint32_t>(SC)};
   cuuint32_t estride[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstride, box, estride,
+  CUresult r = fn(map, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstride, box, estride,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -327,7 +355,7 @@ static void free_basis(tkbo_basis_t bs) {
   delete bs;
 }
 
-int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
+int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int precision) {
   TKBO_REQUIRE(h && out, "null handle/out");
   TKBO_REQUIRE(D >= 1 && d >= 1 && S >= 1, "D, d, S must be >= 1");
   const int DT = pick_dt(d);
@@ -395,6 +423,32 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
     if ((t == 2 || t == 3) && bs->npg != 4) bs->npg = t;
   }
   bs->smem_bytes = bs->stages * stride + 1024 + (bs->npg == 4 ? 2 * proj_x_bytes(DT) : 0);
+  // Wide sample chunks leave room for only 3-5 combined stages, and a stage is then held from its TMA issue through the
+  // projection and the feature producers until its main MMAs retire (~4500 cycles for ~1000 cycles of use).  Split mode
+  // gives the small (W | b) tiles their own ring: the Theta stages are held for TMA latency + main MMAs only, and the
+  // projections / producers run ahead as far as the TMEM ring allows.
+  bs->coop = (bs->npg == 2 && bs->ring <= 3) ? 1 : 0;
+  if (const char* env = getenv("TKBO_COOP")) bs->coop = (bs->npg == 2 && atoi(env) != 0) ? 1 : 0;
+  bs->wstages = 0;
+  if (bs->npg != 4 && bs->stages <= 5 && getenv("TKBO_NOSPLIT") == nullptr) {
+    const int tb = 2 * bs->SC * 128, wb = proj_w_bytes(DT);
+    for (int nt = std::min(kMaxStages, smem_limit / tb); nt >= 3; --nt) {
+      const int nw = std::min(kMaxWStages, (smem_limit - nt * tb) / wb) & ~1;
+      if (nw >= 4 || (nt == 3 && nw >= 2)) {
+        bs->stages = nt; bs->wstages = nw; bs->proj_warps = 2;
+        bs->ring = std::min(bs->ring, nt);
+        bs->smem_bytes = nt * tb + nw * wb + 1024;
+        break;
+      }
+    }
+  }
+  // Precision of the contraction (include/tkbo.h): the e4m3 correction form saves a third of the tensor work and costs
+  // the feature producers ~20 % more instructions, so AUTO takes it where the tensor pipe binds (wide sample chunks).
+  if (const char* env = getenv("TKBO_PRECISION")) {
+    if (precision == TKBO_PRECISION_AUTO)
+      precision = !strcmp(env, "fast") ? TKBO_PRECISION_FAST : (!strcmp(env, "fp32") ? TKBO_PRECISION_FP32 : precision);
+  }
+  bs->corr8 = precision == TKBO_PRECISION_FAST || (precision == TKBO_PRECISION_AUTO && bs->SC >= 128);
   cudaError_t e = cudaSuccess;
   e = e ? e : cudaMalloc(&bs->Wproj, static_cast<size_t>(bs->Dpad) * proj_k_alloc(DT) * sizeof(uint16_t));
   e = e ? e : cudaMalloc(&bs->theta_hi, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
@@ -410,7 +464,7 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S) {
     return TKBO_ERR_NOMEM;
   }
   int rc = make_theta_map(h, &bs->tm_hi, bs->theta_hi, bs->Salloc, bs->Dpad, bs->SC);
-  if (rc == TKBO_OK) rc = make_theta_map(h, &bs->tm_lo, bs->theta_lo, bs->Salloc, bs->Dpad, bs->SC);
+  if (rc == TKBO_OK) rc = make_theta_map(h, &bs->tm_lo, bs->theta_lo, bs->Salloc, bs->Dpad, bs->SC, bs->corr8 != 0);
   if (rc == TKBO_OK) rc = make_wproj_map(h, &bs->tm_w, bs->Wproj, bs->Dpad, DT);
   if (rc != TKBO_OK) {
     free_basis(bs);
@@ -429,11 +483,16 @@ int basis_destroy(tkbo_handle_t, tkbo_basis_t bs) {
 int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b, const double* Theta,
               int transposed, cudaStream_t stream) {
   TKBO_REQUIRE(h && bs && W && b && Theta, "null pointer");
-  prep_theta_scale_kernel<<<bs->Salloc, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Salloc, bs->unscale);
+  prep_theta_scale_kernel<<<bs->Salloc, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Salloc,
+                                                          bs->corr8 ? 7 : 9, bs->corr8 ? 12 : 0, bs->unscale);
   const size_t total = static_cast<size_t>(bs->Salloc) * bs->Dpad;
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
-  prep_theta_split_kernel<<<blocks, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Dpad, bs->Salloc,
-                                                     bs->unscale, bs->theta_hi, bs->theta_lo);
+  if (bs->corr8)
+    prep_theta_split8_kernel<<<blocks, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Dpad, bs->Salloc,
+                                                        bs->unscale, bs->theta_hi, reinterpret_cast<uint8_t*>(bs->theta_lo));
+  else
+    prep_theta_split_kernel<<<blocks, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Dpad, bs->Salloc,
+                                                       bs->unscale, bs->theta_hi, bs->theta_lo);
   prep_wproj_kernel<<<(bs->Dpad + 127) / 128, 128, 0, stream>>>(W, b, bs->D, bs->d, bs->Dpad, bs->DT,
                                                                 proj_k_alloc(bs->DT), bs->Wproj);
   h->launches += 3;
@@ -442,14 +501,20 @@ int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b
   return TKBO_OK;
 }
 
-template <int DT, int MODE, int NPG>
-static int launch_fused_n(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
-  auto kern = rff_fused_kernel<DT, MODE, NPG>;
+template <int DT, int MODE, int NPG, bool C8>
+static int launch_fused_c(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  auto kern = rff_fused_kernel<DT, MODE, NPG, C8>;
   TKBO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs->smem_bytes));
   kern<<<grid, kNumThreadsFor(NPG), bs->smem_bytes, stream>>>(bs->tm_hi, bs->tm_lo, bs->tm_w, p);
   h->launches += 1;
   TKBO_CUDA_CHECK(cudaGetLastError());
   return TKBO_OK;
+}
+
+template <int DT, int MODE, int NPG>
+static int launch_fused_n(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  return bs->corr8 ? launch_fused_c<DT, MODE, NPG, true>(h, bs, p, grid, stream)
+                   : launch_fused_c<DT, MODE, NPG, false>(h, bs, p, grid, stream);
 }
 
 template <int DT, int MODE>
@@ -489,7 +554,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   TKBO_REQUIRE(mt * bs->n_chunks < (int64_t(1) << 31), "too many work items");
   p->n_mtiles = static_cast<int>(mt);
   p->stages = bs->stages; p->ring = bs->ring; p->acc_bufs = bs->acc_bufs; p->xa_bufs = bs->xa_bufs;
-  p->proj_warps = bs->proj_warps;
+  p->proj_warps = bs->proj_warps; p->wstages = bs->wstages; p->coop = bs->coop;
   p->debug = 0;
   if (const char* env = getenv("TKBO_DEBUG")) p->debug = atoi(env);
   p->trace = h->trace; p->trace_cap = h->trace_cap;
@@ -629,7 +694,7 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   p.N = mt * kTileM; p.d = bs->d; p.S = bs->S; p.SC = bs->SC; p.n_chunks = bs->n_chunks;
   p.n_slabs = bs->Dpad / kSlabK; p.n_mtiles = static_cast<int>(mt);
   p.stages = bs->stages; p.ring = bs->ring; p.acc_bufs = bs->acc_bufs; p.xa_bufs = bs->xa_bufs;
-  p.proj_warps = bs->proj_warps;
+  p.proj_warps = bs->proj_warps; p.wstages = bs->wstages; p.coop = bs->coop;
   p.duel_n = n; p.duel_j0 = j_begin; p.duel_nj = j_end - j_begin;
   p.score_fix = reinterpret_cast<unsigned long long*>(fix);
   p.debug = 0;
@@ -669,7 +734,7 @@ int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg) {
   cfg[0] = bs->SC; cfg[1] = bs->n_chunks; cfg[2] = bs->Dpad / kSlabK; cfg[3] = bs->stages; cfg[4] = bs->acc_bufs;
   cfg[5] = bs->DT; cfg[6] = bs->smem_bytes;
   cfg[7] = static_cast<int32_t>(std::min<int64_t>(h->sm_count, std::max<int64_t>(1, mt) * bs->n_chunks));
-  cfg[8] = bs->ring; cfg[9] = kNumThreadsFor(bs->npg); cfg[10] = bs->xa_bufs; cfg[11] = bs->npg; cfg[12] = bs->proj_warps;
+  cfg[8] = bs->ring; cfg[9] = kNumThreadsFor(bs->npg); cfg[10] = bs->xa_bufs; cfg[11] = bs->npg; cfg[12] = bs->proj_warps; cfg[13] = bs->corr8; cfg[14] = bs->wstages; cfg[15] = bs->coop;
   return TKBO_OK;
 }
 

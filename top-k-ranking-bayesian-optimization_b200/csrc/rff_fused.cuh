@@ -42,6 +42,7 @@ constexpr int kProjWarpsFor(int npg) { return 2; }
 constexpr int kNumThreadsFor(int npg) { return 32 * (4 + 4 * npg + 1 + kProjWarpsFor(npg) + 2); }
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 12;       // smem ring (Theta + W tiles)
+constexpr int kMaxWStages = 8;     // separate (W | b) tile ring (split mode)
 constexpr int kMaxRing = 6;          // TMEM ring (projection result -> Phi hi/lo), 64 columns per slot
 
 // Projection K extent for a template input dimension: 6 split products per dimension + 3 bias terms.
@@ -86,6 +87,10 @@ struct RffParams {
   int acc_bufs;              // 1 or 2 accumulator buffers of SC columns
   int xa_bufs;               // 1 or 2 buffers for the split candidate rows
   int proj_warps;            // 1 or 2 projection-issuing warps (2 needs an even smem ring depth)
+  int coop;                  // 1 (two producer groups only): both groups convert every slab, 32 columns each -- half the
+                             // per-slab latency, for shapes whose TMEM ring has only 3 slots
+  int wstages;               // 0: the (W | b) tile of a slab travels in its Theta stage; > 0: it has its own ring of this
+                             // depth, so projections + feature producers run ahead of the (few, large) Theta stages
   int duel_n;                // > 0: the candidates are the ordered pairs [x_i, x_j] of duel_n base points of dimension d / 2
                              // held in X (dts.py:31-45); a tile = one i and 128 consecutive j; never materialised
   int duel_j0, duel_nj;      // this launch's shard of the second argument: j in [duel_j0, duel_j0 + duel_nj)
@@ -125,6 +130,46 @@ __device__ __forceinline__ void cos_split16(const uint32_t* __restrict__ arg, ui
   }
 }
 
+// Fast-precision variant (C8): 16 projection values -> 8 fp16x2 words of u = 2^12 cos (the hi operand; the 2^-12 is folded
+// into the per-sample unscale), then the operand of ONE e4m3 MMA that carries both correction terms: 4 words e4m3(cos)
+// (against e4m3(2^12 Theta_lo)) and 4 words e4m3(u - fp16(u)) (against e4m3(Theta)); byte order = feature order.
+// ~3e-5 of max|f| instead of ~2e-6, 8 instead of 12 MMAs per slab, six instructions per feature.
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a0, float a1, float a2, float a3) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(a1), "f"(a0));      // first source -> upper byte
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(a3), "f"(a2));
+  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+// u - h for a packed pair of halves h (mixed-precision fma: h * -1 + u, one instruction per value, exact)
+__device__ __forceinline__ void sub_half2(float u0, float u1, uint32_t h2, float& l0, float& l1) {
+  asm("{\n\t.reg .b16 a, b, m;\n\t"
+      "mov.b32 {a, b}, %2;\n\t"
+      "mov.b16 m, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %0, a, m, %3;\n\t"
+      "fma.rn.f32.f16 %1, b, m, %4;\n\t}"
+      : "=f"(l0), "=f"(l1) : "r"(h2), "f"(u0), "f"(u1));
+}
+__device__ __forceinline__ void cos_split16_c8(const uint32_t* __restrict__ arg, uint32_t (&out)[16], bool skip) {
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    float c[4], u[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      c[e] = skip ? 1.f : __cosf(__uint_as_float(arg[4 * jj + e]));
+      u[e] = c[e] * 4096.f;
+    }
+    const __half2 h01 = __floats2half2_rn(u[0], u[1]);
+    const __half2 h23 = __floats2half2_rn(u[2], u[3]);
+    const uint32_t w01 = *reinterpret_cast<const uint32_t*>(&h01), w23 = *reinterpret_cast<const uint32_t*>(&h23);
+    sub_half2(u[0], u[1], w01, l[0], l[1]);
+    sub_half2(u[2], u[3], w23, l[2], l[3]);
+    out[2 * jj] = w01;
+    out[2 * jj + 1] = w23;
+    out[8 + jj] = pack_e4m3x4(c[0], c[1], c[2], c[3]);
+    out[12 + jj] = pack_e4m3x4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // x = x1 + x2 + x3 exactly, each term a bf16 (truncating the fp32 bits keeps every step exact).
 __device__ __forceinline__ void bf16_split3(float x, uint32_t& b1, uint32_t& b2, uint32_t& b3) {
   const uint32_t u = __float_as_uint(x);
@@ -136,7 +181,8 @@ __device__ __forceinline__ void bf16_split3(float x, uint32_t& b1, uint32_t& b2,
   b3 = __float_as_uint(r2) >> 16;
 }
 
-template <int DT, int MODE /* 0 = argmax, 1 = store F, 2 = duel soft-Copeland sums */, int NPG /* producer warp groups: 2, 3 or 4 */>
+template <int DT, int MODE /* 0 = argmax, 1 = store F, 2 = duel soft-Copeland sums */, int NPG /* producer warp groups: 2, 3 or 4 */,
+          bool C8 /* corrections as one e4m3 MMA (tm_lo = the e4m3 tile) instead of two fp16 MMAs */>
 __global__ void __launch_bounds__(kNumThreadsFor(NPG), 1)
 rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                  const __grid_constant__ CUtensorMap tm_w, const RffParams p) {
@@ -157,7 +203,9 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     kAccFull = kAFull + kMaxRing,      // [2]
     kAccEmpty = kAccFull + 2,          // [2]
     kXaFull = kAccEmpty + 2,           // [2] split candidate rows of an item are in TMEM
-    kNumBars = kXaFull + 2
+    kWFull = kXaFull + 2,              // [kMaxWStages] split mode: TMA landed the (W | b) tile of a slab
+    kWEmpty = kWFull + kMaxWStages,    // [kMaxWStages] its projection MMAs finished
+    kNumBars = kWEmpty + kMaxWStages
   };
   __shared__ uint64_t bars[kNumBars];
   __shared__ uint32_t tmem_base_smem;
@@ -168,7 +216,9 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   // kernel parameters used in the loops, as registers
   const int SC = p.SC, n_slabs = p.n_slabs, n_chunks = p.n_chunks, stages = p.stages, ring = p.ring;
   const int acc_bufs = p.acc_bufs, xa_bufs = p.xa_bufs;
-  const int sbytes = stage_stride_bytes(SC, DT);
+  const int wstages = p.wstages;
+  const bool split_w = wstages > 0;
+  const int sbytes = split_w ? 2 * SC * 128 : stage_stride_bytes(SC, DT);
   const int n_items = p.n_mtiles * n_chunks;
   const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int total = my_items * n_slabs;              // slab iterations of this CTA
@@ -183,7 +233,11 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     }
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&bars[kPFull + s], 1);
-      mbar_init(&bars[kAFull + s], 4);       // one arrival per producer warp of the owning group
+      mbar_init(&bars[kAFull + s], p.coop ? 8 : 4);   // one arrival per producer warp working on the slab
+    }
+    for (int s = 0; s < kMaxWStages; ++s) {
+      mbar_init(&bars[kWFull + s], 1);
+      mbar_init(&bars[kWEmpty + s], 1);      // one commit by the projection warp that used it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars[kAccFull + a], 2);     // one commit per main MMA warp
@@ -207,31 +261,54 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t xa_col0 = acc_bufs * SC;                         // split candidate rows follow the accumulators (TMEM form)
-  const uint32_t xa_smem0 = smem0 + stages * sbytes;              // or two buffers after the stage ring (smem form)
+  const uint32_t w_smem0 = smem0 + stages * sbytes;               // split mode: the (W | b) ring follows the Theta stages
+  const uint32_t xa_smem0 = w_smem0 + wstages * proj_w_bytes(DT); // candidate rows, smem form: two buffers after the rings
   const uint32_t ring_col0 = kTmemCols - ring * kSlabK;           // the ring occupies the top columns
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer (warp-converged, one elected issuer)
     int st = 0, it = 0;
     uint32_t ph = 0;
-    const uint32_t txbytes = (p.debug & 4) ? proj_w_bytes(DT) : stage_tx_bytes(SC, DT);
     const bool theta = !(p.debug & 4);               // ablation 4: no Theta tile loads
+    const uint32_t txbytes = split_w ? 2 * SC * 128 : ((p.debug & 4) ? proj_w_bytes(DT) : stage_tx_bytes(SC, DT));
+    // split mode: (W | b) tiles run up to `wstages` slabs ahead of the Theta tiles; a tile beyond the current slab is only
+    // fetched if its stage is already free (test), the current slab's tile is waited for
+    int jw = 0, wst = 0;
+    uint32_t wph = 0;
+    auto issue_w = [&](int slab_w, uint32_t dst, uint32_t full) {
+#pragma unroll
+      for (int t = 0; t < proj_tiles(DT); ++t) tma_load_2d(dst + t * kPTile, &tm_w, full, t * 64, slab_w * kSlabK);
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int chunk = item % n_chunks;
       for (int slab = 0; slab < n_slabs; ++slab, ++it) {
+        if (split_w) {
+          while (jw < total && jw < it + wstages) {
+            const uint32_t emp = bar0 + 8 * (kWEmpty + wst);
+            if (jw <= it) mbar_wait(emp, wph ^ 1);
+            else if (!mbar_test_wait(emp, wph ^ 1)) break;
+            if (elect_one()) {
+              const uint32_t full = bar0 + 8 * (kWFull + wst);
+              mbar_arrive_expect_tx(full, proj_w_bytes(DT));
+              issue_w(jw % n_slabs, w_smem0 + wst * proj_w_bytes(DT), full);
+            }
+            __syncwarp();
+            ++jw;
+            if (++wst == wstages) { wst = 0; wph ^= 1; }
+          }
+        }
         mbar_wait(bar0 + 8 * (kBEmpty + st), ph ^ 1);
         trace_event(p, kTrTmaEmpty, it);
         if (elect_one()) {
           const uint32_t sb = smem0 + st * sbytes;
           const uint32_t full = bar0 + 8 * (kBFull + st);
-          mbar_arrive_expect_tx(full, txbytes);
+          if (split_w && !theta) mbar_arrive(full);
+          else mbar_arrive_expect_tx(full, txbytes);
           if (theta) {
             tma_load_2d(sb, &tm_hi, full, slab * kSlabK, chunk * SC);
-            tma_load_2d(sb + SC * 128, &tm_lo, full, slab * kSlabK, chunk * SC);
+            tma_load_2d(sb + SC * 128, &tm_lo, full, slab * kSlabK * (C8 ? 2 : 1), chunk * SC);   // C8: byte tensor
           }
-#pragma unroll
-          for (int t = 0; t < proj_tiles(DT); ++t)
-            tma_load_2d(sb + 2 * SC * 128 + t * kPTile, &tm_w, full, t * 64, slab * kSlabK);
+          if (!split_w) issue_w(slab, sb + 2 * SC * 128, full);
         }
         __syncwarp();
         trace_event(p, kTrTmaIssued, it);
@@ -249,11 +326,14 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     if (h < npw) {
       constexpr uint32_t idesc_proj = idesc_bf16_f32(kTileM, kSlabK);
       constexpr uint32_t kWDescHi = smem_desc_hi(8 * kPRow, kPRow == 128 ? 2u : (kPRow == 64 ? 4u : 6u));
-      const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
-      const uint32_t desc_w0 = smem_desc_lo(smem0 + 2 * SC * 128);        // the (W | b) tile(s) follow Theta hi, lo
+      // the (W | b) tile(s) follow Theta hi, lo inside the stage, or (split mode) sit in their own ring
+      const int wn = split_w ? wstages : stages;
+      const uint32_t desc_stage = static_cast<uint32_t>(split_w ? proj_w_bytes(DT) : sbytes) >> 4;
+      const uint32_t desc_w0 = smem_desc_lo(split_w ? w_smem0 : smem0 + 2 * SC * 128);
+      const uint32_t wfull0 = bar0 + 8 * (split_w ? kWFull : kBFull);
       int slab = h % n_slabs, item = h / n_slabs;      // position of j inside this CTA's item sequence
-      int st = h % stages, slot = h % ring;
-      uint32_t ph = (h / stages) & 1;
+      int st = h % wn, slot = h % ring;
+      uint32_t ph = (h / wn) & 1;
       int fst = 0;                                     // smem stage of slab j - ring (valid once j >= ring)
       uint32_t fph = 0;
       bool new_item = true;
@@ -263,7 +343,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       if (xa_bufs == 1 && h < total)
         for (int i = 0; i < item; ++i) mbar_wait(bar0 + 8 * kXaFull, static_cast<uint32_t>(i) & 1);
       for (int j = h; j < total; j += npw) {
-        mbar_wait(bar0 + 8 * (kBFull + st), ph);
+        mbar_wait(wfull0 + 8 * st, ph);
         if (j >= ring) mbar_wait(bar0 + 8 * (kBEmpty + fst), fph);
         if (new_item) {
           const int xb = (xa_bufs == 2) ? (item & 1) : 0;
@@ -291,13 +371,14 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             }
           }
           tc_commit(bar0 + 8 * (kPFull + slot));
+          if (split_w) tc_commit(bar0 + 8 * (kWEmpty + st));
         }
         __syncwarp();
         trace_event(p, kTrMmaProjIssued, j);
         // advance by npw slab iterations
         if (j >= ring) { fst += npw; if (fst >= stages) { fst -= stages; fph ^= 1; } }
         else if (j + npw >= ring) { fst = (j + npw - ring) % stages; fph = 0; }
-        st += npw; if (st >= stages) { st -= stages; ph ^= 1; }
+        st += npw; if (st >= wn) { st -= wn; ph ^= 1; }
         slot += npw; if (slot >= ring) slot -= ring;
         slab += npw;
         while (slab >= n_slabs) {
@@ -321,6 +402,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int h = warp - kMainWarp;
     const int NH = SC >> 1;
     const uint32_t idesc = idesc_f16_f32(kTileM, NH);
+    const uint32_t idesc8 = idesc_e4m3_f32(kTileM, NH);
     // descriptor low words advance by plain adds: (addr >> 4) never carries out of its 14-bit field
     const uint32_t desc_lo0 = smem_desc_lo(smem0 + h * NH * 128);
     const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
@@ -328,20 +410,24 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const bool hi_only = (p.debug & 1) != 0;
     const bool pairing = ring >= 5 && !(p.debug & 8);  // a pair holds two ring slots while its MMAs run
     int st = 0, slot = 0, ab = 0, slab = 0, nitem = 0;
-    uint32_t sph = 0, aph = 0;
-    // a_full implies (through p_full and the projection warp's wait) that the stage's Theta tiles have landed
+    uint32_t sph = 0, aph = 0, bph = 0;
+    // combined mode: a_full implies (through p_full and the projection warp's wait) that the stage's Theta tiles have
+    // landed; split mode: the Theta stage has its own wait
     for (int it = 0; it < total;) {
       if (slab == 0) {
         mbar_wait(bar0 + 8 * (kAccEmpty + ab), aph ^ 1);
         if (h == 0) trace_event(p, kTrMmaAccEmpty, nitem);
       }
+      if (split_w) mbar_wait(bar0 + 8 * (kBFull + st), bph);
       mbar_wait(bar0 + 8 * (kAFull + slot), sph);
       // second slab of the burst: same item, pair alignment of this warp, operand already produced
       int st2 = st + 1, slot2 = slot + 1;
       uint32_t sph2 = sph;
       if (st2 == stages) st2 = 0;
       if (slot2 == ring) { slot2 = 0; sph2 ^= 1; }
-      const bool two = pairing && ((it & 1) == h) && (slab + 1 < n_slabs) && mbar_test_wait(bar0 + 8 * (kAFull + slot2), sph2);
+      const uint32_t bph2 = (st2 == 0) ? (bph ^ 1) : bph;
+      const bool two = pairing && ((it & 1) == h) && (slab + 1 < n_slabs) && mbar_test_wait(bar0 + 8 * (kAFull + slot2), sph2) &&
+                       (!split_w || mbar_test_wait(bar0 + 8 * (kBFull + st2), bph2));
       if (h == 0) trace_event(p, kTrMmaAFull, it);
       tc_fence_after();
       if (elect_one()) {
@@ -357,8 +443,13 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             const uint32_t a_lo = a_hi + kUmmaK / 2;
             mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_hi + koff), idesc, (sl | k) != 0);
             if (!hi_only) {
-              mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_lo + koff), idesc, 1);
-              mma_f16_ts(d_tmem, a_lo, smem_desc_from_lo(b_hi + koff), idesc, 1);
+              if constexpr (C8) {
+                // K = 32 e4m3: [cos (16) | u - fp16(u) (16)] . [2^12 Theta_lo (16) | Theta (16)], 32 bytes of the lo tile
+                mma_f8_ts(d_tmem, a_lo, smem_desc_from_lo(b_lo + koff), idesc8, 1);
+              } else {
+                mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_lo + koff), idesc, 1);
+                mma_f16_ts(d_tmem, a_lo, smem_desc_from_lo(b_hi + koff), idesc, 1);
+              }
             }
           }
           tc_commit(bar0 + 8 * (kBEmpty + st_));
@@ -371,7 +462,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       if (h == 0) trace_event(p, kTrMmaCommitted, it);
       const int adv = two ? 2 : 1;
       it += adv;
-      st += adv; if (st >= stages) st -= stages;
+      st += adv; if (st >= stages) { st -= stages; bph ^= 1; }
       slot += adv; if (slot >= ring) { slot -= ring; sph ^= 1; }
       slab += adv;
       if (slab == n_slabs) {
@@ -387,6 +478,34 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int q = warp & 3;                          // TMEM lane quarter of this warp
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const bool skip = (p.debug & 2) != 0;
+    auto split16 = [](const uint32_t* a, uint32_t (&o)[16], bool sk) {
+      if constexpr (C8) cos_split16_c8(a, o, sk); else cos_split16(a, o, sk);
+    };
+    if (NPG == 2 && p.coop) {
+      // latency form: every slab is converted by both groups, group g taking columns [32 g, 32 g + 32)
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < total; ++it) {
+        mbar_wait(bar0 + 8 * (kPFull + slot), ph);
+        if (q == 0) trace_event(p, kTrProdPFull + 2 * group, it);
+        tc_fence_after();
+        const uint32_t col = tmem_base + lane_base + ring_col0 + slot * kSlabK + group * 32;
+        uint32_t r0[16], r1[16], out[16];
+        tmem_ld_x16(col, r0);
+        tmem_ld_x16(col + 16, r1);
+        tmem_wait_ld();
+        split16(r0, out, skip);
+        tmem_st_x16(col, out);
+        split16(r1, out, skip);
+        tmem_st_x16(col + 16, out);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * (kAFull + slot));
+        if (q == 0) trace_event(p, kTrProdArrived + 2 * group, it);
+        if (++slot == ring) { slot = 0; ph ^= 1; }
+      }
+    } else {
     int slot = group % ring;
     uint32_t ph = (group / ring) & 1;
     int n = 0;
@@ -401,16 +520,16 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       tmem_ld_x16(col, r0);
       tmem_ld_x16(col + 16, r1);
       tmem_wait_ld();
-      cos_split16(r0, out, skip);
+      split16(r0, out, skip);
       tmem_st_x16(col, out);
       tmem_ld_x16(col + 32, r0);
-      cos_split16(r1, out, skip);
+      split16(r1, out, skip);
       tmem_st_x16(col + 16, out);
       tmem_ld_x16(col + 48, r1);
       tmem_wait_ld();
-      cos_split16(r0, out, skip);
+      split16(r0, out, skip);
       tmem_st_x16(col + 32, out);
-      cos_split16(r1, out, skip);
+      split16(r1, out, skip);
       tmem_st_x16(col + 48, out);
       tmem_wait_st();
       tc_fence_before();
@@ -419,6 +538,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       if (q == 0) trace_event(p, kTrProdArrived + 2 * group, n);
       slot += NPG;
       if (slot >= ring) { slot -= ring; ph ^= 1; }
+    }
     }
   } else {
     // ------------------------------------------------------------------ candidate rows + epilogue

@@ -247,7 +247,12 @@ class SharedBasis:
     """One RFF basis (W (D, d), b (D,)) shared by S posterior weight samples Theta (D, S), resident on one GPU in
     the fused kernel's operand layout.  ``argmax`` / ``eval`` stream any number of candidates through it."""
 
-    def __init__(self, W, b, Theta, device=None):
+    PRECISIONS = {"auto": 0, "fp32": 1, "fast": 2}
+
+    def __init__(self, W, b, Theta, device=None, precision="auto"):
+        """``precision``: "fp32" = three fp16 tensor-core products per term (fp32 emulation, ~2e-6 of max|f|); "fast" =
+        fp16 hi*hi + one e4m3 product for both correction terms (~3e-5 of max|f|, inside the path's 1e-4 tolerance, two
+        thirds of the tensor work); "auto" = fast where the tensor pipe binds (sample chunks >= 128)."""
         torch = nat.require_cuda()
         self.device = _device(device)
         self.W, self.b, self.Theta = _f64(W, self.device), _f64(b, self.device).reshape(-1), _f64(Theta, self.device)
@@ -256,8 +261,8 @@ class SharedBasis:
         assert self.Theta.shape[0] == self.D and self.b.shape[0] == self.D, "SharedBasis: shape mismatch"
         self._h = nat.handle(self.device.index)
         self._basis = ctypes.c_void_p()
-        nat.check(nat.lib().tkbo_rff_basis_create(self._h, ctypes.byref(self._basis), self.D, self.d, self.S),
-                  "tkbo_rff_basis_create")
+        nat.check(nat.lib().tkbo_rff_basis_create_ex(self._h, ctypes.byref(self._basis), self.D, self.d, self.S,
+                                                     self.PRECISIONS[precision]), "tkbo_rff_basis_create_ex")
         nat.check(nat.lib().tkbo_rff_basis_set(self._h, self._basis, nat.ptr(self.W), nat.ptr(self.b), nat.ptr(self.Theta), 0,
                                                nat.current_stream_ptr(self.device)), "tkbo_rff_basis_set")
         self._torch = torch
@@ -305,20 +310,23 @@ class SharedBasis:
                 print("Retry limit exceeded")
                 raise ValueError("Failed")
 
-    def error_bound(self, rel_feature_error=4e-6):
+    def error_bound(self, rel_feature_error=None):
         """Per-sample absolute error bound (S,) of the fused kernel's values: the feature map is evaluated in
         fp32 (argument rounding, cos.approx, fp16 hi/lo split: each cos value is good to ~1e-6, measured
         <= 4e-6 for |x.w + b| up to ~50), so |f_gpu - f_fp64| <= rel_feature_error * ||sqrt(2/D) theta_s||_2 * sqrt(D)
         in the worst case and ~rel_feature_error * ||sqrt(2/D) theta_s||_2 in practice (independent errors).
         A well-posed posterior has ||sqrt(2/D) theta_s|| ~ max|f_s|, i.e. ~1e-6 relative; an ill-posed
-        regression (ff.py:80-82 inverts phi phi^T without jitter) can inflate it by orders of magnitude."""
+        regression (ff.py:80-82 inverts phi phi^T without jitter) can inflate it by orders of magnitude.
+        With the e4m3 correction form (precision "fast") the per-product error is ~2^-12 * 2^-4 instead: 1e-4 here."""
+        if rel_feature_error is None:
+            rel_feature_error = 1e-4 if self.config(1)["e4m3_corrections"] else 4e-6
         return rel_feature_error * (self.Theta * float(np.sqrt(2.0 / self.D))).norm(dim=0)
 
     def config(self, N):
         cfg = (ctypes.c_int32 * 16)()
         nat.check(nat.lib().tkbo_rff_basis_config(self._h, self._basis, int(N), cfg), "tkbo_rff_basis_config")
         keys = ["S_chunk", "n_chunks", "n_slabs", "stages", "acc_bufs", "d_template", "smem_bytes", "grid",
-                "tmem_ring", "threads", "row_bufs", "producer_groups", "proj_warps"]
+                "tmem_ring", "threads", "row_bufs", "producer_groups", "proj_warps", "e4m3_corrections", "w_stages", "producers_share_slab"]
         return dict(zip(keys, list(cfg)))
 
     def _candidates(self, X):
