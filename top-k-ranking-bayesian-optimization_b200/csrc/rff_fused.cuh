@@ -210,6 +210,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   __shared__ uint64_t bars[kNumBars];
   __shared__ uint32_t tmem_base_smem;
   __shared__ int is_last_cta;
+  __shared__ __align__(16) float thr_s[256];       // MODE 0: running per-sample maxima of the current chunk (see the epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -613,33 +614,39 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     stage_rows(0);
     if (xa_bufs == 2) stage_rows(1);
 
-    int ab = 0, nitem = 0, cur_chunk = -1;
+    int ab = 0, nitem = 0;
     uint32_t aph = 0;
-    float bestv[8];
-    uint32_t bestrow[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { bestv[j] = -INFINITY; bestrow[j] = 0xFFFFFFFFu; }
-    // one atomicMax per (warp, sample) whenever the CTA moves to another sample chunk, and at the end
-    auto flush_best = [&]() {
-      if (cur_chunk < 0) return;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int s = cur_chunk * SC + j * 32 + lane;
-        if (j * 32 < SC && s < p.S && bestrow[j] != 0xFFFFFFFFu)
-          atomicMax(p.packed + s, pack_val_row(bestv[j] + 0.0f, bestrow[j]));
-        bestv[j] = -INFINITY;
-        bestrow[j] = 0xFFFFFFFFu;
-      }
-    };
+    // MODE 0: thr_s[c] is a lower bound of the running maximum of sample s_base + c over everything any CTA has recorded
+    // so far (the global keys, re-read at every item, plus this CTA's own finds).  A block of 32 columns in which no row
+    // reaches its column's bound cannot change the result and costs one compare per value; the full (max, lowest row)
+    // reduction + atomicMax runs only for blocks that may improve a sample -- after the first tiles that is rare
+    // (a sample's maximum improves ~ln(#tiles) times).  Ties go through the slow path: the key's ~row decides.
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
       const int mtile = item / n_chunks;
       const int chunk = item % n_chunks;
       const int s_base = chunk * SC;
+      float thr_new[2];
       if constexpr (MODE == 0) {
-        if (chunk != cur_chunk) { flush_best(); cur_chunk = chunk; }
+        // the bounds of this item's chunk: loads issued before the wait, stored after it
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int c = t * 128 + q * 32 + lane;
+          const unsigned long long pk = (c < SC) ? __ldcg(p.packed + s_base + c) : 0ull;
+          thr_new[t] = (pk == 0ull) ? -INFINITY : f32_from_orderable(static_cast<uint32_t>(pk >> 32));
+        }
       }
       mbar_wait(bar0 + 8 * (kAccFull + ab), aph);
+      if constexpr (MODE == 0) {
+        // the four epilogue warps share thr_s: nobody still reads the previous item's bounds / everybody sees the new ones
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int c = t * 128 + q * 32 + lane;
+          if (c < SC) thr_s[c] = thr_new[t];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       if (q == 0) trace_event(p, kTrEpiAccFull, nitem);
       tc_fence_after();
       const long long row0 = static_cast<long long>(mtile) * kTileM + q * 32;
@@ -658,23 +665,34 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 #pragma unroll
               for (int c = 0; c < 32; ++c) v[c] = row_ok ? v[c] : 0xFF800000u;     // -inf
             }
-            float mine = -INFINITY;
-            unsigned minehit = 0u;
+            bool reach = false;                        // !(val < bound): also true for NaN, which the slow path skips
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float val = __uint_as_float(v[c]);
-              const float m = warp_max_f32(val);
-              const unsigned hit = __ballot_sync(0xffffffffu, val == m);
-              if (lane == c) { mine = m; minehit = hit; }
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(&thr_s[j * 32 + c4 * 4]);
+              reach |= !(__uint_as_float(v[4 * c4 + 0]) < t4.x);
+              reach |= !(__uint_as_float(v[4 * c4 + 1]) < t4.y);
+              reach |= !(__uint_as_float(v[4 * c4 + 2]) < t4.z);
+              reach |= !(__uint_as_float(v[4 * c4 + 3]) < t4.w);
             }
-            // lane c now holds (max, rows attaining it) of column c; bestv/bestrow are indexed by j dynamically:
-            // select without local-memory indexing.  Strict > keeps the lowest row (items come in row order).
+            if (__any_sync(0xffffffffu, reach)) {
+              float mine = -INFINITY;
+              unsigned minehit = 0u;
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-              if (jj == j && minehit != 0u && mine > bestv[jj]) {
-                bestv[jj] = mine;
-                bestrow[jj] = static_cast<uint32_t>(row0) + (__ffs(minehit) - 1);
+              for (int c = 0; c < 32; ++c) {
+                const float val = __uint_as_float(v[c]);
+                const float m = warp_max_f32(val);
+                const unsigned hit = __ballot_sync(0xffffffffu, val == m);
+                if (lane == c) { mine = m; minehit = hit; }
               }
+              // lane c holds (max, rows attaining it) of column c; record it if it may beat (or tie) the bound
+              const int cs = j * 32 + lane;
+              if (minehit != 0u && mine > -INFINITY && !(mine < thr_s[cs]) && s_base + cs < p.S) {
+                atomicMax(p.packed + s_base + cs,
+                          pack_val_row(mine + 0.0f, static_cast<uint32_t>(row0) + (__ffs(minehit) - 1)));
+                thr_s[cs] = mine;                      // racing warps may leave the lower of two finds: still a lower bound
+              }
+              __syncwarp();
+            }
           } else if constexpr (MODE == 1) {
             if (row_ok) {
 #pragma unroll
@@ -715,7 +733,6 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       if (++ab == acc_bufs) { ab = 0; aph ^= 1; }
       stage_rows(nitem + xa_bufs);
     }
-    if constexpr (MODE == 0) flush_best();
   }
 
   // ---------------------------------------------------------------------- teardown + final reduce
