@@ -209,6 +209,11 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # communicator set-up (not a step): NCCL connects its channels lazily during the first collectives
+        warm = torch.zeros(64, dtype=torch.int64, device=dev)
+        for _ in range(20):
+            dist.all_reduce(warm, op=dist.ReduceOp.MAX)
+        torch.cuda.synchronize()
     N, d, D, S, lo, hi, ls, desc = WORKLOADS[args.workload]
     W, b, Theta = make_basis_arrays(D, d, S, ls, lo, hi)
     basis = pkg.fourier_features.SharedBasis(W, b, Theta, device=dev)
