@@ -230,7 +230,20 @@ def run_gpu(args):
     offset = rank * N
     h = nat.handle(local)
 
+    # N > 1: the per-rank (value, index) keys are merged over NVLink peer memory by the kernel itself (the last CTA pushes
+    # the S keys into every rank's buffer; a tiny merge kernel acquires the flags); TKBO_MERGE=nccl takes the
+    # all_reduce(MAX)-over-int64 path instead
+    peer = None
+    merge = "none"
+    if world > 1:
+        merge = "one int64 all_reduce(MAX) (NCCL)"
+        if os.environ.get("TKBO_MERGE", "peer") == "peer":
+            peer = pkg.distributed.PeerMerge(S, dev)
+            merge = "keys pushed to peer memory by the kernel's last CTA + flag-acquiring merge kernel (no collective call)"
+
     def step(i):
+        if peer is not None:
+            return peer.argmax(basis, dev_bufs[i % n_rot], offset)
         if world > 1:       # key output + one all_reduce(MAX) over int64 + unpack
             return pkg.distributed.sharded_argmax_fast(basis, dev_bufs[i % n_rot], offset)
         return basis.argmax(dev_bufs[i % n_rot], idx_offset=offset)
@@ -315,7 +328,7 @@ def run_gpu(args):
                 "data": "synthetic",
                 "config": {"workload": desc, "N_per_gpu": N, "d": d, "D": D, "S": S,
                            "l2": f"{n_rot} rotating candidate buffers ({n_rot * N * d * 4 >> 20} MiB > 126 MiB L2)",
-                           "tiling": cfg, "parallelism": f"candidate shards x{world}, one int64 all_reduce(MAX) merge"},
+                           "tiling": cfg, "parallelism": f"candidate shards x{world}, merge: {merge}"},
                 "e2e": {"value": world * N * S / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "what": "tkbo_rff_argmax_host (C ABI, host buffers): pinned candidates + fp64 basis -> device (candidate chunks "

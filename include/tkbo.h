@@ -100,6 +100,19 @@ int tkbo_copeland_finish(tkbo_handle_t h, const uint64_t* fix, int S, int n, flo
 int tkbo_rff_argmax_key(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, int64_t idx_offset,
                         int64_t* out_key, void* stream);
 int tkbo_unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val, int64_t* out_idx, void* stream);
+/* The same merge fused into the kernel over NVLink peer memory (no collective call; SURVEY 8(e)'s all-gather of 8 S bytes
+ * per rank done by the producing kernel): every rank owns a peer buffer of tkbo_peer_buffer_bytes(world, S) bytes, zeroed
+ * once, that ALL ranks of the node can store to (peer_bufs[r] = rank r's buffer as mapped in this process: CUDA IPC /
+ * torch symmetric memory).  tkbo_rff_argmax_peer runs the fused kernel and has its last CTA store the S keys into slot
+ * (epoch & 1, rank) of every rank's buffer, then release flag[rank] = epoch there; tkbo_merge_peer_keys (same stream,
+ * same epoch, on every rank) acquires all `world` flags of the LOCAL buffer, takes the per-sample maximum and unpacks.
+ * Epochs start at 1 and increase by one per call pair on all ranks alike; world <= 8 (one NVSwitch node).  If a peer
+ * never delivers, the merge gives up after ~10 s and returns index -2 for every sample instead of hanging. */
+int64_t tkbo_peer_buffer_bytes(int world, int S);
+int tkbo_rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, int64_t idx_offset,
+                         void* const* peer_bufs, int world, int rank, uint64_t epoch, void* stream);
+int tkbo_merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int S, uint64_t epoch, float* out_val,
+                         int64_t* out_idx, void* stream);
 /* Per-rank partial results [G, S] (e.g. after an all-gather) -> global (value, lowest index). */
 int tkbo_merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, int G, int S,
                       float* out_val, int64_t* out_idx, void* stream);

@@ -114,6 +114,22 @@ def test_rff_precision_modes(pbo, N, D, d, S):
     assert errs["fast"] > errs["fp32"]                     # the modes really differ
 
 
+def test_peer_merge_single_rank(pbo):
+    """The peer-memory merge with one rank (its own buffer is the only peer): keys pushed by the kernel's last CTA, flags,
+    epoch parity and the merge kernel give the same (value, index) as the plain call, over several epochs and shapes of
+    the same buffer.  (Two and eight ranks: tools/peer_merge_check.py under torchrun.)"""
+    rng = np.random.default_rng(77)
+    X, W, b, Theta = _basis_inputs(rng, 5000, 192, 3, 40, 0.0, 1.0, 0.5)
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    pm = pbo.distributed.PeerMerge(basis.S, "cuda:0")
+    for it in range(5):
+        Xi = np.ascontiguousarray(X[it * 700:(it + 1) * 700 + 1500])
+        val, idx = pm.argmax(basis, Xi, idx_offset=1000 * it)
+        val0, idx0 = basis.argmax(Xi, idx_offset=1000 * it)
+        assert torch.equal(val, val0) and torch.equal(idx, idx0)
+    assert pm.epoch == 5
+
+
 def test_rff_argmax_wide_dynamic_range_theta(pbo):
     """Per-sample power-of-two scaling keeps tiny and huge weight samples equally accurate."""
     rng = np.random.default_rng(5)

@@ -17,6 +17,11 @@ int basis_destroy(tkbo_handle_t h, tkbo_basis_t bs);
 int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b, const double* Theta, int transposed,
               cudaStream_t stream);
 int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg);
+size_t peer_buffer_words(int world, int S);
+int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs,
+                    int world, int rank, uint64_t epoch, cudaStream_t stream);
+int merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int S, uint64_t epoch, float* out_val, int64_t* out_idx,
+                    cudaStream_t stream);
 int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, float* out_val,
                int64_t* out_idx, cudaStream_t stream);
 int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float* out_F, int64_t ldf, cudaStream_t stream);
@@ -225,6 +230,21 @@ int tkbo_merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, in
                       int64_t* out_idx, void* stream) {
   TKBO_ENTER(h);
   return merge_argmax(h, vals, idx, G, S, out_val, out_idx, as_stream(stream));
+}
+
+int64_t tkbo_peer_buffer_bytes(int world, int S) {
+  if (world < 1 || world > 8 || S < 1) return TKBO_ERR_INVALID;
+  return static_cast<int64_t>(peer_buffer_words(world, S) * sizeof(unsigned long long));
+}
+int tkbo_rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, int64_t idx_offset,
+                         void* const* peer_bufs, int world, int rank, uint64_t epoch, void* stream) {
+  TKBO_ENTER(h);
+  return rff_argmax_peer(h, basis, X, N, idx_offset, peer_bufs, world, rank, epoch, as_stream(stream));
+}
+int tkbo_merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int S, uint64_t epoch, float* out_val,
+                         int64_t* out_idx, void* stream) {
+  TKBO_ENTER(h);
+  return merge_peer_keys(h, local_buf, world, S, epoch, out_val, out_idx, as_stream(stream));
 }
 
 int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,

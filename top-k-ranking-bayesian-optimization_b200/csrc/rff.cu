@@ -548,6 +548,8 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->done_counter = reinterpret_cast<unsigned int*>(bs->packed + bs->Salloc);
   p->out_val = nullptr; p->out_idx = nullptr; p->out_key = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
   p->duel_n = 0; p->duel_j0 = 0; p->duel_nj = 0; p->score_fix = nullptr;
+  p->peer_world = 0; p->peer_rank = 0; p->peer_epoch = 0;
+  for (int r = 0; r < 8; ++r) p->peer_buf[r] = nullptr;
   p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
   p->n_slabs = bs->Dpad / kSlabK;
   const int64_t mt = (N + kTileM - 1) / kTileM;
@@ -586,6 +588,78 @@ int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, 
   p.out_key = reinterpret_cast<long long*>(out_key);
   p.idx_offset = idx_offset;
   return dispatch_fused<0>(h, bs, p, grid, stream);
+}
+
+// ---- merge over peer memory ---------------------------------------------------------------------------------------
+// Peer buffer of a rank (uint64 units): keys[2][world][S] (epoch parity, source rank, sample) then flags[8] (source rank ->
+// last epoch that rank has delivered).  Rank r's fused kernel of epoch e stores its keys into slot (e & 1, r) of every
+// rank's buffer and then releases flag[r] = e; the merge kernel of epoch e acquires flag[r] >= e for all r, takes the
+// maximum over the `world` slots and unpacks.  Two parities suffice: a rank can only start epoch e + 2 after its merge of
+// e + 1, which has seen every peer's e + 1 keys, and those were launched behind that peer's merge of e.
+size_t peer_buffer_words(int world, int S) { return 2ull * world * S + 8; }
+
+int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs,
+                    int world, int rank, uint64_t epoch, cudaStream_t stream) {
+  RffParams p;
+  int grid = 0;
+  int rc = fill_params(h, bs, X, N, &p, &grid);
+  if (rc != TKBO_OK) return rc;
+  TKBO_REQUIRE(peer_bufs && world >= 1 && world <= 8 && rank >= 0 && rank < world && epoch >= 1, "bad peer arguments");
+  TKBO_REQUIRE(idx_offset >= 0 && idx_offset + N <= (int64_t(1) << 32) - 1, "global index must stay below 2^32 - 1 for the key form");
+  for (int r = 0; r < world; ++r) {
+    TKBO_REQUIRE(peer_bufs[r] != nullptr, "null peer buffer");
+    p.peer_buf[r] = static_cast<unsigned long long*>(peer_bufs[r]);
+  }
+  p.peer_world = world; p.peer_rank = rank; p.peer_epoch = epoch;
+  p.idx_offset = idx_offset;
+  return dispatch_fused<0>(h, bs, p, grid, stream);
+}
+
+// One block per 256 samples; its first `world` threads wait for the flags (bounded: ~10 s, then every index of the block
+// reads -2 so that a lost peer shows up as an error instead of a hang).
+__global__ void merge_peer_keys_kernel(const unsigned long long* __restrict__ buf, int world, int S, unsigned long long epoch,
+                                       float* __restrict__ out_val, long long* __restrict__ out_idx) {
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const unsigned long long* flag = buf + 2ull * world * S + threadIdx.x;
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long f;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(flag) : "memory");
+      if (f >= epoch) break;
+      if (clock64() - t0 > 20000000000ll) { timed_out = 1; break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  if (timed_out) { out_val[s] = __int_as_float(0x7fc00000); out_idx[s] = -2; return; }
+  long long best = kEmptyKey;
+  const unsigned long long* keys = buf + static_cast<size_t>(epoch & 1ull) * world * S;
+  for (int r = 0; r < world; ++r) {
+    unsigned long long k;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(k) : "l"(keys + static_cast<size_t>(r) * S + s) : "memory");
+    best = max(best, static_cast<long long>(k));
+  }
+  float v;
+  long long gi;
+  argmax_unkey(best, &v, &gi);
+  out_val[s] = v;
+  out_idx[s] = gi;
+}
+
+int merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int S, uint64_t epoch, float* out_val, int64_t* out_idx,
+                    cudaStream_t stream) {
+  TKBO_REQUIRE(h && local_buf && out_val && out_idx, "null pointer");
+  TKBO_REQUIRE(world >= 1 && world <= 8 && S >= 1 && epoch >= 1, "bad peer arguments");
+  merge_peer_keys_kernel<<<(S + 255) / 256, 256, 0, stream>>>(static_cast<const unsigned long long*>(local_buf), world, S, epoch,
+                                                               out_val, reinterpret_cast<long long*>(out_idx));
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
 }
 
 __global__ void unpack_key_kernel(const long long* __restrict__ key, int S, float* __restrict__ out_val,
@@ -695,6 +769,8 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   p.n_slabs = bs->Dpad / kSlabK; p.n_mtiles = static_cast<int>(mt);
   p.stages = bs->stages; p.ring = bs->ring; p.acc_bufs = bs->acc_bufs; p.xa_bufs = bs->xa_bufs;
   p.proj_warps = bs->proj_warps; p.wstages = bs->wstages; p.coop = bs->coop;
+  p.peer_world = 0; p.peer_rank = 0; p.peer_epoch = 0;
+  for (int r = 0; r < 8; ++r) p.peer_buf[r] = nullptr;
   p.duel_n = n; p.duel_j0 = j_begin; p.duel_nj = j_end - j_begin;
   p.score_fix = reinterpret_cast<unsigned long long*>(fix);
   p.debug = 0;

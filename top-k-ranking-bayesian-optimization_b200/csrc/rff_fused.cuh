@@ -72,6 +72,12 @@ struct RffParams {
   float* out_val;            // [S]
   long long* out_idx;        // [S]
   long long* out_key;        // [S] or null: signed-orderable (value, ~global index) key instead of out_val/out_idx
+  // multi-GPU merge without a collective call: the last CTA stores this rank's S keys into slot `peer_rank` of EVERY
+  // rank's peer buffer (NVLink peer stores; buffers mapped into this process, layout in rff.cu: peer_buffer_*) and then
+  // releases flag[peer_rank] = peer_epoch there; each rank's merge kernel waits for its own flags.  peer_world = 0: off.
+  unsigned long long* peer_buf[8];
+  int peer_world, peer_rank;
+  unsigned long long peer_epoch;
   float* out_F;              // [S, ldf] (eval mode)
   long long ldf;
   long long idx_offset;
@@ -757,14 +763,25 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         const float v = none ? __int_as_float(0x7fc00000)
                              : f32_from_orderable(static_cast<uint32_t>(pk >> 32)) * p.unscale[s];
         const long long gi = none ? -1 : static_cast<long long>(0xFFFFFFFFu - static_cast<uint32_t>(pk)) + p.idx_offset;
-        if (p.out_key != nullptr) {
-          p.out_key[s] = none ? kEmptyKey : argmax_key(v, static_cast<uint32_t>(gi));
+        if (p.out_key != nullptr || p.peer_world > 0) {
+          const long long key = none ? kEmptyKey : argmax_key(v, static_cast<uint32_t>(gi));
+          if (p.out_key != nullptr) p.out_key[s] = key;
+          const size_t slot = (static_cast<size_t>(p.peer_epoch & 1ull) * p.peer_world + p.peer_rank) * p.S + s;
+          for (int r = 0; r < p.peer_world; ++r) p.peer_buf[r][slot] = static_cast<unsigned long long>(key);
         } else {
           p.out_val[s] = v;
           p.out_idx[s] = gi;
         }
       }
       if (threadIdx.x == 0) *p.done_counter = 0u;
+      if (p.peer_world > 0) {
+        __threadfence_system();                     // every thread's key stores before the flags
+        __syncthreads();
+        if (threadIdx.x < p.peer_world) {
+          unsigned long long* flag = p.peer_buf[threadIdx.x] + 2ull * p.peer_world * p.S + p.peer_rank;
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(p.peer_epoch) : "memory");
+        }
+      }
     }
   }
 }

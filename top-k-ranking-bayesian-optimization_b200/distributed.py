@@ -100,6 +100,55 @@ def sharded_argmax_fast(basis, X_local, idx_offset, group=None):
     return allreduce_argmax(basis, key, group=group)
 
 
+class PeerMerge:
+    """Merge of the per-rank (value, index) keys fused into the kernel over NVLink peer memory: no collective call per
+    iteration.  Every rank owns a small buffer that all ranks of the node can store to (torch symmetric memory, or a plain
+    tensor for a single rank); the last CTA of K1 on rank r stores its S keys into slot r of every buffer and releases a
+    flag, the merge kernel on each rank acquires the flags of its own buffer, takes the per-sample maximum and unpacks
+    (the all-gather of 8 S bytes per rank + max, done by the producing kernel).  One NVSwitch node, <= 8 ranks.
+    All ranks must call ``argmax`` the same number of times (the epoch counter advances in lock step)."""
+
+    def __init__(self, S, device, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _native as nat
+        self.S, self.device, self.epoch = int(S), torch.device(device), 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 8:
+            raise nat.TkboError("PeerMerge serves one NVSwitch node (<= 8 ranks); use sharded_argmax_fast across nodes")
+        words = int(nat.lib().tkbo_peer_buffer_bytes(self.world, self.S)) // 8
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm
+            self.buf = symm.empty(words, dtype=torch.int64, device=self.device)
+            self.buf.zero_()
+            self._hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            ptrs = [int(q) for q in self._hdl.buffer_ptrs]
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)                      # every buffer is zeroed before anybody stores into it
+        else:
+            self.buf = torch.zeros(words, dtype=torch.int64, device=self.device)
+            ptrs = [self.buf.data_ptr()]
+        self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self._nat = nat
+
+    def argmax(self, basis, X_local, idx_offset):
+        """(val[S], idx[S]) over all ranks' shards; X_local are rows [idx_offset, idx_offset + N_local) (N_local >= 1)."""
+        import ctypes
+        import torch
+        nat = self._nat
+        assert basis.S == self.S
+        self.epoch += 1
+        basis.argmax_peer(X_local, idx_offset, self._ptrs, self.rank, self.epoch)
+        val = torch.empty(self.S, dtype=torch.float32, device=self.device)
+        idx = torch.empty(self.S, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().tkbo_merge_peer_keys(nat.handle(self.device.index), ctypes.c_void_p(self.buf.data_ptr()), self.world,
+                                                 self.S, self.epoch, nat.ptr(val), nat.ptr(idx),
+                                                 nat.current_stream_ptr(self.device)), "tkbo_merge_peer_keys")
+        return val, idx
+
+
 def sharded_argmax(basis, X_local, idx_offset, group=None):
     """K1 on this rank's shard, then the all-gather merge.  ``basis`` is a fourier_features.SharedBasis holding
     the same (W, b, Theta) on every rank; X_local (N_local, d) are rows [idx_offset, idx_offset + N_local)."""

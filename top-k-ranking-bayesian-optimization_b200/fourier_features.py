@@ -354,6 +354,15 @@ class SharedBasis:
                                                 nat.current_stream_ptr(self.device)), "tkbo_rff_argmax_key")
         return key
 
+    def argmax_peer(self, X, idx_offset, peer_ptrs, rank, epoch):
+        """Fused kernel + merge push: this rank's S keys go straight into slot (epoch & 1, rank) of every rank's peer
+        buffer (``peer_ptrs`` = ctypes array of the buffers as mapped here), followed by a release of flag[rank] = epoch;
+        see distributed.PeerMerge, include/tkbo.h tkbo_rff_argmax_peer."""
+        X = self._candidates(X)
+        nat.check(nat.lib().tkbo_rff_argmax_peer(self._h, self._basis, nat.ptr(X), X.shape[0], int(idx_offset), peer_ptrs,
+                                                 len(peer_ptrs), int(rank), int(epoch), nat.current_stream_ptr(self.device)),
+                  "tkbo_rff_argmax_peer")
+
     def unpack_key(self, key):
         """(val[S] float32, idx[S] int64) from merge keys (idx = -1 where no candidate was seen)."""
         torch = self._torch
