@@ -277,7 +277,7 @@ def run_gpu(args):
     value = world * N * S / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI with HOST buffers (tkbo_rff_argmax_host): every step copies the step's pinned
-    # candidates and the float64 basis to the device (candidate chunks pipelined against the kernel), runs the fused
+    # candidates and the float64 basis to the device (one launch consuming the candidate chunks as their copies land), runs the fused
     # argmax and reads the S results back.  N > 1: each rank does that for its shard, then one all_reduce(MAX) of keys.
     W_h, b_h, T_h = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (W, b, Theta))
     res_val = torch.empty(S, dtype=torch.float32).pin_memory()
@@ -331,8 +331,8 @@ def run_gpu(args):
                            "tiling": cfg, "parallelism": f"candidate shards x{world}, merge: {merge}"},
                 "e2e": {"value": world * N * S / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "what": "tkbo_rff_argmax_host (C ABI, host buffers): pinned candidates + fp64 basis -> device (candidate chunks "
-                                "pipelined against the kernel), operand prep, fused argmax, S results -> host"},
+                        "what": "tkbo_rff_argmax_host (C ABI, host buffers): pinned candidates + fp64 basis -> device, operand prep, ONE "
+                                "fused-argmax launch that consumes the candidate chunks while their copies land, S results -> host"},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": alg_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",

@@ -266,17 +266,21 @@ def test_rff_argmax_host_entry_point(pbo):
 
 
 def test_rff_argmax_host_chunked_pipeline(pbo):
-    """Large N goes through the chunked copy/compute pipeline of the host entry point: same result as the
-    device-resident call, repeated calls reuse the cached staging, a shape change rebuilds it."""
+    """Large N goes through the streamed pipeline of the host entry point (one launch that consumes candidate chunks as
+    their H2D copies land): same result as the device-resident call, with pinned and with pageable candidates (whose
+    copies are queued, host-synchronously, after the kernel is already waiting for them); repeated calls reuse the
+    cached staging, a shape change rebuilds it."""
     rng = np.random.default_rng(9)
     X, W, b, Theta = _basis_inputs(rng, 400000, 128, 2, 40, -1.5, 1.5, 0.6)
     Xp = torch.from_numpy(X).pin_memory()
     basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
     val, idx = basis.argmax(X)
-    for _ in range(2):
-        v, i = pbo.fourier_features.argmax_host(W, b, Theta, Xp)
+    for src in (Xp, Xp, X, Xp):
+        v, i = pbo.fourier_features.argmax_host(W, b, Theta, src)
         np.testing.assert_array_equal(i, idx.cpu().numpy())
         np.testing.assert_array_equal(v, val.cpu().numpy())
+    # the winners sit in late chunks too: a kernel that read a chunk before it landed would miss them
+    assert (idx.cpu().numpy() > 200000).any()
     X2, W2, b2, Theta2 = _basis_inputs(rng, 3000, 64, 3, 20, 0.0, 1.0, 0.4)
     v, i = pbo.fourier_features.argmax_host(W2, b2, Theta2, X2)
     val2, idx2 = pbo.fourier_features.SharedBasis(W2, b2, Theta2, device="cuda:0").argmax(X2)

@@ -17,6 +17,8 @@ int basis_destroy(tkbo_handle_t h, tkbo_basis_t bs);
 int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b, const double* Theta, int transposed,
               cudaStream_t stream);
 int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg);
+int rff_argmax_streamed(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t rows_per_chunk,
+                        unsigned int* ready_flag, float* out_val, int64_t* out_idx, cudaStream_t stream);
 size_t peer_buffer_words(int world, int S);
 int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs,
                     int world, int rank, uint64_t epoch, cudaStream_t stream);
@@ -78,19 +80,20 @@ struct DeviceGuard {
   if (!_guard.ok) { set_error("cannot select the handle's device"); return TKBO_ERR_CUDA; }
 
 // Host-buffer entry point.  State (basis layout, device staging, two streams) lives on the handle and is reused while
-// (D, d, S) and the sizes fit, so a steady-state call is: basis H2D + prep kernels, then the candidates in up to
-// kHostChunksMax chunks, the H2D copy of chunk k+1 overlapping the fused kernel on chunk k (pass PINNED host memory
-// for that overlap), one merge of the per-chunk keys, and the D2H of the S results.
-constexpr int kHostChunksMax = 8;
+// (D, d, S) and the sizes fit.  A steady-state call is ONE launch of the fused kernel over all N candidates that starts
+// as soon as the basis is prepared, while the copy stream is still bringing the candidates in (pass PINNED host memory
+// for that overlap) in up to kHostChunksMax chunks, each followed by a 4-byte copy that bumps a "chunks landed" counter;
+// the kernel's row-staging warps acquire that counter before they read a tile of a chunk (rff_fused.cuh, ready_flag).
+// The kernel waits on DMA copies only, never on another kernel; a chunk that does not arrive within ~10 s is reported
+// (TKBO_ERR_CUDA) instead of hanging.
+constexpr int kHostChunksMax = 16;
 
 static void host_path_release(tkbo_handle_t h) {
   auto& hp = h->host;
   if (hp.basis) basis_destroy(h, hp.basis);
-  cudaFree(hp.dbasis); cudaFree(hp.dX[0]); cudaFree(hp.dX[1]); cudaFree(hp.keys); cudaFree(hp.dval); cudaFree(hp.didx);
-  for (int i = 0; i < 2; ++i) {
-    if (hp.copied[i]) cudaEventDestroy(hp.copied[i]);
-    if (hp.consumed[i]) cudaEventDestroy(hp.consumed[i]);
-  }
+  cudaFree(hp.dbasis); cudaFree(hp.dX); cudaFree(hp.dflag); cudaFree(hp.dval); cudaFree(hp.didx);
+  if (hp.hflag) cudaFreeHost(hp.hflag);
+  if (hp.flag_reset) cudaEventDestroy(hp.flag_reset);
   if (hp.copy_stream) cudaStreamDestroy(hp.copy_stream);
   if (hp.exec_stream) cudaStreamDestroy(hp.exec_stream);
   hp = tkbo_handle_s::HostPath();
@@ -257,10 +260,10 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
   if (!hp.exec_stream) {
     TKBO_CUDA_CHECK(cudaStreamCreateWithFlags(&hp.exec_stream, cudaStreamNonBlocking));
     TKBO_CUDA_CHECK(cudaStreamCreateWithFlags(&hp.copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      TKBO_CUDA_CHECK(cudaEventCreateWithFlags(&hp.copied[i], cudaEventDisableTiming));
-      TKBO_CUDA_CHECK(cudaEventCreateWithFlags(&hp.consumed[i], cudaEventDisableTiming));
-    }
+    TKBO_CUDA_CHECK(cudaEventCreateWithFlags(&hp.flag_reset, cudaEventDisableTiming));
+    TKBO_CUDA_CHECK(cudaMalloc(&hp.dflag, 2 * sizeof(unsigned int)));
+    TKBO_CUDA_CHECK(cudaHostAlloc(&hp.hflag, (kHostChunksMax + 1) * sizeof(unsigned int), cudaHostAllocDefault));
+    for (int k = 0; k < kHostChunksMax; ++k) hp.hflag[k] = static_cast<unsigned int>(k + 1);
   }
   if (!hp.basis || hp.D != D || hp.d != d || hp.S != S) {
     if (hp.basis) { basis_destroy(h, hp.basis); hp.basis = nullptr; }
@@ -275,55 +278,61 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
     hp.dbasis_doubles = nb;
   }
   if (hp.out_S < S) {
-    cudaFree(hp.keys); cudaFree(hp.dval); cudaFree(hp.didx);
-    hp.keys = nullptr; hp.dval = nullptr; hp.didx = nullptr; hp.out_S = 0;
-    TKBO_CUDA_CHECK(cudaMalloc(&hp.keys, sizeof(long long) * kHostChunksMax * S));
+    cudaFree(hp.dval); cudaFree(hp.didx);
+    hp.dval = nullptr; hp.didx = nullptr; hp.out_S = 0;
     TKBO_CUDA_CHECK(cudaMalloc(&hp.dval, sizeof(float) * S));
     TKBO_CUDA_CHECK(cudaMalloc(&hp.didx, sizeof(long long) * S));
     hp.out_S = S;
   }
-  // chunks of whole 128-candidate tiles, at least 2^17 candidates each (below that the kernel's tail dominates)
-  int chunks = static_cast<int>(std::min<int64_t>(kHostChunksMax, std::max<int64_t>(1, N >> 17)));
-  if (chunks > 1) chunks = std::min(chunks, 4);
+  // chunks of whole 128-candidate tiles, about 2^16 candidates each (a few hundred KB: ~10 us of PCIe time before the
+  // kernel can start on the first one)
+  int chunks = static_cast<int>(std::min<int64_t>(kHostChunksMax, std::max<int64_t>(1, N >> 16)));
   const int64_t per = (((N + chunks - 1) / chunks) + 127) / 128 * 128;
   chunks = static_cast<int>((N + per - 1) / per);
-  if (hp.dX_floats < static_cast<size_t>(per) * d) {
-    cudaFree(hp.dX[0]); cudaFree(hp.dX[1]); hp.dX[0] = hp.dX[1] = nullptr; hp.dX_floats = 0;
-    TKBO_CUDA_CHECK(cudaMalloc(&hp.dX[0], sizeof(float) * per * d));
-    TKBO_CUDA_CHECK(cudaMalloc(&hp.dX[1], sizeof(float) * per * d));
-    hp.dX_floats = static_cast<size_t>(per) * d;
+  if (hp.dX_floats < static_cast<size_t>(N) * d) {
+    cudaFree(hp.dX); hp.dX = nullptr; hp.dX_floats = 0;
+    TKBO_CUDA_CHECK(cudaMalloc(&hp.dX, sizeof(float) * N * d));
+    hp.dX_floats = static_cast<size_t>(N) * d;
   }
   cudaStream_t sx = hp.exec_stream, sc = hp.copy_stream;
   double* dW = hp.dbasis;
   double* db = dW + static_cast<size_t>(D) * d;
   double* dT = db + D;
-  // first candidate chunk goes out before the basis so that the copy engine is busy while the basis is prepared
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(hp.dX[0], X, sizeof(float) * std::min<int64_t>(per, N) * d, cudaMemcpyHostToDevice, sc));
-  TKBO_CUDA_CHECK(cudaEventRecord(hp.copied[0], sc));
+  auto copy_chunk = [&](int k) -> cudaError_t {
+    const int64_t n0 = static_cast<int64_t>(k) * per, nk = std::min<int64_t>(per, N - n0);
+    cudaError_t e = cudaMemcpyAsync(hp.dX + n0 * d, X + n0 * d, sizeof(float) * nk * d, cudaMemcpyHostToDevice, sc);
+    // stream order: the counter moves only after the chunk's bytes are in device memory
+    return e ? e : cudaMemcpyAsync(hp.dflag, hp.hflag + k, sizeof(unsigned int), cudaMemcpyHostToDevice, sc);
+  };
+  TKBO_CUDA_CHECK(cudaMemsetAsync(hp.dflag, 0, 2 * sizeof(unsigned int), sx));
+  TKBO_CUDA_CHECK(cudaEventRecord(hp.flag_reset, sx));
+  TKBO_CUDA_CHECK(cudaStreamWaitEvent(sc, hp.flag_reset, 0));
+  // the first chunk goes out before the basis so that the copy engine is busy while the basis is prepared; the rest is
+  // queued after the kernel launch, so that pageable (host-synchronous) candidate copies do not delay the launch
+  TKBO_CUDA_CHECK(copy_chunk(0));
   TKBO_CUDA_CHECK(cudaMemcpyAsync(dW, W, sizeof(double) * D * d, cudaMemcpyHostToDevice, sx));
   TKBO_CUDA_CHECK(cudaMemcpyAsync(db, b, sizeof(double) * D, cudaMemcpyHostToDevice, sx));
   TKBO_CUDA_CHECK(cudaMemcpyAsync(dT, Theta, sizeof(double) * D * S, cudaMemcpyHostToDevice, sx));
   int rc = basis_set(h, hp.basis, dW, db, dT, 0, sx);
-  for (int k = 0; k < chunks && rc == TKBO_OK; ++k) {
-    const int buf = k & 1;
-    const int64_t n0 = static_cast<int64_t>(k) * per, nk = std::min<int64_t>(per, N - n0);
-    if (k + 1 < chunks) {                 // copy of the next chunk, once its buffer has been consumed
-      const int nb2 = (k + 1) & 1;
-      const int64_t m0 = n0 + per, mk = std::min<int64_t>(per, N - m0);
-      if (k >= 1) TKBO_CUDA_CHECK(cudaStreamWaitEvent(sc, hp.consumed[nb2], 0));
-      TKBO_CUDA_CHECK(cudaMemcpyAsync(hp.dX[nb2], X + m0 * d, sizeof(float) * mk * d, cudaMemcpyHostToDevice, sc));
-      TKBO_CUDA_CHECK(cudaEventRecord(hp.copied[nb2], sc));
-    }
-    TKBO_CUDA_CHECK(cudaStreamWaitEvent(sx, hp.copied[buf], 0));
-    rc = rff_argmax_key(h, hp.basis, hp.dX[buf], nk, n0, reinterpret_cast<int64_t*>(hp.keys) + static_cast<size_t>(k) * S, sx);
-    TKBO_CUDA_CHECK(cudaEventRecord(hp.consumed[buf], sx));
+  if (rc == TKBO_OK)
+    rc = rff_argmax_streamed(h, hp.basis, hp.dX, N, per, hp.dflag, hp.dval, reinterpret_cast<int64_t*>(hp.didx), sx);
+  cudaError_t ce = cudaSuccess;
+  for (int k = 1; k < chunks && ce == cudaSuccess; ++k) ce = copy_chunk(k);
+  if (rc != TKBO_OK || ce != cudaSuccess) {
+    // a launched kernel may be waiting for chunks that were never queued: let its bounded wait expire rather than leave it
+    cudaStreamSynchronize(sc); cudaStreamSynchronize(sx);
+    if (rc == TKBO_OK) { set_error(std::string("candidate copy: ") + cudaGetErrorString(ce)); rc = TKBO_ERR_CUDA; }
+    return rc;
   }
-  if (rc == TKBO_OK) rc = merge_unpack_keys(h, reinterpret_cast<int64_t*>(hp.keys), chunks, S, hp.dval,
-                                            reinterpret_cast<int64_t*>(hp.didx), sx);
-  if (rc != TKBO_OK) { cudaStreamSynchronize(sx); cudaStreamSynchronize(sc); return rc; }
   TKBO_CUDA_CHECK(cudaMemcpyAsync(out_val, hp.dval, sizeof(float) * S, cudaMemcpyDeviceToHost, sx));
   TKBO_CUDA_CHECK(cudaMemcpyAsync(out_idx, hp.didx, sizeof(int64_t) * S, cudaMemcpyDeviceToHost, sx));
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(hp.hflag + kHostChunksMax, hp.dflag + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, sx));
   TKBO_CUDA_CHECK(cudaStreamSynchronize(sx));
+  TKBO_CUDA_CHECK(cudaStreamSynchronize(sc));
+  if (hp.hflag[kHostChunksMax] != 0u) {
+    set_error("tkbo_rff_argmax_host: a candidate chunk did not reach the device within the kernel's wait limit");
+    return TKBO_ERR_CUDA;
+  }
   return TKBO_OK;
 }
 

@@ -49,14 +49,15 @@ struct tkbo_handle_s {
     int D = 0, d = 0, S = 0;
     double* dbasis = nullptr;            // W | b | Theta as float64
     size_t dbasis_doubles = 0;
-    float* dX[2] = {nullptr, nullptr};   // two candidate chunks (copy of chunk k+1 overlaps the kernel on chunk k)
-    size_t dX_floats = 0;                // capacity of each
-    long long* keys = nullptr;           // [kHostChunksMax, S] merge keys
+    float* dX = nullptr;                 // all N candidates; filled chunk by chunk while the kernel already runs
+    size_t dX_floats = 0;
+    unsigned int* dflag = nullptr;       // [0] chunks landed so far, [1] the kernel's "chunk never arrived" report
+    unsigned int* hflag = nullptr;       // pinned: 1, 2, ..., kHostChunksMax (sources of the flag copies) and the report read-back
     float* dval = nullptr;
     long long* didx = nullptr;
     int out_S = 0;
     cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
-    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    cudaEvent_t flag_reset = nullptr;
   } host;
   // optional K1 pipeline trace target (tkbo_debug_set_trace); caller-owned device memory
   unsigned long long* trace = nullptr;

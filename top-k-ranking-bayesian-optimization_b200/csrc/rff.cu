@@ -548,7 +548,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->done_counter = reinterpret_cast<unsigned int*>(bs->packed + bs->Salloc);
   p->out_val = nullptr; p->out_idx = nullptr; p->out_key = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
   p->duel_n = 0; p->duel_j0 = 0; p->duel_nj = 0; p->score_fix = nullptr;
-  p->peer_world = 0; p->peer_rank = 0; p->peer_epoch = 0;
+  p->peer_world = 0; p->peer_rank = 0; p->peer_epoch = 0; p->ready_flag = nullptr; p->rows_per_chunk = 0;
   for (int r = 0; r < 8; ++r) p->peer_buf[r] = nullptr;
   p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
   p->n_slabs = bs->Dpad / kSlabK;
@@ -574,6 +574,23 @@ int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int6
   p.out_val = out_val;
   p.out_idx = reinterpret_cast<long long*>(out_idx);
   p.idx_offset = idx_offset;
+  return dispatch_fused<0>(h, bs, p, grid, stream);
+}
+
+// X is being filled by H2D copies on another stream, `rows_per_chunk` (multiple of 128) rows at a time; ready_flag[0]
+// counts the chunks that have landed (see RffParams::ready_flag).
+int rff_argmax_streamed(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t rows_per_chunk,
+                        unsigned int* ready_flag, float* out_val, int64_t* out_idx, cudaStream_t stream) {
+  RffParams p;
+  int grid = 0;
+  int rc = fill_params(h, bs, X, N, &p, &grid);
+  if (rc != TKBO_OK) return rc;
+  TKBO_REQUIRE(out_val && out_idx && ready_flag, "null pointer");
+  TKBO_REQUIRE(rows_per_chunk >= kTileM && rows_per_chunk % kTileM == 0, "rows_per_chunk must be a multiple of 128");
+  p.out_val = out_val;
+  p.out_idx = reinterpret_cast<long long*>(out_idx);
+  p.ready_flag = ready_flag;
+  p.rows_per_chunk = rows_per_chunk;
   return dispatch_fused<0>(h, bs, p, grid, stream);
 }
 
@@ -769,7 +786,7 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   p.n_slabs = bs->Dpad / kSlabK; p.n_mtiles = static_cast<int>(mt);
   p.stages = bs->stages; p.ring = bs->ring; p.acc_bufs = bs->acc_bufs; p.xa_bufs = bs->xa_bufs;
   p.proj_warps = bs->proj_warps; p.wstages = bs->wstages; p.coop = bs->coop;
-  p.peer_world = 0; p.peer_rank = 0; p.peer_epoch = 0;
+  p.peer_world = 0; p.peer_rank = 0; p.peer_epoch = 0; p.ready_flag = nullptr; p.rows_per_chunk = 0;
   for (int r = 0; r < 8; ++r) p.peer_buf[r] = nullptr;
   p.duel_n = n; p.duel_j0 = j_begin; p.duel_nj = j_end - j_begin;
   p.score_fix = reinterpret_cast<unsigned long long*>(fix);

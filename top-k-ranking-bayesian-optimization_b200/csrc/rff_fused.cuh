@@ -78,6 +78,11 @@ struct RffParams {
   unsigned long long* peer_buf[8];
   int peer_world, peer_rank;
   unsigned long long peer_epoch;
+  // streamed candidates (tkbo_rff_argmax_host): X arrives in chunks of `rows_per_chunk` rows by H2D copies on another
+  // stream while this launch runs; ready_flag[0] = number of chunks landed so far (written by a copy queued behind each
+  // chunk), ready_flag[1] = set by the kernel if a chunk never arrived.  Null: all of X is resident.
+  unsigned int* ready_flag;
+  long long rows_per_chunk;
   float* out_F;              // [S, ldf] (eval mode)
   long long ldf;
   long long idx_offset;
@@ -121,17 +126,35 @@ __device__ __forceinline__ void trace_event(const RffParams& p, int ev, int idx)
 #endif
 }
 
-// 16 projection values (fp32 bits) -> 8 packed fp16x2 hi words followed by 8 lo words.
+// u - h for a packed pair of halves h (mixed-precision fma: h * -1 + u, one instruction per value, exact)
+__device__ __forceinline__ void sub_half2(float u0, float u1, uint32_t h2, float& l0, float& l1) {
+  asm("{\n\t.reg .b16 a, b, m;\n\t"
+      "mov.b32 {a, b}, %2;\n\t"
+      "mov.b16 m, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %0, a, m, %3;\n\t"
+      "fma.rn.f32.f16 %1, b, m, %4;\n\t}"
+      : "=f"(l0), "=f"(l1) : "r"(h2), "f"(u0), "f"(u1));
+}
+// The producers' cos; the timing ablation that skips it (TKBO_DEBUG & 2) exists in the trace build only.
+__device__ __forceinline__ float feature_cos(uint32_t arg_bits, bool skip) {
+#ifdef TKBO_TRACE
+  if (skip) return 1.f;
+#endif
+  return __cosf(__uint_as_float(arg_bits));
+}
+
+// 16 projection values (fp32 bits) -> 8 packed fp16x2 hi words followed by 8 lo words: five instructions per feature
+// (FMUL.RZ + MUFU.COS, half an F2FP for hi, one FHFMA for the residual, half an F2FP for lo).
 __device__ __forceinline__ void cos_split16(const uint32_t* __restrict__ arg, uint32_t (&out)[16], bool skip) {
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
-    float c0, c1;
-    if (skip) { c0 = 1.f; c1 = 1.f; }
-    else { c0 = __cosf(__uint_as_float(arg[2 * jj])); c1 = __cosf(__uint_as_float(arg[2 * jj + 1])); }
+    const float c0 = feature_cos(arg[2 * jj], skip), c1 = feature_cos(arg[2 * jj + 1], skip);
     const __half2 h = __floats2half2_rn(c0, c1);
-    const float2 back = __half22float2(h);
-    const __half2 l = __floats2half2_rn(c0 - back.x, c1 - back.y);
-    out[jj] = *reinterpret_cast<const uint32_t*>(&h);
+    const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
+    float l0, l1;
+    sub_half2(c0, c1, hw, l0, l1);
+    const __half2 l = __floats2half2_rn(l0, l1);
+    out[jj] = hw;
     out[8 + jj] = *reinterpret_cast<const uint32_t*>(&l);
   }
 }
@@ -146,22 +169,13 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a0, float a1, float a2, fl
   asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(a3), "f"(a2));
   return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
 }
-// u - h for a packed pair of halves h (mixed-precision fma: h * -1 + u, one instruction per value, exact)
-__device__ __forceinline__ void sub_half2(float u0, float u1, uint32_t h2, float& l0, float& l1) {
-  asm("{\n\t.reg .b16 a, b, m;\n\t"
-      "mov.b32 {a, b}, %2;\n\t"
-      "mov.b16 m, 0xBC00;\n\t"
-      "fma.rn.f32.f16 %0, a, m, %3;\n\t"
-      "fma.rn.f32.f16 %1, b, m, %4;\n\t}"
-      : "=f"(l0), "=f"(l1) : "r"(h2), "f"(u0), "f"(u1));
-}
 __device__ __forceinline__ void cos_split16_c8(const uint32_t* __restrict__ arg, uint32_t (&out)[16], bool skip) {
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
     float c[4], u[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      c[e] = skip ? 1.f : __cosf(__uint_as_float(arg[4 * jj + e]));
+      c[e] = feature_cos(arg[4 * jj + e], skip);
       u[e] = c[e] * 4096.f;
     }
     const __half2 h01 = __floats2half2_rn(u[0], u[1]);
@@ -574,13 +588,29 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         row_b = row_a;
         dsplit = p.d;
       }
+      if (p.ready_flag != nullptr) {
+        // tiles never straddle chunks (rows_per_chunk is a multiple of 128); the copy engine owes us chunk `need - 1`
+        const unsigned need = static_cast<unsigned>(row_a / p.rows_per_chunk) + 1u;
+        if (lane == 0) {
+          const long long t0 = clock64();
+          for (;;) {
+            unsigned got;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(p.ready_flag) : "memory");
+            if (got >= need) break;
+            if (clock64() - t0 > 20000000000ll) { atomicExch(p.ready_flag + 1, 1u); break; }   // ~10 s: report, do not hang
+            __nanosleep(100);
+          }
+        }
+        __syncwarp();
+      }
       const int dx = (p.duel_n > 0) ? dsplit : p.d;  // row stride of X
       uint32_t w[kPCols];
 #pragma unroll
       for (int c = 0; c < kPCols; ++c) w[c] = 0u;
 #pragma unroll
       for (int i = 0; i < DT; ++i) {
-        const float x = (i < p.d) ? ((i < dsplit) ? __ldg(p.X + row_a * dx + i) : __ldg(p.X + row_b * dx + (i - dsplit))) : 0.f;
+        // L2 loads: every element is read once, and streamed rows must not be looked up in a non-coherent cache
+        const float x = (i < p.d) ? ((i < dsplit) ? __ldcg(p.X + row_a * dx + i) : __ldcg(p.X + row_b * dx + (i - dsplit))) : 0.f;
         uint32_t b1, b2, b3;
         bf16_split3(x, b1, b2, b3);
         w[3 * i + 0] = b1 | (b1 << 16);              // k = 6i, 6i+1

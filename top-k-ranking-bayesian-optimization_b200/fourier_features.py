@@ -216,8 +216,9 @@ def sample_maximizers(X, count, n_init, D, model, min_val, max_val, num_steps=30
 # ---------------------------------------------------------------------------------------------------
 def argmax_host(W, b, Theta, X, device=0, out_val=None, out_idx=None):
     """End-to-end host-buffer call (C ABI ``tkbo_rff_argmax_host``): W (D, d), b (D,), Theta (D, S) float64 and the
-    candidates X (N, d) float32 are HOST arrays (NumPy, or CPU torch tensors - pinned memory lets the H2D copy of
-    candidate chunk k+1 overlap the kernel on chunk k); returns (val[S] float32, idx[S] int64) NumPy arrays.
+    candidates X (N, d) float32 are HOST arrays (NumPy, or CPU torch tensors - with pinned memory the single kernel
+    launch consumes the candidate chunks while their H2D copies are still landing); returns (val[S] float32,
+    idx[S] int64) NumPy arrays.
     Device staging and the basis layout are cached on the handle between calls of the same shape."""
     def host(a, dtype):
         if hasattr(a, "data_ptr"):
