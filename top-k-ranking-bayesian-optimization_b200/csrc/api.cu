@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <new>
+#include <string.h>
 #include <string>
 
 #include "common.h"
@@ -91,8 +92,9 @@ constexpr int kHostChunksMax = 16;
 static void host_path_release(tkbo_handle_t h) {
   auto& hp = h->host;
   if (hp.basis) basis_destroy(h, hp.basis);
-  cudaFree(hp.dbasis); cudaFree(hp.dX); cudaFree(hp.dflag); cudaFree(hp.dval); cudaFree(hp.didx);
+  cudaFree(hp.dbasis); cudaFree(hp.dX); cudaFree(hp.dout);
   if (hp.hflag) cudaFreeHost(hp.hflag);
+  if (hp.hout) cudaFreeHost(hp.hout);
   if (hp.flag_reset) cudaEventDestroy(hp.flag_reset);
   if (hp.copy_stream) cudaStreamDestroy(hp.copy_stream);
   if (hp.exec_stream) cudaStreamDestroy(hp.exec_stream);
@@ -261,8 +263,7 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
     TKBO_CUDA_CHECK(cudaStreamCreateWithFlags(&hp.exec_stream, cudaStreamNonBlocking));
     TKBO_CUDA_CHECK(cudaStreamCreateWithFlags(&hp.copy_stream, cudaStreamNonBlocking));
     TKBO_CUDA_CHECK(cudaEventCreateWithFlags(&hp.flag_reset, cudaEventDisableTiming));
-    TKBO_CUDA_CHECK(cudaMalloc(&hp.dflag, 2 * sizeof(unsigned int)));
-    TKBO_CUDA_CHECK(cudaHostAlloc(&hp.hflag, (kHostChunksMax + 1) * sizeof(unsigned int), cudaHostAllocDefault));
+    TKBO_CUDA_CHECK(cudaHostAlloc(&hp.hflag, kHostChunksMax * sizeof(unsigned int), cudaHostAllocDefault));
     for (int k = 0; k < kHostChunksMax; ++k) hp.hflag[k] = static_cast<unsigned int>(k + 1);
   }
   if (!hp.basis || hp.D != D || hp.d != d || hp.S != S) {
@@ -277,13 +278,18 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
     TKBO_CUDA_CHECK(cudaMalloc(&hp.dbasis, nb * sizeof(double)));
     hp.dbasis_doubles = nb;
   }
+  const size_t out_bytes = static_cast<size_t>(S) * 12 + 8;
   if (hp.out_S < S) {
-    cudaFree(hp.dval); cudaFree(hp.didx);
-    hp.dval = nullptr; hp.didx = nullptr; hp.out_S = 0;
-    TKBO_CUDA_CHECK(cudaMalloc(&hp.dval, sizeof(float) * S));
-    TKBO_CUDA_CHECK(cudaMalloc(&hp.didx, sizeof(long long) * S));
+    cudaFree(hp.dout); hp.dout = nullptr;
+    if (hp.hout) { cudaFreeHost(hp.hout); hp.hout = nullptr; }
+    hp.out_S = 0;
+    TKBO_CUDA_CHECK(cudaMalloc(&hp.dout, out_bytes));
+    TKBO_CUDA_CHECK(cudaHostAlloc(&hp.hout, out_bytes, cudaHostAllocDefault));
     hp.out_S = S;
   }
+  long long* didx = reinterpret_cast<long long*>(hp.dout);
+  float* dval = reinterpret_cast<float*>(hp.dout + static_cast<size_t>(S) * 8);
+  unsigned int* dflag = reinterpret_cast<unsigned int*>(hp.dout + static_cast<size_t>(S) * 12);
   // chunks of whole 128-candidate tiles, about 2^16 candidates each (a few hundred KB: ~10 us of PCIe time before the
   // kernel can start on the first one)
   int chunks = static_cast<int>(std::min<int64_t>(kHostChunksMax, std::max<int64_t>(1, N >> 16)));
@@ -302,9 +308,9 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
     const int64_t n0 = static_cast<int64_t>(k) * per, nk = std::min<int64_t>(per, N - n0);
     cudaError_t e = cudaMemcpyAsync(hp.dX + n0 * d, X + n0 * d, sizeof(float) * nk * d, cudaMemcpyHostToDevice, sc);
     // stream order: the counter moves only after the chunk's bytes are in device memory
-    return e ? e : cudaMemcpyAsync(hp.dflag, hp.hflag + k, sizeof(unsigned int), cudaMemcpyHostToDevice, sc);
+    return e ? e : cudaMemcpyAsync(dflag, hp.hflag + k, sizeof(unsigned int), cudaMemcpyHostToDevice, sc);
   };
-  TKBO_CUDA_CHECK(cudaMemsetAsync(hp.dflag, 0, 2 * sizeof(unsigned int), sx));
+  TKBO_CUDA_CHECK(cudaMemsetAsync(dflag, 0, 2 * sizeof(unsigned int), sx));
   TKBO_CUDA_CHECK(cudaEventRecord(hp.flag_reset, sx));
   TKBO_CUDA_CHECK(cudaStreamWaitEvent(sc, hp.flag_reset, 0));
   // the first chunk goes out before the basis so that the copy engine is busy while the basis is prepared; the rest is
@@ -315,7 +321,7 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
   TKBO_CUDA_CHECK(cudaMemcpyAsync(dT, Theta, sizeof(double) * D * S, cudaMemcpyHostToDevice, sx));
   int rc = basis_set(h, hp.basis, dW, db, dT, 0, sx);
   if (rc == TKBO_OK)
-    rc = rff_argmax_streamed(h, hp.basis, hp.dX, N, per, hp.dflag, hp.dval, reinterpret_cast<int64_t*>(hp.didx), sx);
+    rc = rff_argmax_streamed(h, hp.basis, hp.dX, N, per, dflag, dval, reinterpret_cast<int64_t*>(didx), sx);
   cudaError_t ce = cudaSuccess;
   for (int k = 1; k < chunks && ce == cudaSuccess; ++k) ce = copy_chunk(k);
   if (rc != TKBO_OK || ce != cudaSuccess) {
@@ -324,12 +330,14 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
     if (rc == TKBO_OK) { set_error(std::string("candidate copy: ") + cudaGetErrorString(ce)); rc = TKBO_ERR_CUDA; }
     return rc;
   }
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(out_val, hp.dval, sizeof(float) * S, cudaMemcpyDeviceToHost, sx));
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(out_idx, hp.didx, sizeof(int64_t) * S, cudaMemcpyDeviceToHost, sx));
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(hp.hflag + kHostChunksMax, hp.dflag + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, sx));
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(hp.hout, hp.dout, out_bytes, cudaMemcpyDeviceToHost, sx));
   TKBO_CUDA_CHECK(cudaStreamSynchronize(sx));
   TKBO_CUDA_CHECK(cudaStreamSynchronize(sc));
-  if (hp.hflag[kHostChunksMax] != 0u) {
+  memcpy(out_idx, hp.hout, static_cast<size_t>(S) * 8);
+  memcpy(out_val, hp.hout + static_cast<size_t>(S) * 8, static_cast<size_t>(S) * 4);
+  unsigned int report;
+  memcpy(&report, hp.hout + static_cast<size_t>(S) * 12 + 4, sizeof(report));
+  if (report != 0u) {
     set_error("tkbo_rff_argmax_host: a candidate chunk did not reach the device within the kernel's wait limit");
     return TKBO_ERR_CUDA;
   }

@@ -51,10 +51,11 @@ struct tkbo_handle_s {
     size_t dbasis_doubles = 0;
     float* dX = nullptr;                 // all N candidates; filled chunk by chunk while the kernel already runs
     size_t dX_floats = 0;
-    unsigned int* dflag = nullptr;       // [0] chunks landed so far, [1] the kernel's "chunk never arrived" report
-    unsigned int* hflag = nullptr;       // pinned: 1, 2, ..., kHostChunksMax (sources of the flag copies) and the report read-back
-    float* dval = nullptr;
-    long long* didx = nullptr;
+    // one device block  idx[S] i64 | val[S] f32 | flag[2] u32  read back with a single D2H copy into `hout` (pinned);
+    // flag[0] = chunks landed so far, flag[1] = the kernel's "chunk never arrived" report
+    unsigned char* dout = nullptr;
+    unsigned char* hout = nullptr;
+    unsigned int* hflag = nullptr;       // pinned: 1, 2, ..., kHostChunksMax (sources of the flag copies)
     int out_S = 0;
     cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
     cudaEvent_t flag_reset = nullptr;

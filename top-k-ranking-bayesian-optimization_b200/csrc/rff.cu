@@ -26,73 +26,6 @@ __device__ __forceinline__ double theta_at(const double* T, int transposed, int 
   return transposed ? T[static_cast<size_t>(s) * D + j] : T[static_cast<size_t>(j) * S + s];
 }
 
-// e_s is chosen so that max_j |sqrt(2/D) Theta[j,s]| 2^e_s lies in [2^top, 2^(top+1)); unscale[s] = 2^(-e_s - post) is what
-// the epilogue multiplies the accumulator by (post = the power of two the feature operand carries).
-// top = 9, post = 0 (three-fp16 form) keeps the fp16 hi part far from overflow and the lo part (<= 2^-11 of hi) far above
-// fp16's subnormal step; top = 7, post = 12 (e4m3 correction form, features scaled by 2^12) puts the entries themselves
-// (< 2^8) and the 2^12-scaled lo parts (<= 2^8) into e4m3's normal range [2^-6, 448] down to 2^-14 of the column maximum.
-__global__ void prep_theta_scale_kernel(const double* __restrict__ Theta, int transposed, int D, int S, int Salloc,
-                                        int top, int post, float* __restrict__ unscale) {
-  const int s = blockIdx.x;
-  __shared__ double red[256];
-  double m = 0.0;
-  if (s < S)
-    for (int j = threadIdx.x; j < D; j += blockDim.x) m = fmax(m, fabs(theta_at(Theta, transposed, D, S, j, s)));
-  red[threadIdx.x] = m;
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const double amax = red[0] * sqrt(2.0 / D);
-    int e = 0;
-    if (amax > 0.0 && isfinite(amax)) e = top - ilogb(amax);
-    e = max(-100, min(100, e));
-    unscale[s] = static_cast<float>(ldexp(1.0, -e - post));
-  }
-}
-
-__global__ void prep_theta_split_kernel(const double* __restrict__ Theta, int transposed, int D, int S, int Dpad,
-                                        int Salloc, const float* __restrict__ unscale, __half* __restrict__ hi,
-                                        __half* __restrict__ lo) {
-  const size_t total = static_cast<size_t>(Salloc) * Dpad;
-  const double root = sqrt(2.0 / D);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int s = static_cast<int>(i / Dpad);
-    const int j = static_cast<int>(i % Dpad);
-    double v = 0.0;
-    if (s < S && j < D) v = theta_at(Theta, transposed, D, S, j, s) * root / static_cast<double>(unscale[s]);
-    const __half h = __double2half(v);
-    const __half l = __double2half(v - static_cast<double>(__half2float(h)));
-    hi[i] = h;
-    lo[i] = l;
-  }
-}
-
-// e4m3 correction tile (rff_fused.cuh, C8): row s = per 16 features 16 bytes e4m3(2^12 lo part) then 16 bytes
-// e4m3(value), i.e. 128 bytes per 64-feature slab; hi = the fp16 tile as in the three-MMA form.
-__global__ void prep_theta_split8_kernel(const double* __restrict__ Theta, int transposed, int D, int S, int Dpad,
-                                         int Salloc, const float* __restrict__ unscale, __half* __restrict__ hi,
-                                         uint8_t* __restrict__ c8) {
-  const size_t total = static_cast<size_t>(Salloc) * Dpad;
-  const double root = sqrt(2.0 / D);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int s = static_cast<int>(i / Dpad);
-    const int j = static_cast<int>(i % Dpad);
-    double v = 0.0;
-    if (s < S && j < D) v = theta_at(Theta, transposed, D, S, j, s) * root / (static_cast<double>(unscale[s]) * 4096.0);
-    const __half h = __double2half(v);
-    hi[i] = h;
-    const float lo = static_cast<float>(v - static_cast<double>(__half2float(h)));
-    uint8_t* row = c8 + static_cast<size_t>(s) * 2 * Dpad + (j >> 4) * 32 + (j & 15);
-    row[0] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(lo * 4096.f, __NV_SATFINITE, __NV_E4M3));
-    row[16] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(static_cast<float>(v), __NV_SATFINITE, __NV_E4M3));
-  }
-}
-
 // bf16(v) with round-to-nearest-even, as raw bits and as the double it represents.
 __device__ __forceinline__ uint16_t bf16_rn_bits(double v) {
   const float f = static_cast<float>(v);
@@ -105,29 +38,85 @@ __device__ __forceinline__ double bf16_bits_value(uint16_t h) {
   return static_cast<double>(__uint_as_float(static_cast<uint32_t>(h) << 16));
 }
 
+// All of basis_set in one launch: blocks [0, Salloc) each scale and split one sample's weights (max reduction, then the
+// row's fp16 hi + fp16 lo / e4m3 correction entries), the remaining blocks write 128 rows of Wproj each.
+//
+// e_s is chosen so that max_j |sqrt(2/D) Theta[j,s]| 2^e_s lies in [2^top, 2^(top+1)); unscale[s] = 2^(-e_s - post) is what
+// the epilogue multiplies the accumulator by (post = the power of two the feature operand carries).
+// top = 9, post = 0 (three-fp16 form) keeps the fp16 hi part far from overflow and the lo part (<= 2^-11 of hi) far above
+// fp16's subnormal step; top = 7, post = 12 (e4m3 correction form, features scaled by 2^12) puts the entries themselves
+// (< 2^8) and the 2^12-scaled lo parts (<= 2^8) into e4m3's normal range [2^-6, 448] down to 2^-14 of the column maximum.
+// e4m3 correction tile (rff_fused.cuh, C8): row s = per 16 features 16 bytes e4m3(2^12 lo part) then 16 bytes
+// e4m3(value), i.e. 128 bytes per 64-feature slab; hi = the fp16 tile as in the three-MMA form.
+//
 // Wproj[j, :] = the K-row of feature j for the projection MMA (rff_fused.cuh): per input dimension i the six
 // entries  w1 w2 w1 w3 w2 w1  (w = w1 + w2 + w3 in bf16, paired with x1 x1 x2 x1 x2 x3), then b1 b2 b3 at
 // k = 6 DT .. 6 DT + 2 (paired with ones), zero padding.  Padded features get all zeros: cos(0) = 1 against
 // zero Theta rows.
-__global__ void prep_wproj_kernel(const double* __restrict__ W, const double* __restrict__ b, int D, int d, int Dpad,
-                                  int DT, int KA, uint16_t* __restrict__ Wproj) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= Dpad) return;
-  uint16_t* row = Wproj + static_cast<size_t>(j) * KA;
-  for (int k = 0; k < KA; ++k) row[k] = 0;
-  if (j >= D) return;
-  for (int i = 0; i <= d; ++i) {                    // i == d: the phase b_j
-    const double w = (i < d) ? W[static_cast<size_t>(j) * d + i] : b[j];
-    const uint16_t w1 = bf16_rn_bits(w);
-    const double r1 = w - bf16_bits_value(w1);
-    const uint16_t w2 = bf16_rn_bits(r1);
-    const uint16_t w3 = bf16_rn_bits(r1 - bf16_bits_value(w2));
-    if (i < d) {
-      uint16_t* o = row + 6 * i;
-      o[0] = w1; o[1] = w2; o[2] = w1; o[3] = w3; o[4] = w2; o[5] = w1;
+__global__ void __launch_bounds__(256)
+prep_basis_kernel(const double* __restrict__ Theta, int transposed, const double* __restrict__ W,
+                  const double* __restrict__ b, int D, int d, int S, int Dpad, int Salloc, int DT, int KA, int corr8,
+                  float* __restrict__ unscale, __half* __restrict__ hi, __half* __restrict__ lo,
+                  uint16_t* __restrict__ Wproj) {
+  if (static_cast<int>(blockIdx.x) >= Salloc) {
+    const int j = (static_cast<int>(blockIdx.x) - Salloc) * 128 + static_cast<int>(threadIdx.x);
+    if (threadIdx.x >= 128 || j >= Dpad) return;
+    uint16_t* row = Wproj + static_cast<size_t>(j) * KA;
+    for (int k = 0; k < KA; ++k) row[k] = 0;
+    if (j >= D) return;
+    for (int i = 0; i <= d; ++i) {
+      const double w = (i < d) ? W[static_cast<size_t>(j) * d + i] : b[j];
+      const uint16_t w1 = bf16_rn_bits(w);
+      const double r1 = w - bf16_bits_value(w1);
+      const uint16_t w2 = bf16_rn_bits(r1);
+      const uint16_t w3 = bf16_rn_bits(r1 - bf16_bits_value(w2));
+      if (i < d) {
+        uint16_t* o = row + 6 * i;
+        o[0] = w1; o[1] = w2; o[2] = w1; o[3] = w3; o[4] = w2; o[5] = w1;
+      } else {
+        uint16_t* o = row + 6 * DT;
+        o[0] = w1; o[1] = w2; o[2] = w3;
+      }
+    }
+    return;
+  }
+  const int s = blockIdx.x;
+  __shared__ double red[256];
+  __shared__ double scale_sh;
+  double m = 0.0;
+  if (s < S)
+    for (int j = threadIdx.x; j < D; j += blockDim.x) m = fmax(m, fabs(theta_at(Theta, transposed, D, S, j, s)));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  const double root = sqrt(2.0 / D);
+  if (threadIdx.x == 0) {
+    const double amax = red[0] * root;
+    int e = 0;
+    if (amax > 0.0 && isfinite(amax)) e = (corr8 ? 7 : 9) - ilogb(amax);
+    e = max(-100, min(100, e));
+    const float u = static_cast<float>(ldexp(1.0, -e - (corr8 ? 12 : 0)));
+    unscale[s] = u;
+    scale_sh = 1.0 / (static_cast<double>(u) * (corr8 ? 4096.0 : 1.0));
+  }
+  __syncthreads();
+  const double sc = scale_sh;
+  for (int j = threadIdx.x; j < Dpad; j += blockDim.x) {
+    double v = 0.0;
+    if (s < S && j < D) v = theta_at(Theta, transposed, D, S, j, s) * root * sc;
+    const __half h = __double2half(v);
+    const size_t i = static_cast<size_t>(s) * Dpad + j;
+    hi[i] = h;
+    if (corr8) {
+      const float l = static_cast<float>(v - static_cast<double>(__half2float(h)));
+      uint8_t* row = reinterpret_cast<uint8_t*>(lo) + static_cast<size_t>(s) * 2 * Dpad + (j >> 4) * 32 + (j & 15);
+      row[0] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(l * 4096.f, __NV_SATFINITE, __NV_E4M3));
+      row[16] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(static_cast<float>(v), __NV_SATFINITE, __NV_E4M3));
     } else {
-      uint16_t* o = row + 6 * DT;
-      o[0] = w1; o[1] = w2; o[2] = w3;
+      lo[i] = __double2half(v - static_cast<double>(__half2float(h)));
     }
   }
 }
@@ -483,19 +472,11 @@ int basis_destroy(tkbo_handle_t, tkbo_basis_t bs) {
 int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b, const double* Theta,
               int transposed, cudaStream_t stream) {
   TKBO_REQUIRE(h && bs && W && b && Theta, "null pointer");
-  prep_theta_scale_kernel<<<bs->Salloc, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Salloc,
-                                                          bs->corr8 ? 7 : 9, bs->corr8 ? 12 : 0, bs->unscale);
-  const size_t total = static_cast<size_t>(bs->Salloc) * bs->Dpad;
-  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
-  if (bs->corr8)
-    prep_theta_split8_kernel<<<blocks, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Dpad, bs->Salloc,
-                                                        bs->unscale, bs->theta_hi, reinterpret_cast<uint8_t*>(bs->theta_lo));
-  else
-    prep_theta_split_kernel<<<blocks, 256, 0, stream>>>(Theta, transposed, bs->D, bs->S, bs->Dpad, bs->Salloc,
-                                                       bs->unscale, bs->theta_hi, bs->theta_lo);
-  prep_wproj_kernel<<<(bs->Dpad + 127) / 128, 128, 0, stream>>>(W, b, bs->D, bs->d, bs->Dpad, bs->DT,
-                                                                proj_k_alloc(bs->DT), bs->Wproj);
-  h->launches += 3;
+  const int wblocks = (bs->Dpad + 127) / 128;
+  prep_basis_kernel<<<bs->Salloc + wblocks, 256, 0, stream>>>(Theta, transposed, W, b, bs->D, bs->d, bs->S, bs->Dpad,
+                                                            bs->Salloc, bs->DT, proj_k_alloc(bs->DT), bs->corr8,
+                                                            bs->unscale, bs->theta_hi, bs->theta_lo, bs->Wproj);
+  h->launches += 1;
   TKBO_CUDA_CHECK(cudaGetLastError());
   bs->is_set = true;
   return TKBO_OK;
