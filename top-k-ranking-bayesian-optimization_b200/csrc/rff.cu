@@ -194,7 +194,7 @@ __global__ void argmax_rows_f64_kernel(const double* __restrict__ f, int count, 
 // f and df/dx at the current x, block-reduces the loss, grid-syncs, checks the early-stop rule on the
 // global mean loss and applies  x <- clip(x - lr g / (sqrt(g^2) + eps))  with g = dloss/dx.
 struct AscentState {
-  double* partial;     // [gridDim.x] per-block sum of f
+  double* partial;     // [2][gridDim.x] per-block sum of f, by step parity
   int* steps;          // steps actually run
 };
 
@@ -203,7 +203,7 @@ __global__ void rff_ascent_batched_kernel(double* __restrict__ X, const double* 
                                           int n, int D, int d, double min_val, double max_val, int num_steps,
                                           double lr, double eps, double rel_tol, AscentState st) {
   cg::grid_group grid = cg::this_grid();
-  extern __shared__ double sh[];                       // [warps_per_block] f partials
+  extern __shared__ double sh[];                       // [warps_per_block] f partials + the grid total
   const int warps_per_block = blockDim.x >> 5;
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -216,12 +216,20 @@ __global__ void rff_ascent_batched_kernel(double* __restrict__ X, const double* 
   int steps_done = 0;
   bool stop = false;
 
+  // X holds two copies of the points (ping-pong): `cur` is the accepted iterate, the tentative update of a pass goes to the
+  // other copy and becomes current only if the stop test lets the step through -- one grid-wide barrier per step.  The
+  // per-block loss partials are double-buffered by step parity for the same reason.  A point is always handled by the
+  // same warp, so the copies need no cross-block ordering.
+  const size_t half = static_cast<size_t>(total) * d;
+  int sel = 0;
   for (int step = 0; step <= num_steps && !stop; ++step) {
     // pass `step`: evaluate loss at the current x (step 0 = prev_loss of ff.py:148) and the gradient
+    double* cur = X + (sel ? half : 0);
+    double* nxt = X + (sel ? 0 : half);
     double fsum = 0.0;
     for (int pt = blockIdx.x * warps_per_block + wib; pt < total; pt += warps_total) {
       const int c = pt / n;
-      double* x = X + static_cast<size_t>(pt) * d;
+      const double* x = cur + static_cast<size_t>(pt) * d;
       const double* Wc = W + static_cast<size_t>(c) * D * d;
       double f = 0.0;
       double g[kMaxD];
@@ -246,42 +254,46 @@ __global__ void rff_ascent_batched_kernel(double* __restrict__ X, const double* 
           if (k < d) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
       }
       fsum += f * root;
-      // stash the gradient of the loss in registers of lane k: applied after the stop test below
-      // (every lane holds all g[k]; lane k < d owns coordinate k)
-      __syncwarp();
+      // every lane holds all g[k]; lane k < d owns coordinate k
       if (lane < d) {
         double gk = 0.0;
 #pragma unroll
         for (int k = 0; k < kMaxD; ++k)
           if (k == lane) gk = g[k] * gcoef;
-        // tentative update is written to a shadow so that a stop at this step leaves x untouched
-        // (shadow lives behind X: X has room for 2 * total * d doubles)
         const double xn = x[lane] - lr * gk / (sqrt(gk * gk) + eps);
-        X[static_cast<size_t>(total) * d + static_cast<size_t>(pt) * d + lane] = fmin(fmax(xn, min_val), max_val);
+        nxt[static_cast<size_t>(pt) * d + lane] = fmin(fmax(xn, min_val), max_val);
       }
     }
     if (lane == 0) sh[wib] = fsum;
     __syncthreads();
+    double* partial = st.partial + static_cast<size_t>(step & 1) * gridDim.x;
     if (threadIdx.x == 0) {
       double s = 0.0;
       for (int w = 0; w < warps_per_block; ++w) s += sh[w];
-      st.partial[blockIdx.x] = s;
+      partial[blockIdx.x] = s;
     }
     grid.sync();
-    double tot = 0.0;
-    for (int bl = 0; bl < gridDim.x; ++bl) tot += st.partial[bl];
+    // every block sums the partials in the same order (warp 0, lane-strided + butterfly): identical `tot` everywhere
+    if (wib == 0) {
+      double t = 0.0;
+      for (int bl = lane; bl < static_cast<int>(gridDim.x); bl += 32) t += partial[bl];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) sh[warps_per_block] = t;
+    }
+    __syncthreads();
+    const double tot = sh[warps_per_block];
+    __syncthreads();                                  // sh is rewritten by the next pass
     const double loss = -tot / static_cast<double>(total);
     if (step > 0) {
       steps_done = step;
       if (fabs((loss - prev_loss) / prev_loss) < rel_tol) stop = true;      // ff.py:154
     }
     prev_loss = loss;
-    if (!stop && step < num_steps) {
-      // commit the update computed from this pass's gradient (ff.py:150)
-      for (int pt = blockIdx.x * warps_per_block + wib; pt < total; pt += warps_total)
-        if (lane < d) X[static_cast<size_t>(pt) * d + lane] = X[static_cast<size_t>(total) * d + static_cast<size_t>(pt) * d + lane];
-    }
-    grid.sync();
+    if (!stop && step < num_steps) sel ^= 1;          // commit the update computed from this pass's gradient (ff.py:150)
+  }
+  if (sel) {                                          // the accepted iterate goes back to the first copy
+    for (int pt = blockIdx.x * warps_per_block + wib; pt < total; pt += warps_total)
+      if (lane < d) X[static_cast<size_t>(pt) * d + lane] = X[half + static_cast<size_t>(pt) * d + lane];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *st.steps = steps_done;
 }
@@ -863,20 +875,20 @@ int rff_ascent_batched(tkbo_handle_t h, double* X, const double* W, const double
   const int block = 256, wpb = block / 32;
   int per_sm = 0;
   TKBO_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rff_ascent_batched_kernel, block,
-                                                                wpb * sizeof(double)));
+                                                                (wpb + 1) * sizeof(double)));
   TKBO_REQUIRE(per_sm >= 1, "ascent kernel does not fit on an SM");
   int grid = std::min(h->sm_count * per_sm, (total + wpb - 1) / wpb);
   grid = std::max(grid, 1);
   // X + shadow copy for the tentative update
   double* work = nullptr;
-  TKBO_CUDA_CHECK(cudaMallocAsync(&work, sizeof(double) * (2 * static_cast<size_t>(total) * d + grid) + sizeof(int), stream));
+  TKBO_CUDA_CHECK(cudaMallocAsync(&work, sizeof(double) * (2 * static_cast<size_t>(total) * d + 2 * grid) + sizeof(int), stream));
   TKBO_CUDA_CHECK(cudaMemcpyAsync(work, X, sizeof(double) * total * d, cudaMemcpyDeviceToDevice, stream));
   AscentState st;
   st.partial = work + 2 * static_cast<size_t>(total) * d;
-  st.steps = reinterpret_cast<int*>(st.partial + grid);
+  st.steps = reinterpret_cast<int*>(st.partial + 2 * grid);
   void* args[] = {&work, &W, &b, &theta, &count, &n, &D, &d, &min_val, &max_val, &num_steps, &lr, &eps, &rel_tol, &st};
   TKBO_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rff_ascent_batched_kernel), dim3(grid), dim3(block),
-                                              args, wpb * sizeof(double), stream));
+                                              args, (wpb + 1) * sizeof(double), stream));
   h->launches += 1;
   TKBO_CUDA_CHECK(cudaMemcpyAsync(X, work, sizeof(double) * total * d, cudaMemcpyDeviceToDevice, stream));
   int steps = 0;
