@@ -336,7 +336,7 @@ def run_gpu(args):
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": alg_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                             "frac": alg_tf / pk["bf16_tflops"], "traffic": 8.74e6 if args.workload == "c2" else None,
+                             "frac": alg_tf / pk["bf16_tflops"], "traffic": 8.75e6 if args.workload == "c2" else None,
                              "kernel": "rff_fused_kernel", "flops_per_launch": 2.0 * N * D * S,
                              "executed": exec_tf, "executed_frac": exec_tf / pk["bf16_tflops"],
                              "mufu": {"cos_per_s": cos_rate, "peak_cos_per_s": cos_peak, "frac": cos_rate / cos_peak,
@@ -348,7 +348,7 @@ def run_gpu(args):
                                         "hi*hi + hi*lo + lo*hi, fp32-accurate") + ") and "
                                      "the bf16x3 projection X W^T + b (K = " + str(proj_k) + "); peak = measured bf16 cuBLAS burst ("
                                      + pk["source"] + "); traffic = dram bytes of one launch from the committed ncu capture "
-                                     "(profiles/r01_prof_k1_v6_summary.txt; algorithmic: 4*N*d = 8.39e6)"}}
+                                     "(profiles/r01_prof_k1_c2_v8_summary.txt; algorithmic: 4*N*d = 8.39e6)"}}
     # ---- MPES kernel at c5
     if rank == 0 and not args.no_mpes:
         Sm, Q, C, k, M = 1024, 100000, 5, 3, 20

@@ -671,3 +671,40 @@ def test_large_shape_properties(pbo):
     xw = X[idx].cpu().numpy().astype(np.float64)
     f64 = rff_oracle.rff_values_shared(xw, W, b, Theta)
     assert np.max(np.abs(np.diag(f64) - val.cpu().numpy()) / np.abs(np.diag(f64))) < VAL_RTOL
+
+
+def test_large_shape_properties_tensor_bound_form(pbo):
+    """The same properties at a c3-like shape (d = 6, D = 4096, S = 256: one 256-sample chunk, e4m3 correction form,
+    separate (W | b) ring, slab-sharing producers), plus agreement of the fast and fp32 contraction forms."""
+    rng = np.random.default_rng(2)
+    N, D, d, S = 1 << 19, 4096, 6, 256
+    W = rng.standard_normal((D, d)) / 0.2
+    b = rng.uniform(0, 2 * np.pi, D)
+    Theta = rng.standard_normal((D, S))
+    X = torch.rand((N, d), device="cuda:0")
+    basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0")
+    cfg = basis.config(N)
+    assert cfg["e4m3_corrections"] == 1 and cfg["w_stages"] >= 2 and cfg["S_chunk"] == 256
+    val, idx = basis.argmax(X)
+    perm = torch.randperm(N, device="cuda:0")
+    val_p, idx_p = basis.argmax(X[perm].contiguous())
+    assert torch.equal(val, val_p)
+    rows = basis.eval(X[idx].contiguous())
+    assert torch.equal(rows.diagonal(), val)
+    third = (N // 3) // 128 * 128
+    parts = [basis.argmax(X[lo:hi], idx_offset=lo) for lo, hi in ((0, third), (third, 2 * third), (2 * third, N))]
+    mv, mi = pbo.distributed.merge_pairs(torch.stack([p[0] for p in parts]).cpu(), torch.stack([p[1] for p in parts]).cpu())
+    assert torch.equal(mv, val.cpu()) and torch.equal(mi, idx.cpu())
+    xw = X[idx].cpu().numpy().astype(np.float64)
+    f64 = np.diag(rff_oracle.rff_values_shared(xw, W, b, Theta))
+    assert np.max(np.abs(f64 - val.cpu().numpy()) / np.abs(f64)) < VAL_RTOL
+    precise = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0", precision="fp32")
+    val32, idx32 = precise.argmax(X)
+    assert np.max(np.abs(f64 - val32.cpu().numpy()[np.arange(S)]) / np.abs(f64)) < 1e-4
+    rel = (val - val32).abs() / val32.abs()
+    assert float(rel.max()) < VAL_RTOL
+    # the two forms may pick different winners only where the top-2 gap is below the tolerance
+    diff = (idx != idx32).nonzero().flatten()
+    if diff.numel():
+        f_at_fast = precise.eval(X[idx[diff]].contiguous())[diff, torch.arange(diff.numel(), device="cuda:0")]
+        assert float(((val32[diff] - f_at_fast) / val32[diff].abs()).max()) < VAL_RTOL
