@@ -1,2 +1,3 @@
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:rff_fused_kernel -s 3 -c 1 -o gpurun_out/prof_k1_c2_v8 -f python bench.py --steps 2 --warmup 3 --no-mpes --no-cpu > gpurun_out/ncu_c2.log 2>&1; tail -2 gpurun_out/ncu_c2.log | cut -c1-200
+TKBO_ACC1=1 timeout 200 python bench.py --no-mpes --no-cpu 2>/dev/null | python tools/_pj.py c2 acc1-ring7
+timeout 200 python bench.py --no-mpes --no-cpu 2>/dev/null | python tools/_pj.py c2 base
+TKBO_ACC1=1 timeout 100 python tools/stress_k1.py 12 13 2>&1 | tail -3
