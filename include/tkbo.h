@@ -111,6 +111,10 @@ int tkbo_unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* ou
 int64_t tkbo_peer_buffer_bytes(int world, int S);
 int tkbo_rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, int64_t idx_offset,
                          void* const* peer_bufs, int world, int rank, uint64_t epoch, void* stream);
+/* Delivers ready-made keys [S] for this epoch instead of running the fused kernel; keys == NULL delivers "no candidate"
+ * (INT64_MIN) -- what a rank whose shard is empty calls so that its peers' merges do not wait for it. */
+int tkbo_peer_push_keys(tkbo_handle_t h, const int64_t* keys, int S, void* const* peer_bufs, int world, int rank,
+                        uint64_t epoch, void* stream);
 int tkbo_merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int S, uint64_t epoch, float* out_val,
                          int64_t* out_idx, void* stream);
 /* Per-rank partial results [G, S] (e.g. after an all-gather) -> global (value, lowest index). */

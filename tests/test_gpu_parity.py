@@ -128,6 +128,12 @@ def test_peer_merge_single_rank(pbo):
         val0, idx0 = basis.argmax(Xi, idx_offset=1000 * it)
         assert torch.equal(val, val0) and torch.equal(idx, idx0)
     assert pm.epoch == 5
+    # an empty shard delivers "no candidate": value NaN, index -1, and the next epoch works as before
+    val, idx = pm.argmax(basis, torch.empty((0, 3), device="cuda:0"), idx_offset=0)
+    assert bool(torch.isnan(val).all()) and bool((idx == -1).all())
+    val, idx = pm.argmax(basis, X[:900], idx_offset=7)
+    val0, idx0 = basis.argmax(X[:900], idx_offset=7)
+    assert torch.equal(val, val0) and torch.equal(idx, idx0)
 
 
 def test_rff_argmax_wide_dynamic_range_theta(pbo):

@@ -1,3 +1,5 @@
+#!/usr/bin/env python
+"""One-line digest of a bench.py JSON line read from stdin:  python bench.py ... | python tools/bench_line.py [label ...]"""
 import sys, json
 for l in sys.stdin:
     try: j = json.loads(l)

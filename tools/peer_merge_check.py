@@ -33,6 +33,13 @@ def main():
         val2, idx2 = pkg.distributed.sharded_argmax_fast(basis, Xl, lo)
         assert torch.equal(val, val2) and torch.equal(idx, idx2), f"rank {rank} iteration {it}: peer merge != NCCL merge"
         assert torch.equal(val, ref_val) and torch.equal(idx, ref_idx), f"rank {rank} iteration {it}: != single-GPU result"
+    # the last rank's shard is empty: it delivers "no candidate" and the others must not wait for more
+    lo_last, _ = pkg.distributed.shard_range(N, world - 1, world)
+    exp_val, exp_idx = basis.argmax(torch.from_numpy(X[:lo_last]).to(dev))
+    for it in range(3):
+        mine = Xl if rank < world - 1 else Xl[:0]
+        val, idx = pm.argmax(basis, mine, lo)
+        assert torch.equal(val, exp_val) and torch.equal(idx, exp_idx), f"rank {rank}: empty-shard merge differs"
     # timing: merge overhead per iteration, both ways
     out = {}
     for name, fn in (("peer", lambda: pm.argmax(basis, Xl, lo)), ("nccl", lambda: pkg.distributed.sharded_argmax_fast(basis, Xl, lo))):

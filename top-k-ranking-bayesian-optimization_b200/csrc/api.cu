@@ -21,6 +21,8 @@ int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg);
 int rff_argmax_streamed(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t rows_per_chunk,
                         unsigned int* ready_flag, float* out_val, int64_t* out_idx, cudaStream_t stream);
 size_t peer_buffer_words(int world, int S);
+int peer_push_keys(tkbo_handle_t h, const int64_t* keys, int S, void* const* peer_bufs, int world, int rank, uint64_t epoch,
+                   cudaStream_t stream);
 int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs,
                     int world, int rank, uint64_t epoch, cudaStream_t stream);
 int merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int S, uint64_t epoch, float* out_val, int64_t* out_idx,
@@ -245,6 +247,11 @@ int tkbo_rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t basis, const float* X, in
                          void* const* peer_bufs, int world, int rank, uint64_t epoch, void* stream) {
   TKBO_ENTER(h);
   return rff_argmax_peer(h, basis, X, N, idx_offset, peer_bufs, world, rank, epoch, as_stream(stream));
+}
+int tkbo_peer_push_keys(tkbo_handle_t h, const int64_t* keys, int S, void* const* peer_bufs, int world, int rank,
+                        uint64_t epoch, void* stream) {
+  TKBO_ENTER(h);
+  return peer_push_keys(h, keys, S, peer_bufs, world, rank, epoch, as_stream(stream));
 }
 int tkbo_merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int S, uint64_t epoch, float* out_val,
                          int64_t* out_idx, void* stream) {

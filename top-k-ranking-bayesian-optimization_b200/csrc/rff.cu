@@ -608,6 +608,12 @@ int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, 
 // e + 1, which has seen every peer's e + 1 keys, and those were launched behind that peer's merge of e.
 size_t peer_buffer_words(int world, int S) { return 2ull * world * S + 8; }
 
+struct RffPeer {
+  unsigned long long* buf[8];
+  int world, rank;
+  unsigned long long epoch;
+};
+
 int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs,
                     int world, int rank, uint64_t epoch, cudaStream_t stream) {
   RffParams p;
@@ -623,6 +629,36 @@ int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N,
   p.peer_world = world; p.peer_rank = rank; p.peer_epoch = epoch;
   p.idx_offset = idx_offset;
   return dispatch_fused<0>(h, bs, p, grid, stream);
+}
+
+// Delivery of ready-made keys (or, keys == nullptr, of "nothing seen": a rank whose shard is empty still has to release
+// its flag): one block, same stores / fence / release as the fused kernel's last CTA.
+__global__ void peer_push_keys_kernel(const long long* __restrict__ keys, int S, RffPeer pr) {
+  const size_t slot0 = (static_cast<size_t>(pr.epoch & 1ull) * pr.world + pr.rank) * S;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const long long key = keys ? keys[s] : kEmptyKey;
+    for (int r = 0; r < pr.world; ++r) pr.buf[r][slot0 + s] = static_cast<unsigned long long>(key);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < pr.world) {
+    unsigned long long* flag = pr.buf[threadIdx.x] + 2ull * pr.world * S + pr.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(pr.epoch) : "memory");
+  }
+}
+
+int peer_push_keys(tkbo_handle_t h, const int64_t* keys, int S, void* const* peer_bufs, int world, int rank, uint64_t epoch,
+                   cudaStream_t stream) {
+  TKBO_REQUIRE(h && peer_bufs && S >= 1, "null pointer");
+  TKBO_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && epoch >= 1, "bad peer arguments");
+  RffPeer pr;
+  for (int r = 0; r < 8; ++r) pr.buf[r] = r < world ? static_cast<unsigned long long*>(peer_bufs[r]) : nullptr;
+  for (int r = 0; r < world; ++r) TKBO_REQUIRE(pr.buf[r] != nullptr, "null peer buffer");
+  pr.world = world; pr.rank = rank; pr.epoch = epoch;
+  peer_push_keys_kernel<<<1, 256, 0, stream>>>(reinterpret_cast<const long long*>(keys), S, pr);
+  h->launches += 1;
+  TKBO_CUDA_CHECK(cudaGetLastError());
+  return TKBO_OK;
 }
 
 // One block per 256 samples; its first `world` threads wait for the flags (bounded: ~10 s, then every index of the block

@@ -134,13 +134,19 @@ class PeerMerge:
         self._nat = nat
 
     def argmax(self, basis, X_local, idx_offset):
-        """(val[S], idx[S]) over all ranks' shards; X_local are rows [idx_offset, idx_offset + N_local) (N_local >= 1)."""
+        """(val[S], idx[S]) over all ranks' shards; X_local are rows [idx_offset, idx_offset + N_local); an empty shard
+        delivers "no candidate" so that the peers do not wait for it."""
         import ctypes
         import torch
         nat = self._nat
         assert basis.S == self.S
         self.epoch += 1
-        basis.argmax_peer(X_local, idx_offset, self._ptrs, self.rank, self.epoch)
+        if X_local.shape[0] == 0:
+            nat.check(nat.lib().tkbo_peer_push_keys(nat.handle(self.device.index), None, self.S, self._ptrs, self.world,
+                                                    self.rank, self.epoch, nat.current_stream_ptr(self.device)),
+                      "tkbo_peer_push_keys")
+        else:
+            basis.argmax_peer(X_local, idx_offset, self._ptrs, self.rank, self.epoch)
         val = torch.empty(self.S, dtype=torch.float32, device=self.device)
         idx = torch.empty(self.S, dtype=torch.int64, device=self.device)
         nat.check(nat.lib().tkbo_merge_peer_keys(nat.handle(self.device.index), ctypes.c_void_p(self.buf.data_ptr()), self.world,
