@@ -284,3 +284,55 @@ def test_pes_building_blocks_reassemble_to_I():
         log_pz = torch.logsumexp(log_px + log_pz_x, dim=0)                      # pes.py:115-118
         total += float((torch.exp(log_px) * torch.exp(log_pz_x) * (log_pz_x - log_pz)).sum())
     np.testing.assert_allclose(total, mpes_oracle.pes_I_from_samples(samples, M), rtol=1e-9)
+
+
+def _gloo_query_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    pkg = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    mi = rng.random(1000)                                             # the full MI vector, same on all ranks
+    mi[777] = mi[40] = mi.max() + 0.5                                 # exact tie across shards -> lowest query index
+    lo, hi = pkg.distributed.query_shard(1000, rank, world)
+    loc = torch.from_numpy(mi[lo:hi])
+    best = pkg.distributed.best_query(loc, lo)
+    full = pkg.distributed.allgather_queries(loc, 1000)
+    # a rank without queries (more ranks than 32-query tiles) contributes nothing
+    lo2, hi2 = pkg.distributed.query_shard(20, rank, world)
+    best2 = pkg.distributed.best_query(torch.from_numpy(mi[lo2:hi2]), lo2)
+    q.put((rank, best, full.numpy(), (lo2, hi2), best2))
+    dist.destroy_process_group()
+
+
+def test_query_shards_best_and_gather_world2_gloo():
+    """K2's multi-GPU side: contiguous query shards of whole 32-query tiles, the (best MI, lowest index)
+    pair over all shards, and the gathered MI vector, on two gloo ranks."""
+    import torch.multiprocessing as mp
+    pkg = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
+    for Q, world in ((1000, 2), (100000, 8), (31, 4), (33, 2)):
+        ranges = [pkg.distributed.query_shard(Q, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == Q
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert all(lo % 32 == 0 or lo == Q for lo, _ in ranges)
+        sizes = [hi - lo for lo, hi in ranges]
+        assert max(sizes) - min(sizes) <= 32 + (Q % 32 != 0) * 32
+    assert pkg.distributed.best_query(torch.tensor([0.1, 0.7, 0.7, 0.2]), 10) == (pytest.approx(0.7), 11)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_query_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(5)
+    mi = rng.random(1000)
+    mi[777] = mi[40] = mi.max() + 0.5
+    for _, best, full, (lo2, hi2), best2 in res:
+        assert best == (mi[40], 40)
+        np.testing.assert_array_equal(full, mi)
+        assert best2 == (mi[:20].max(), int(np.argmax(mi[:20])))
+    assert sorted(r[3] for r in res) == [(0, 20), (20, 20)]           # the second rank's shard is empty

@@ -714,3 +714,27 @@ def test_large_shape_properties_tensor_bound_form(pbo):
     if diff.numel():
         f_at_fast = precise.eval(X[idx[diff]].contiguous())[diff, torch.arange(diff.numel(), device="cuda:0")]
         assert float(((val32[diff] - f_at_fast) / val32[diff].abs()).max()) < VAL_RTOL
+
+
+def test_mpes_query_shards_equal_full(pbo):
+    """K2 is independent per query set given the (global) samples: the MI of a query shard computed alone is bitwise
+    the MI of those queries in the full batch, for ragged shard boundaries too, and the sharded best query is np.argmax."""
+    gen = torch.Generator(device="cuda:0").manual_seed(11)
+    S, Q, C, k, M = 512, 3000, 5, 3, 12
+    fchi = torch.randn((S, Q, C), device="cuda:0", generator=gen)
+    fstar = torch.randn((S, M), device="cuda:0", generator=gen)
+    common = pbo.acquisitions._common
+    nat = pbo._native
+    full = common.mpes_from_device_samples(fchi, fstar, k, nat.MPES_RANK)
+    dist_ = pbo.distributed
+    parts, bests = [], []
+    for r in range(3):
+        lo, hi = dist_.query_shard(Q, r, 3)
+        mi, best = dist_.sharded_mpes(fchi[:, lo:hi, :].contiguous(), fstar, k, nat.MPES_RANK, lo)
+        parts.append(mi)
+        bests.append(best)
+    assert torch.equal(torch.cat(parts), full)
+    top = max(bests, key=lambda b: (b[0], -b[1]))
+    assert top[1] == int(torch.argmax(full)) and top[0] == float(full.max())
+    mi0, best0 = dist_.sharded_mpes(fchi[:, :0, :].contiguous(), fstar, k, nat.MPES_RANK, 0)
+    assert mi0.numel() == 0 and best0 == (-float("inf"), -1)

@@ -1,6 +1,8 @@
-"""Multi-GPU use of the RFF sampler: the candidate axis shards across ranks, (W, b, Theta) are replicated, and
-the only exchange is one all-gather of each rank's S (value, index) pairs (8 S bytes per rank, over NCCL /
-NVLink on GPUs; gloo in the CPU tests of the merge logic).  One process per GPU (torchrun).
+"""Multi-GPU use of the path.  K1: the candidate axis shards across ranks, (W, b, Theta) are replicated, and the only
+exchange is the merge of each rank's S (value, index) keys (8 S bytes per rank: pushed over NVLink peer memory by the
+kernel itself, ``PeerMerge``; or one NCCL all_reduce(MAX) / all-gather; gloo in the CPU tests of the merge logic).
+K2: the query axis shards, the posterior samples are global, and callers exchange either one (best MI, index) pair per
+rank or the MI shards.  One process per GPU (torchrun).
 """
 from __future__ import annotations
 
@@ -187,6 +189,70 @@ def sharded_duel_copeland(basis, X_base, group=None, scores=True):
     else:
         fix = basis.duel_copeland_partial(X_base, 0, n)
     return basis.copeland_finish(fix, scores=scores)
+
+
+# ---- K2 (MPES / PES / indifference MI): the query axis shards, the samples are global ------------------------------------
+def query_shard(Q, rank, world_size):
+    """Contiguous range [lo, hi) of rank's query sets; sizes differ by at most one 32-query tile (K2's work unit)."""
+    tiles = (Q + 31) // 32
+    per, rem = divmod(tiles, world_size)
+    lo_t = rank * per + min(rank, rem)
+    hi_t = lo_t + per + (1 if rank < rem else 0)
+    return min(Q, lo_t * 32), min(Q, hi_t * 32)
+
+
+def best_query(mi_local, q_offset, group=None):
+    """(max MI, global query index) over all ranks' shards, lowest index on ties: the ``np.argmax(I_vals)`` of
+    MPES_Forr.py:309 without gathering the Q values.  One all-gather of a float64 pair per rank; the same result on every
+    rank.  ``mi_local`` may be empty (a rank without queries)."""
+    import torch
+    import torch.distributed as dist
+    mi_local = torch.as_tensor(mi_local)
+    if mi_local.numel():
+        v = mi_local.to(torch.float64).max()
+        i = (mi_local.to(torch.float64) == v).nonzero()[0, 0]      # lowest index attaining it, like np.argmax
+        pair = torch.stack([v, (i + q_offset).to(torch.float64)])
+    else:
+        pair = torch.tensor([-float("inf"), -1.0], dtype=torch.float64, device=mi_local.device)
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return float(pair[0]), int(pair[1])
+    gathered = [torch.empty_like(pair) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(gathered, pair, group=group)
+    allp = torch.stack(gathered).cpu()
+    best = allp[:, 0].max()
+    idx = allp[(allp[:, 0] == best) & (allp[:, 1] >= 0), 1]
+    return float(best), (int(idx.min()) if idx.numel() else -1)
+
+
+def allgather_queries(mi_local, Q, group=None):
+    """Full (Q,) MI vector on every rank from the per-rank shards laid out by ``query_shard`` (what a caller that wants
+    all of ``I_vals`` uses; 8 Q / G bytes per rank)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return mi_local
+    world = dist.get_world_size(group)
+    sizes = [hi - lo for lo, hi in (query_shard(Q, r, world) for r in range(world))]
+    pad = max(sizes)
+    buf = torch.zeros(pad, dtype=mi_local.dtype, device=mi_local.device)
+    buf[: mi_local.numel()] = mi_local
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    return torch.cat([g[:n] for g, n in zip(gathered, sizes)])
+
+
+def sharded_mpes(fchi_local, fstar, topk, mode, q_offset, group=None, perms=None):
+    """K2 on this rank's query shard: fchi_local (S, Q_local, C) are the f-samples at the shard's query sets, fstar
+    (S, M) the samples at the maximisers -- the SAME S joint posterior draws on every rank (replicated basis /
+    ``broadcast_basis_arrays``), so the grouping by arg max and p(x*) are global without any exchange.
+    -> (mi_local (Q_local,) float64, (best value, best global query index))."""
+    from .acquisitions import _common
+    if fchi_local.shape[1] == 0:
+        import torch
+        mi_local = torch.empty(0, dtype=torch.float64, device=fchi_local.device)
+    else:
+        mi_local = _common.mpes_from_device_samples(fchi_local, fstar, topk, mode, perms=perms)
+    return mi_local, best_query(mi_local, q_offset, group=group)
 
 
 def broadcast_basis_arrays(W, b, Theta, src=0, group=None, device=None):
