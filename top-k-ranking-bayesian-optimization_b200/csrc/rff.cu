@@ -424,14 +424,19 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
     if ((t == 2 || t == 3) && bs->npg != 4) bs->npg = t;
   }
   bs->smem_bytes = bs->stages * stride + 1024 + (bs->npg == 4 ? 2 * proj_x_bytes(DT) : 0);
-  // Wide sample chunks leave room for only 3-5 combined stages, and a stage is then held from its TMA issue through the
-  // projection and the feature producers until its main MMAs retire (~4500 cycles for ~1000 cycles of use).  Split mode
-  // gives the small (W | b) tiles their own ring: the Theta stages are held for TMA latency + main MMAs only, and the
-  // projections / producers run ahead as far as the TMEM ring allows.
-  bs->coop = (bs->npg == 2 && bs->ring <= 3) ? 1 : 0;
+  // Slab-sharing producers (both groups convert every slab, half the per-slab latency) paid off only while a conversion
+  // took ~9 instructions per feature; with 4-6 the fixed per-slab cost per warp outweighs it (c3 shard 6.8 vs 6.3 ms), so
+  // the mode is off unless asked for.
+  bs->coop = 0;
   if (const char* env = getenv("TKBO_COOP")) bs->coop = (bs->npg == 2 && atoi(env) != 0) ? 1 : 0;
+  // The widest sample chunks (SC > 192) leave room for only 3 combined stages, and a stage is then held from its TMA issue
+  // through the projection and the feature producers until its main MMAs retire (~4500 cycles for ~1000 cycles of use).
+  // Split mode gives the small (W | b) tiles their own ring: the Theta stages are held for TMA latency + main MMAs only,
+  // and the projections / producers run ahead as far as the TMEM ring allows (c3 shard 7.2 -> 6.3 ms).  With 4 or more
+  // combined stages the extra b_full wait of the main warps costs more than the decoupling brings (measured at
+  // SC = 128 .. 192), so those keep the combined ring.
   bs->wstages = 0;
-  if (bs->npg != 4 && bs->stages <= 5 && getenv("TKBO_NOSPLIT") == nullptr) {
+  if (bs->npg != 4 && bs->stages <= 3 && getenv("TKBO_NOSPLIT") == nullptr) {
     const int tb = 2 * bs->SC * 128, wb = proj_w_bytes(DT);
     for (int nt = std::min(kMaxStages, smem_limit / tb); nt >= 3; --nt) {
       const int nw = std::min(kMaxWStages, (smem_limit - nt * tb) / wb) & ~1;
