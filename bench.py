@@ -238,8 +238,17 @@ def run_gpu(args):
     if world > 1:
         merge = "one int64 all_reduce(MAX) (NCCL)"
         if os.environ.get("TKBO_MERGE", "peer") == "peer":
-            peer = pkg.distributed.PeerMerge(S, dev)
-            merge = "keys pushed to peer memory by the kernel's last CTA + flag-acquiring merge kernel (no collective call)"
+            try:
+                peer = pkg.distributed.PeerMerge(S, dev)
+            except Exception as err:                     # no peer mapping on this box: every rank must take the same path
+                print(f"[bench] rank {rank}: peer-memory merge unavailable ({err}); using the NCCL merge", file=sys.stderr)
+                peer = None
+            agree = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if int(agree.item()) == 0:
+                peer = None
+            else:
+                merge = "keys pushed to peer memory by the kernel's last CTA + flag-acquiring merge kernel (no collective call)"
 
     def step(i):
         if peer is not None:
