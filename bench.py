@@ -384,6 +384,21 @@ def run_gpu(args):
                                      "frac": bytes_alg / (mms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
                                      "kernel": "mpes_all_perms_kernel<5,3>"},
                         "checksum": float(mi.sum())}
+        if world == 1 and not args.no_cpu:
+            # the reference's algorithm for this kernel on one host core: rank_pes.I_batch restated in NumPy (oracle/,
+            # pinned to golden vectors of the unmodified rank_pes.py), on a bounded slice of the same samples; doubles as
+            # a parity spot check of the values the timed kernel produced
+            from oracle import mpes_oracle
+            Qc = 512
+            f_cpu = fchi[:, :Qc, :].double().cpu().numpy()
+            s_cpu = fstar.double().cpu().numpy()
+            tc0 = time.perf_counter()
+            mi_cpu = mpes_oracle.rank_mpes_from_samples(f_cpu, s_cpu, topk=k)
+            tc = time.perf_counter() - tc0
+            mi_gpu = mi[:Qc].cpu().numpy()
+            line["mpes"]["cpu_baseline"] = {"value": Qc / tc, "unit": "acq evals/s", "cores": 1, "kind": "port",
+                                            "sample": f"{Qc} of the {Q} query sets (NumPy restatement of rank_pes.py:10-108)",
+                                            "max_rel_diff_vs_gpu": float(np.max(np.abs(mi_gpu - mi_cpu) / np.abs(mi_cpu)))}
         del fchi, fstar
         # the whole acquisition on the device: RFF joint samples at the query points and the maximisers (K1, store-F
         # epilogue, 1024 samples = 4 chunks of 256), winning maximiser per sample, K2, best query
