@@ -295,10 +295,10 @@ def run_gpu(args):
 
     def e2e_step(i):
         ff.argmax_host(W_h, b_h, T_h, host_bufs[i % len(host_bufs)], device=local, out_val=res_val, out_idx=res_idx)
-        if world > 1:       # merge the per-rank results (global index = local + rank offset)
-            key = torch.stack([res_val.to(dev).double(), -(res_idx.to(dev) + offset).double()])
-            gathered = [torch.empty_like(key) for _ in range(world)]
-            dist.all_gather(gathered, key)
+        if world > 1:       # merge the per-rank host results: one packed int64 key per sample, all_reduce(MAX), back to the host
+            key = pkg.distributed.pack_argmax_key(res_val, res_idx + offset).to(dev, non_blocking=True)
+            dist.all_reduce(key, op=dist.ReduceOp.MAX)
+            return int(key.cpu()[0])
         return float(res_val[0])
 
     for i in range(min(3, args.warmup)):
