@@ -1,3 +1,7 @@
+#!/bin/bash
+# bench.py on N GPUs of this node for the given workloads, one digest line each (results in gpurun_out/):
+#   bash tools/bench_multi_gpu.sh 8 c2 c3s c4d
+mkdir -p gpurun_out
 N=$1; shift
 for w in "$@"; do
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --workload $w --no-mpes --no-cpu > gpurun_out/mg${N}_$w.json 2> gpurun_out/mg${N}_$w.err

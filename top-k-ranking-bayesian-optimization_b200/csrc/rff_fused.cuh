@@ -5,22 +5,26 @@
 // Work item = (128-candidate tile, chunk of SC samples).  Per item the CTA accumulates
 //     acc[128 x SC] = sum over 64-feature slabs of  Phi_slab[128 x 64] * ThetaScaled_slab[SC x 64]^T
 // with Phi and Theta each split into fp16 hi + lo parts and three tcgen05.mma (hi*hi + hi*lo + lo*hi) per
-// K=16 step, fp32 accumulation in TMEM ("fp32 emulation": ~2^-22 relative per product).
+// K=16 step, fp32 accumulation in TMEM ("fp32 emulation": ~2^-22 relative per product) -- or, template C8, hi*hi in
+// fp16 plus ONE e4m3 tcgen05.mma (K = 32) that carries both correction terms: two thirds of the tensor work at ~3e-5
+// of max|f| (see cos_split16_c8).
 //
 // Both GEMMs of the path run on the tensor pipe.  The projection  arg = X W^T + b  of a slab is itself a small
 // tcgen05.mma: X and (W | b) are split into three bf16 terms each (x = x1 + x2 + x3 exactly) and the six products
 // of order >= 2^-16 are laid side by side along K (K = 6 d + 3 <= 112), so that arg lands in TMEM with fp32
-// accuracy.  The feature producers then only do  TMEM -> cos -> fp16 hi/lo split -> TMEM  in place: five
+// accuracy.  The feature producers then only do  TMEM -> cos -> fp16 hi/lo split -> TMEM  in place: four to six
 // instructions per feature, independent of d, no shared-memory traffic.
 //
 // Warp roles (32 * (6 + 4 NPG) threads, one CTA per SM, persistent over work items):
 //   warps 0-3   per item: write the bf16-split candidate rows (projection A operand) into TMEM ahead of time;
-//               epilogue: accumulator -> per-sample warp max (CREDUX) + ballot row -> register best, one atomicMax
-//               per (warp, sample) at the end; or store F
+//               epilogue: accumulator -> one compare per value against the running per-sample maxima (thr_s); only
+//               32-column blocks that may improve a sample run the warp max (CREDUX) + ballot row + atomicMax of the
+//               packed (value, ~row) key; or store F; or soft-Copeland sums (duel mode)
 //   warps 4..   feature producers (NPG groups of four warps; group g takes global slab iterations g, g+NPG, ...):
 //               thread = one candidate row: tcgen05.ld 64 projection values, cos, hi/lo split, tcgen05.st back
 //               into the same 64 TMEM columns, which the main MMAs then read as their A operand
 //   next warp   TMA: Theta hi/lo slab tiles (128B-swizzled, K-major) + the bf16 (W | b) slab tile into the smem ring
+//               (wstages > 0: the (W | b) tiles have their own, deeper ring and run ahead of the Theta stages)
 //   2 warps     projection MMAs, alternating slabs (1 warp when the smem ring depth is odd): they run ahead of the
 //               main MMAs as far as free TMEM ring slots and landed tiles allow
 //   2 warps     main MMAs, each owning one half of the accumulator columns (N = SC / 2 per instruction), two slabs
@@ -28,6 +32,10 @@
 //   A lone warp needs ~300 cycles for the waits, commits and address arithmetic of one slab while the tensor
 //   pipe queues only ~4 instructions, so a single issuing warp starves the pipe (tools/probe_mma_chain.cu);
 //   splitting the issue work by columns keeps every accumulator column's MMAs in one program order.
+//
+// Around the launch: the last CTA unpacks the running keys and, for the multi-GPU merge, stores them into every rank's
+// peer-mapped buffer and releases a flag (RffParams::peer_buf); with host candidates the row-staging warps acquire a
+// "chunks landed" counter that the H2D copy stream bumps, so one launch overlaps the transfer (RffParams::ready_flag).
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
