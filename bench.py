@@ -545,7 +545,7 @@ def run_gpu_duel(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": ("f32 (fp16 hi*hi + e4m3 correction tcgen05.mma" if mma_eq == 2 else "f32 (fp16 hi/lo split x3 tcgen05.mma")
-                         + ", fp32 accumulate; sigmoid sums in 2^-24 fixed point)",
+                         + ", fp32 accumulate; sigmoid sums in 2^-23 fixed point)",
                 "data": "synthetic",
                 "config": {"workload": "c4d: DTS batch Thompson, n=2048 base points (d_obj=2), duels [x_i, x_j] generated in the "
                                        "kernel, D=2048, S=4096, soft-Copeland winners; per rank the j-shard of n/8 = 2^19 duels "

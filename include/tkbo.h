@@ -87,7 +87,7 @@ int tkbo_rff_eval(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N
  * may be NULL) and out_argmax[s] = lowest i attaining the maximum (may be NULL).  The per-duel values never leave the SM. */
 int tkbo_rff_duel_copeland(tkbo_handle_t h, tkbo_basis_t basis, const float* Xbase, int n, float* out_score,
                            int64_t* out_argmax, void* stream);
-/* Sharded form: accumulate fix[s, i] += sum_{j in [j_begin, j_end)} round(2^24 sigmoid(f_s([x_i, x_j]))) into the caller's
+/* Sharded form: accumulate fix[s, i] += sum_{j in [j_begin, j_end)} round(2^23 sigmoid(f_s([x_i, x_j]))) into the caller's
  * zero-initialised uint64 [S, n] buffer (integer sums: shards held by different ranks combine exactly with one
  * all-reduce(SUM) over int64), then tkbo_copeland_finish turns the sums into mean scores and winners. */
 int tkbo_rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t basis, const float* Xbase, int n, int j_begin, int j_end,

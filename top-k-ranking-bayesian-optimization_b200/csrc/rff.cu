@@ -769,7 +769,7 @@ int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float*
   return dispatch_fused<1>(h, bs, p, grid, stream);
 }
 
-// score[s, i] = fix[s, i] / (2^24 n), argmax over i (lowest index on ties)                 [dts.py:94-97]
+// score[s, i] = fix[s, i] / (2^23 n), argmax over i (lowest index on ties)                 [dts.py:94-97]
 __global__ void copeland_finish_kernel(const unsigned long long* __restrict__ fix, int n, float* __restrict__ score,
                                        long long* __restrict__ out_arg) {
   const int s = blockIdx.x;
@@ -777,7 +777,7 @@ __global__ void copeland_finish_kernel(const unsigned long long* __restrict__ fi
   __shared__ int bi[256];
   unsigned long long best = 0ull;
   int idx = 0x7fffffff;
-  const double inv = 1.0 / (16777216.0 * static_cast<double>(n));
+  const double inv = 1.0 / (static_cast<double>(kCopelandFixScale) * static_cast<double>(n));
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned long long v = fix[static_cast<size_t>(s) * n + i];
     if (score) score[static_cast<size_t>(s) * n + i] = static_cast<float>(static_cast<double>(v) * inv);
@@ -799,7 +799,7 @@ __global__ void copeland_finish_kernel(const unsigned long long* __restrict__ fi
 }
 
 // Dueling-Thompson soft-Copeland sums over the ordered pairs (i, j), j in [j_begin, j_end), of n base points; the duels are
-// generated on the fly and fix[s, i] += sum_j round(sigmoid(f_s([x_i, x_j])) * 2^24) (the caller zeroes fix; shards of j held by
+// generated on the fly and fix[s, i] += sum_j round(sigmoid(f_s([x_i, x_j])) * 2^23) (the caller zeroes fix; shards of j held by
 // different ranks add up exactly with an integer all-reduce).
 int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xbase, int n, int j_begin, int j_end,
                               uint64_t* fix, cudaStream_t stream) {

@@ -51,7 +51,9 @@ constexpr int kNumThreadsFor(int npg) { return 32 * (4 + 4 * npg + 1 + kProjWarp
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 12;       // smem ring (Theta + W tiles)
 constexpr int kMaxWStages = 8;     // separate (W | b) tile ring (split mode)
-constexpr int kMaxRing = 6;          // TMEM ring (projection result -> Phi hi/lo), 64 columns per slot
+constexpr int kMaxRing = 6;
+constexpr int kCopelandFixBits = 23;                     // soft-Copeland sums: sigmoid in 2^-23 fixed point
+constexpr float kCopelandFixScale = 8388608.f;           // 2^23, also the magic number that rounds s 2^23 to an integer          // TMEM ring (projection result -> Phi hi/lo), 64 columns per slot
 
 // Projection K extent for a template input dimension: 6 split products per dimension + 3 bias terms.
 __host__ __device__ constexpr int proj_k_used(int DT) { return ((6 * DT + 3 + 15) / 16) * 16; }     // K multiplied
@@ -113,7 +115,7 @@ struct RffParams {
   int duel_n;                // > 0: the candidates are the ordered pairs [x_i, x_j] of duel_n base points of dimension d / 2
                              // held in X (dts.py:31-45); a tile = one i and 128 consecutive j; never materialised
   int duel_j0, duel_nj;      // this launch's shard of the second argument: j in [duel_j0, duel_j0 + duel_nj)
-  unsigned long long* score_fix;   // [S, duel_n] (MODE 2) sum over j of sigmoid(f) in 2^-24 fixed point (deterministic atomics)
+  unsigned long long* score_fix;   // [S, duel_n] (MODE 2) sum over j of sigmoid(f) in 2^-23 fixed point (deterministic atomics)
   int debug;                 // timing ablations (TKBO_DEBUG): 1 = hi*hi MMA only, 2 = producers skip the cos, 4 = no Theta TMA
   unsigned long long* trace; // optional clock64() event log of CTA 0 ([kTraceEvents][trace_cap]), tools/trace_k1.py
   int trace_cap;
@@ -747,22 +749,37 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             }
           } else {
             // soft-Copeland partial sums (dts.py:94-96): this tile holds f_s([x_i, x_j]) for one i and 128 values of j.
-            // sigmoid in fp32, rounded to 2^-24 fixed point, summed over the warp's 32 rows with an integer redux and
-            // added to score_fix[s, i] with one 64-bit atomic per (warp, sample): integer sums commute exactly.
+            // sigmoid in fp32, rounded to 2^-23 fixed point (kCopelandFixBits), summed over the warp's 32 rows with an integer
+            // redux and added to score_fix[s, i] with one 64-bit atomic per (warp, sample): integer sums commute exactly.
+            // The read-out is not overlapped when the accumulator is single-buffered and its XU work (ex2, rcp, float ->
+            // int) bound it, so: two columns share one reciprocal, 1/((1+e0)(1+e1)) times the other factor (f clamped
+            // to +-20, beyond which the sigmoid rounds to 0 or 1 on the grid anyway, keeps the product finite), and the
+            // rounding to integer is the magic-number add  s 2^23 + 2^23  on the FMA pipe (exact for 0 <= s <= 1).
             const int tpi = (p.duel_nj + kTileM - 1) / kTileM;
             const int i_row = mtile / tpi;
             const bool j_ok = (mtile % tpi) * kTileM + q * 32 + lane < p.duel_nj;
             unsigned mine = 0u;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int s = min(s_base + j * 32 + c, p.S - 1);
-              const float f = __uint_as_float(v[c]) * __ldg(p.unscale + s);
-              float e, sg;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * f));
-              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + e));
-              const unsigned u = j_ok ? __float2uint_rn(sg * 16777216.f) : 0u;
-              const unsigned r = __reduce_add_sync(0xffffffffu, u);
-              if (lane == c) mine = r;
+            for (int c = 0; c < 32; c += 2) {
+              float d[2];
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const int s = min(s_base + j * 32 + c + t, p.S - 1);
+                const float f = fminf(fmaxf(__uint_as_float(v[c + t]) * __ldg(p.unscale + s), -20.f), 20.f);
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * f));
+                d[t] = 1.f + e;
+              }
+              float rinv;
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d[0] * d[1]));
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const float sg = rinv * d[1 - t];                                     // 1 / d[t]
+                const unsigned bits = __float_as_uint(fmaf(sg, kCopelandFixScale, kCopelandFixScale));
+                const unsigned u = j_ok ? bits - 0x4B000000u : 0u;                    // round(sg 2^23) = mantissa of sg 2^23 + 2^23
+                const unsigned r = __reduce_add_sync(0xffffffffu, u);
+                if (lane == c + t) mine = r;
+              }
             }
             const int s = s_base + j * 32 + lane;
             if (s < p.S)
