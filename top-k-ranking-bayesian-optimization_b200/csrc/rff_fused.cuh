@@ -240,7 +240,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   __shared__ uint64_t bars[kNumBars];
   __shared__ uint32_t tmem_base_smem;
   __shared__ int is_last_cta;
-  __shared__ __align__(16) float thr_s[256];       // MODE 0: running per-sample maxima of the current chunk (see the epilogue)
+  __shared__ __align__(16) float thr_s[256];       // per column of the current chunk: running maxima (MODE 0) / unscale (MODE 1, 2)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -672,27 +672,28 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       const int mtile = item / n_chunks;
       const int chunk = item % n_chunks;
       const int s_base = chunk * SC;
+      // per-column constants of this item's chunk in shared memory (thr_s): the running-maximum bounds (MODE 0) or the
+      // per-sample unscale factors (MODE 1, 2); loads issued before the wait, stored after it
       float thr_new[2];
-      if constexpr (MODE == 0) {
-        // the bounds of this item's chunk: loads issued before the wait, stored after it
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int c = t * 128 + q * 32 + lane;
+      for (int t = 0; t < 2; ++t) {
+        const int c = t * 128 + q * 32 + lane;
+        if constexpr (MODE == 0) {
           const unsigned long long pk = (c < SC) ? __ldcg(p.packed + s_base + c) : 0ull;
           thr_new[t] = (pk == 0ull) ? -INFINITY : f32_from_orderable(static_cast<uint32_t>(pk >> 32));
+        } else {
+          thr_new[t] = (c < SC) ? __ldg(p.unscale + s_base + c) : 0.f;
         }
       }
       mbar_wait(bar0 + 8 * (kAccFull + ab), aph);
-      if constexpr (MODE == 0) {
-        // the four epilogue warps share thr_s: nobody still reads the previous item's bounds / everybody sees the new ones
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+      // the four epilogue warps share thr_s: nobody still reads the previous item's values / everybody sees the new ones
+      asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int c = t * 128 + q * 32 + lane;
-          if (c < SC) thr_s[c] = thr_new[t];
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int t = 0; t < 2; ++t) {
+        const int c = t * 128 + q * 32 + lane;
+        if (c < SC) thr_s[c] = thr_new[t];
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       if (q == 0) trace_event(p, kTrEpiAccFull, nitem);
       tc_fence_after();
       const long long row0 = static_cast<long long>(mtile) * kTileM + q * 32;
@@ -744,7 +745,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
                 const int s = s_base + j * 32 + c;
-                if (s < p.S) p.out_F[static_cast<long long>(s) * p.ldf + row] = __uint_as_float(v[c]) * __ldg(p.unscale + s);
+                if (s < p.S) p.out_F[static_cast<long long>(s) * p.ldf + row] = __uint_as_float(v[c]) * thr_s[j * 32 + c];
               }
             }
           } else {
@@ -764,8 +765,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
               float d[2];
 #pragma unroll
               for (int t = 0; t < 2; ++t) {
-                const int s = min(s_base + j * 32 + c + t, p.S - 1);
-                const float f = fminf(fmaxf(__uint_as_float(v[c + t]) * __ldg(p.unscale + s), -20.f), 20.f);
+                const float f = fminf(fmaxf(__uint_as_float(v[c + t]) * thr_s[j * 32 + c + t], -20.f), 20.f);
                 float e;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * f));
                 d[t] = 1.f + e;
