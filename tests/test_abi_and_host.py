@@ -336,3 +336,24 @@ def test_query_shards_best_and_gather_world2_gloo():
         np.testing.assert_array_equal(full, mi)
         assert best2 == (mi[:20].max(), int(np.argmax(mi[:20])))
     assert sorted(r[3] for r in res) == [(0, 20), (20, 20)]           # the second rank's shard is empty
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) runs without a GPU and prints one
+    JSON line with the contract's keys: same metric / unit / config as the GPU arm, impl = reference, a cpu_baseline
+    describing the run, and an e2e object without transfers."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["n_gpus"] == 1 and j["steps"] == 1
+    assert j["metric"].startswith("RFF posterior-sample candidate*samples/s") and j["unit"] == "candidate*samples/s"
+    assert j["higher_is_better"] is True and j["value"] > 0 and j["dtype"] == "f64"
+    assert j["config"]["workload"].startswith("c2") and j["config"]["N_per_gpu"] == 1 << 20
+    cb = j["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
