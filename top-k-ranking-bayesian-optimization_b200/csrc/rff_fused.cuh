@@ -759,7 +759,8 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             const int tpi = (p.duel_nj + kTileM - 1) / kTileM;
             const int i_row = mtile / tpi;
             const bool j_ok = (mtile % tpi) * kTileM + q * 32 + lane < p.duel_nj;
-            unsigned mine = 0u;
+            // two passes: all 32 fixed-point values first (independent arithmetic the scheduler can interleave), then the 32
+            // warp reductions -- a redux.sync between the columns would serialise their ex2 -> rcp -> fma chains
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
               float d[2];
@@ -776,10 +777,14 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
               for (int t = 0; t < 2; ++t) {
                 const float sg = rinv * d[1 - t];                                     // 1 / d[t]
                 const unsigned bits = __float_as_uint(fmaf(sg, kCopelandFixScale, kCopelandFixScale));
-                const unsigned u = j_ok ? bits - 0x4B000000u : 0u;                    // round(sg 2^23) = mantissa of sg 2^23 + 2^23
-                const unsigned r = __reduce_add_sync(0xffffffffu, u);
-                if (lane == c + t) mine = r;
+                v[c + t] = j_ok ? bits - 0x4B000000u : 0u;                            // round(sg 2^23) = mantissa of sg 2^23 + 2^23
               }
+            }
+            unsigned mine = 0u;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const unsigned r = __reduce_add_sync(0xffffffffu, v[c]);
+              if (lane == c) mine = r;
             }
             const int s = s_base + j * 32 + lane;
             if (s < p.S)
