@@ -125,7 +125,9 @@ int tkbo_merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, in
  * the end-to-end call a non-torch caller would make. All arrays are HOST pointers.  The fused kernel is launched once,
  * right after the basis is prepared, and consumes the candidates in up to 16 chunks while their H2D copies (second
  * stream) are still landing -- pass pinned X for that overlap; pageable X works, its copies then run host-synchronously
- * behind the launch.  Returns TKBO_ERR_CUDA if a chunk fails to arrive within ~10 s (the kernel does not hang). */
+ * behind the launch.  Returns TKBO_ERR_CUDA if a chunk fails to arrive within ~10 s (the kernel does not hang).
+ * Profilers / sanitizers that serialise kernels against copies defeat the overlap (every launch would sit out its wait
+ * limit): set TKBO_HOST_STREAMED=0 in the environment to queue all copies before the launch. */
 int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, const double* Theta,
                          int D, int d, int S, const float* X, int64_t N, float* out_val, int64_t* out_idx);
 

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -323,6 +324,15 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
   // the first chunk goes out before the basis so that the copy engine is busy while the basis is prepared; the rest is
   // queued after the kernel launch, so that pageable (host-synchronous) candidate copies do not delay the launch
   TKBO_CUDA_CHECK(copy_chunk(0));
+  // Tools that serialise kernels against copies (ncu, compute-sanitizer) would leave the kernel waiting for chunks whose
+  // copies they hold back until its bounded wait expires: TKBO_HOST_STREAMED=0 queues every copy first and launches behind them.
+  const char* streamed_env = getenv("TKBO_HOST_STREAMED");
+  const bool streamed = !(streamed_env != nullptr && atoi(streamed_env) == 0);
+  if (!streamed) {
+    for (int k = 1; k < chunks; ++k) TKBO_CUDA_CHECK(copy_chunk(k));
+    TKBO_CUDA_CHECK(cudaEventRecord(hp.flag_reset, sc));
+    TKBO_CUDA_CHECK(cudaStreamWaitEvent(sx, hp.flag_reset, 0));
+  }
   TKBO_CUDA_CHECK(cudaMemcpyAsync(dW, W, sizeof(double) * D * d, cudaMemcpyHostToDevice, sx));
   TKBO_CUDA_CHECK(cudaMemcpyAsync(db, b, sizeof(double) * D, cudaMemcpyHostToDevice, sx));
   TKBO_CUDA_CHECK(cudaMemcpyAsync(dT, Theta, sizeof(double) * D * S, cudaMemcpyHostToDevice, sx));
@@ -330,7 +340,7 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
   if (rc == TKBO_OK)
     rc = rff_argmax_streamed(h, hp.basis, hp.dX, N, per, dflag, dval, reinterpret_cast<int64_t*>(didx), sx);
   cudaError_t ce = cudaSuccess;
-  for (int k = 1; k < chunks && ce == cudaSuccess; ++k) ce = copy_chunk(k);
+  for (int k = 1; streamed && k < chunks && ce == cudaSuccess; ++k) ce = copy_chunk(k);
   if (rc != TKBO_OK || ce != cudaSuccess) {
     // a launched kernel may be waiting for chunks that were never queued: let its bounded wait expire rather than leave it
     cudaStreamSynchronize(sc); cudaStreamSynchronize(sx);
