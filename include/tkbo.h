@@ -60,9 +60,11 @@ int tkbo_rff_basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int 
 /* Same with an explicit contraction precision.  Phi and Theta are each split into an fp16 hi part and a remainder:
  *   TKBO_PRECISION_FP32  hi*hi + hi*lo + lo*hi as three fp16 tcgen05.mma (fp32 emulation, ~2e-6 of max|F|);
  *   TKBO_PRECISION_FAST  hi*hi in fp16 + both correction terms in ONE e4m3 tcgen05.mma (K = 32): two thirds of the
- *                        tensor work, ~3e-5 of max|F| -- inside the 1e-4 parity tolerance of the path;
- *   TKBO_PRECISION_AUTO  (what tkbo_rff_basis_create uses) FAST where the tensor pipe binds (sample chunks >= 128),
- *                        FP32 otherwise; the environment variable TKBO_PRECISION=fp32|fast overrides AUTO. */
+ *                        tensor work; error ~1e-5 ||sqrt(2/D) theta_s||_2, i.e. ~3e-5 of max|F| for a well-posed
+ *                        regression and above the path's 1e-4 tolerance when the weights cancel (||theta'|| >> max|F|);
+ *   TKBO_PRECISION_AUTO  (what tkbo_rff_basis_create and the _host entry points use) = FP32: the library does not know
+ *                        max|F|, so it never trades accuracy on its own.  The Python SharedBasis picks FAST only when the
+ *                        caller supplies the scale of f and the bound stays below 0.3e-4 of it. */
 #define TKBO_PRECISION_AUTO 0
 #define TKBO_PRECISION_FP32 1
 #define TKBO_PRECISION_FAST 2
@@ -109,8 +111,17 @@ int tkbo_unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* ou
  * Epochs start at 1 and increase by one per call pair on all ranks alike; world <= 8 (one NVSwitch node).  If a peer
  * never delivers, the merge gives up after ~10 s and returns index -2 for every sample instead of hanging. */
 int64_t tkbo_peer_buffer_bytes(int world, int S);
+/* out_val / out_idx both non-NULL: the launch's last CTA also performs the merge (it acquires the `world` flags of this
+ * rank's own buffer after delivering its keys) and writes the GLOBAL (value, index) there -- one launch per rank and
+ * iteration, no tkbo_merge_peer_keys call.  Both NULL: delivery only, merge with tkbo_merge_peer_keys.
+ * All calls of one peer group must be issued in the same order on every rank (epochs advance in lock step) and, per rank,
+ * on one stream. */
 int tkbo_rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, int64_t idx_offset,
-                         void* const* peer_bufs, int world, int rank, uint64_t epoch, void* stream);
+                         void* const* peer_bufs, int world, int rank, uint64_t epoch, float* out_val, int64_t* out_idx,
+                         void* stream);
+/* 0, or the epoch of a merge on this handle that gave up waiting for a peer (index -2 in its outputs); reading clears it.
+ * The word lives in host-mapped memory, so it is meaningful once the stream that ran the merge has been synchronised. */
+int64_t tkbo_peer_status(tkbo_handle_t h);
 /* Delivers ready-made keys [S] for this epoch instead of running the fused kernel; keys == NULL delivers "no candidate"
  * (INT64_MIN) -- what a rank whose shard is empty calls so that its peers' merges do not wait for it. */
 int tkbo_peer_push_keys(tkbo_handle_t h, const int64_t* keys, int S, void* const* peer_bufs, int world, int rank,
@@ -130,6 +141,14 @@ int tkbo_merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, in
  * limit): set TKBO_HOST_STREAMED=0 in the environment to queue all copies before the launch. */
 int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, const double* Theta,
                          int D, int d, int S, const float* X, int64_t N, float* out_val, int64_t* out_idx);
+/* The same for one rank of a candidate-sharded job on one NVSwitch node: X [N, d] is this rank's shard (rows idx_offset ..
+ * idx_offset + N of the global set), peer_bufs / world / rank / epoch as in tkbo_rff_argmax_peer.  One fused launch per call:
+ * it streams the shard in, delivers this rank's keys to every peer, merges in its last CTA, and the GLOBAL S results come
+ * back with a single D2H copy -- no collective call, no second launch.  Synchronous; returns TKBO_ERR_CUDA if a chunk or a
+ * peer fails to arrive within ~10 s.  Every rank of the group must make the call with the same epoch. */
+int tkbo_rff_argmax_host_peer(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
+                              const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs, int world, int rank,
+                              uint64_t epoch, float* out_val, int64_t* out_idx);
 
 /* ---- per-sample-basis RFF (reference-exact shapes, float64 end to end) ----------------------------
  * X [count, n, d], W [count, D, d], b [count, D], theta [count, D]:

@@ -236,3 +236,20 @@ def indiff_mpes_from_samples(fchi, fstar, indifference_threshold=0.1):
         ll = indiff_log_likelihood(fchi[arg == m], S, indifference_threshold)           # :60-65 (C + 1, Q)
         mi += np.sum(np.exp(ll) * (ll - np.log(p_xstar[m]) - log_p_obs), axis=0)        # :80-90
     return mi
+
+
+# --------------------------------------------------------------------------------------
+# pes.py:9-41  grid-argmax maximiser samplers, given the per-batch draws
+# --------------------------------------------------------------------------------------
+def grid_maximizers_from_batches(data, batches, batch_size):
+    """pes.py:24-41: ``samples`` (count, num_data) is filled batch by batch with independent joint draws
+    (``batches[i]`` (count, batch_size) = what ``model.predict_f_samples(data[first:last], count)`` returned), rows past
+    the last FULL batch keep their initial zeros (the loop runs ``num_data // batch_size`` times), then the per-sample
+    argmax over all num_data columns picks the maximiser.  -> (count, input_dims)"""
+    data = np.asarray(data, dtype=np.float64)
+    num_data = data.shape[0]
+    count = np.asarray(batches[0]).shape[0]
+    samples = np.zeros((count, num_data))
+    for i in range(num_data // batch_size):
+        samples[:, i * batch_size:(i + 1) * batch_size] = np.asarray(batches[i], dtype=np.float64)
+    return np.take(data, np.argmax(samples, axis=1), axis=0)

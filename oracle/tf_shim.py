@@ -13,8 +13,14 @@ Semantics mirrored: eager execution, float64, ``tf.linalg.inv`` raising
 ``tf.errors.InvalidArgumentError`` on a singular input, ``tf.scatter_nd`` summing duplicate indices,
 ``tf.math.argmax`` returning the lowest index on ties.  Random streams are NumPy's (seed with
 ``seed()``); parity is always defined on the arrays actually drawn, never on TF's RNG stream.
-No autodiff: ``optimizer.minimize`` is not provided, so the reference's gradient-ascent loop
-(ff.py:149-157) can only be executed with ``num_steps=0``.
+Autodiff for the one place the reference needs it (``optimizer.minimize(loss, var_list=[x_star])``, ff.py:150):
+``_RMSprop.minimize`` re-runs the reference's own ``loss`` closure with the variable replaced by a torch float64
+leaf -- every shim op and every operator on ``Tensor`` forwards to torch when it meets a torch operand -- takes
+``torch.autograd`` gradients and applies the update of ``tf.keras.optimizers.RMSprop`` as TF 2.1 defines it for
+momentum = 0, centered = False (optimizer_v2/rmsprop.py, python path): ``rms <- rho rms + (1 - rho) g^2``,
+``var <- var - lr g / (sqrt(rms) + epsilon)`` (lr = 1e-3, epsilon = 1e-7 by default), then the variable's
+``constraint``.  The gradient, the loop, the loss bookkeeping and the early stop are therefore the reference's own
+code; only this update rule is restated from the TF sources (which are not available offline).
 """
 from __future__ import annotations
 
@@ -22,6 +28,11 @@ import sys
 import types
 
 import numpy as np
+
+try:                                                    # torch is only needed for the autodiff of ``minimize``
+    import torch as _torch
+except Exception:                                       # pragma: no cover
+    _torch = None
 
 _rng = np.random.default_rng(0)
 _variables = []          # every tf.Variable created, in order (lets a test recover ff.py's x_star)
@@ -37,8 +48,36 @@ def created_variables():
     return list(_variables)
 
 
+def _is_torch(x):
+    return _torch is not None and isinstance(x, _torch.Tensor)
+
+
+def _as_torch(x):
+    """torch float64 view of a shim tensor / array; a traced Variable maps to its autograd leaf."""
+    if _is_torch(x):
+        return x
+    leaf = getattr(x, "_leaf", None)
+    if leaf is not None:
+        return leaf
+    return _torch.from_numpy(np.array(np.asarray(x), dtype=np.float64))
+
+
+def _binary(name, reflected=False):
+    base = getattr(np.ndarray, name)
+
+    def op(self, other):
+        if _is_torch(other) or getattr(self, "_leaf", None) is not None or getattr(other, "_leaf", None) is not None:
+            a, b = _as_torch(self), _as_torch(other)
+            fn = getattr(_torch.Tensor, name.replace("__r", "__") if reflected else name)
+            return fn(b, a) if reflected else fn(a, b)
+        return base(self, other)
+    return op
+
+
 class Tensor(np.ndarray):
-    """ndarray with the two eager-tensor members the reference uses: ``.numpy()`` and ``.assign``."""
+    """ndarray with the two eager-tensor members the reference uses: ``.numpy()`` and ``.assign``.  Binary operators
+    forward to torch when the other operand is a torch tensor (the autodiff pass of ``_RMSprop.minimize``)."""
+    __array_priority__ = 1000
 
     def numpy(self):
         return np.asarray(self)
@@ -46,6 +85,16 @@ class Tensor(np.ndarray):
     def assign(self, value):
         self[...] = np.asarray(value)
         return self
+
+    def __neg__(self):
+        leaf = getattr(self, "_leaf", None)
+        return -leaf if leaf is not None else np.ndarray.__neg__(self)
+
+
+for _n in ("__add__", "__sub__", "__mul__", "__truediv__", "__matmul__"):
+    setattr(Tensor, _n, _binary(_n))
+for _n in ("__radd__", "__rsub__", "__rmul__", "__rtruediv__", "__rmatmul__"):
+    setattr(Tensor, _n, _binary(_n, reflected=True))
 
 
 def _t(a, dtype=None):
@@ -60,11 +109,14 @@ class _Variable(Tensor):
         arr = np.array(np.asarray(initial_value), dtype=np.float64 if dtype is None else dtype, copy=True)
         obj = arr.view(cls)
         obj._constraint = constraint
+        obj._leaf = None                               # torch autograd leaf while minimize() traces the loss
+        obj.initial_value = arr.copy()                 # what the reference initialised it with (ff.py:141-144)
         _variables.append(obj)
         return obj
 
     def __array_finalize__(self, obj):
         self._constraint = getattr(obj, "_constraint", None)
+        self._leaf = None
 
     def __getitem__(self, item):
         # slices stay writable views so `expected_log[:, i].assign(...)` (pes.py:119) lands in place
@@ -112,9 +164,9 @@ def build_modules():
     tf.Variable = _Variable
     tf.function = lambda f=None, **kw: f if f is not None else (lambda g: g)
     tf.constant = lambda v, dtype=None, **kw: _t(v, dtype)
-    tf.cast = lambda x, dtype: _t(x, dtype)
+    tf.cast = lambda x, dtype: x if _is_torch(x) else _t(x, dtype)
     tf.sqrt = lambda x: _t(np.sqrt(x))
-    tf.cos = lambda x: _t(np.cos(np.asarray(x)))
+    tf.cos = lambda x: _torch.cos(x) if _is_torch(x) else _t(np.cos(np.asarray(x)))
     tf.exp = lambda x: _t(np.exp(np.asarray(x)))
     tf.zeros = lambda shape, dtype=np.float32: _t(np.zeros(shape, dtype=dtype))
     tf.ones = lambda shape, dtype=np.float32: _t(np.ones(shape, dtype=dtype))
@@ -128,13 +180,15 @@ def build_modules():
     tf.argmax = lambda x, axis=0, output_type=np.int64: _t(np.argmax(np.asarray(x), axis=axis).astype(output_type))
     tf.gather_nd = lambda params, indices: _gather_nd(params, indices)
     tf.scatter_nd = lambda indices, updates, shape: _scatter_nd(indices, updates, shape)
-    tf.reduce_mean = lambda x: _t(np.mean(np.asarray(x)))
+    tf.reduce_mean = lambda x: _torch.mean(x) if _is_torch(x) else _t(np.mean(np.asarray(x)))
     tf.reduce_sum = lambda x, axis=None: _t(np.sum(np.asarray(x), axis=axis))
     tf.reduce_logsumexp = lambda x, axis=None: _logsumexp(x, axis)
     tf.clip_by_value = lambda x, lo, hi: _t(np.clip(np.asarray(x), lo, hi))
     tf.cond = lambda pred, true_fn, false_fn: true_fn() if bool(pred) else false_fn()
     tf.linalg = types.SimpleNamespace(
-        matrix_transpose=lambda x: _t(np.swapaxes(np.asarray(x), -1, -2)),
+        matrix_transpose=lambda x: (_torch.swapaxes(_as_torch(x), -1, -2)
+                                    if (_is_torch(x) or getattr(x, "_leaf", None) is not None)
+                                    else _t(np.swapaxes(np.asarray(x), -1, -2))),
         inv=_inv)
     tf.math = types.SimpleNamespace(
         argmax=lambda x, axis=0, output_type=np.int64: _t(np.argmax(np.asarray(x), axis=axis).astype(output_type)),
@@ -149,12 +203,33 @@ def build_modules():
             _t(_rng.uniform(minval, 1.0 if maxval is None else maxval, size=tuple(shape)), dtype))
     tf.errors = types.SimpleNamespace(InvalidArgumentError=InvalidArgumentError)
 
-    class _RMSprop:                                   # constructed at ff.py:139; minimize needs autodiff
-        def __init__(self, *a, **kw):
-            self.kw = kw
+    class _RMSprop:                                   # constructed at ff.py:139 as RMSprop(rho=0.0)
+        """TF 2.1 tf.keras.optimizers.RMSprop, momentum = 0, centered = False (see the module docstring)."""
 
-        def minimize(self, *a, **kw):
-            raise NotImplementedError("tf_shim has no autodiff; run the reference with num_steps=0")
+        def __init__(self, learning_rate=0.001, rho=0.9, momentum=0.0, epsilon=1e-7, centered=False, **kw):
+            assert momentum == 0.0 and not centered, "only the plain RMSprop path is restated"
+            self.lr, self.rho, self.epsilon = float(learning_rate), float(rho), float(epsilon)
+            self.rms = {}
+
+        def minimize(self, loss, var_list):
+            if _torch is None:
+                raise NotImplementedError("tf_shim.minimize needs torch for autodiff")
+            for v in var_list:
+                v._leaf = _torch.from_numpy(np.array(np.asarray(v), dtype=np.float64)).requires_grad_(True)
+            try:
+                value = loss()                         # the reference's closure, executed on torch tensors
+                grads = _torch.autograd.grad(value, [v._leaf for v in var_list])
+            finally:
+                for v in var_list:
+                    v._leaf = None
+            for v, g in zip(var_list, grads):
+                g = g.numpy()
+                rms = self.rho * self.rms.get(id(v), np.zeros_like(g)) + (1.0 - self.rho) * g * g
+                self.rms[id(v)] = rms
+                new = np.asarray(v) - self.lr * g / (np.sqrt(rms) + self.epsilon)
+                if v._constraint is not None:
+                    new = np.asarray(v._constraint(_t(new)))
+                v[...] = new
 
     tf.keras = types.SimpleNamespace(
         backend=types.SimpleNamespace(epsilon=lambda: 1e-7),

@@ -344,8 +344,8 @@ def test_bench_reference_arm_contract():
     describing the run, and an e2e object without transfers."""
     import json
     import subprocess
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--budget-s", "3"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -353,7 +353,9 @@ def test_bench_reference_arm_contract():
     assert j["impl"] == "reference" and j["n_gpus"] == 1 and j["steps"] == 1
     assert j["metric"].startswith("RFF posterior-sample candidate*samples/s") and j["unit"] == "candidate*samples/s"
     assert j["higher_is_better"] is True and j["value"] > 0 and j["dtype"] == "f64"
-    assert j["config"]["workload"].startswith("c2") and j["config"]["N_per_gpu"] == 1 << 20
+    # the default workload is the largest single-GPU configuration (c3); `config` is exactly the GPU arm's dict
+    assert j["config"] == {"workload": j["config"]["workload"], "N_total": 1 << 24, "d": 6, "D": 4096, "S": 256}
+    assert j["config"]["workload"].startswith("c3") and j["scaling"] == "strong"
     cb = j["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -3,9 +3,9 @@
 ``I`` (pes.py:92-123) draws one sample matrix at [x_star; chi] and evaluates the eps-smoothed MI; the
 Monte-Carlo body (pes.py:44-89, 108-123) runs in ``tkbo_mpes_topk`` (mode TKBO_MPES_PES).  ``I_batch``
 (pes.py:126-132) is a Python loop over ``I`` in the reference, i.e. one independent sample matrix per query;
-that remains the behaviour for a model that only offers ``predict_f_samples``.  With ``joint=True`` (default
-when the model can sample on the device) all queries share one joint draw at [x_star; chi_1; ...; chi_Q] and
-are scored by a single kernel launch — the same estimator, without 3000 tiny launches per BO iteration.
+that is the default here too.  ``joint=True`` (opt-in; needs a model with ``predict_f_samples_device`` or
+``rff_features``) lets all queries share one joint RFF draw at [x_star; chi_1; ...; chi_Q] scored by a single kernel
+launch — the same estimator without 3000 tiny launches per BO iteration, but not the reference's sampling scheme.
 """
 from __future__ import annotations
 
@@ -41,7 +41,7 @@ def I_batch(chi_batch, x_star, model, *, num_samples=1000, joint=None, device=No
     Q, C, d = chi_batch.shape
     M = x_star.shape[0]
     if joint is None:
-        joint = hasattr(model, "predict_f_samples_device") or rff_features is not None
+        joint = rff_features is not None               # reference semantics unless the caller asks for the joint draw
     if not joint:
         return np.array([float(I(chi, x_star, model, num_samples=num_samples, device=device)) for chi in chi_batch])
     dev = _common.device_of(device)
@@ -53,21 +53,59 @@ def I_batch(chi_batch, x_star, model, *, num_samples=1000, joint=None, device=No
     return _common.mpes_from_device_samples(fchi, fstar, 1, nat.MPES_PES).cpu().numpy()
 
 
-def sample_maximizers_discrete(model, count, data, batch_size=1000, *, D=1024, device=None):
-    """Grid-argmax maximiser sampling (signature of pes.py:24-41).  The reference draws exact GP samples in
-    independent 1000-point batches; here the ``count`` samples are RFF posterior draws evaluated on ALL of
-    ``data`` by the fused kernel, argmax'd per sample (``batch_size`` is accepted and unused).
-    -> (count, input_dims) CPU float64 tensor."""
-    from .. import fourier_features as ff
-    basis = ff.SharedBasis.sample(model.Z if hasattr(model, "Z") else to_numpy(model.inducing_variable.Z), model, D=D,
-                                  count=count, device=device)
-    return basis.maximizers(data)
+def _argmax_rows_device(samples, dev):
+    """Per-row arg max (lowest index on ties, np.argmax semantics) of a (count, num_data) matrix on the GPU."""
+    torch = nat.require_cuda()
+    smp = _common.as_f32_device(samples, dev)
+    count, num_data = smp.shape
+    arg = torch.empty(count, dtype=torch.int32, device=dev)
+    nat.check(nat.lib().tkbo_argmax_rows(nat.handle(dev.index), nat.ptr(smp), count, num_data, nat.ptr(arg),
+                                         nat.current_stream_ptr(dev)), "tkbo_argmax_rows")
+    return arg.cpu().numpy().astype(np.int64)
 
 
-def sample_maximizers_simple(model, count, num_discrete_points, *, D=1024, device=None):
-    """Grid-argmax maximiser sampling on ``num_discrete_points`` points of [0, 1] -> (count, 1).     [pes.py:9-21]"""
+def sample_maximizers_discrete(model, count, data, batch_size=1000, *, rff_features=None, device=None, return_info=False):
+    """Grid-argmax maximiser sampling.                                                              [pes.py:24-41]
+
+    Default = the reference's scheme: ``model.predict_f_samples(data[first:last], count)`` for every FULL batch of
+    ``batch_size`` points (independent joint draws per batch; rows beyond the last full batch keep the value 0, as
+    ``range(num_data // batch_size)`` leaves them), then the per-sample arg max over all ``num_data`` columns
+    (``tkbo_argmax_rows``) and ``np.take`` -> (count, input_dims) CPU float64 tensor.
+
+    ``rff_features=D`` (opt-in) instead draws ``count`` RFF posterior samples on ONE shared basis and evaluates them on
+    all of ``data`` with the fused argmax kernel (``batch_size`` is then unused): a different sampler of the same
+    posterior that scales to millions of points; ``return_info`` also returns the basis and the indices."""
+    import torch
+    data_np = to_numpy(data)
+    dev = _common.device_of(device)
+    if rff_features is not None:
+        from .. import fourier_features as ff
+        Z = model.Z if hasattr(model, "Z") else to_numpy(model.inducing_variable.Z)
+        basis = ff.SharedBasis.sample(Z, model, D=int(rff_features), count=count, device=dev)
+        val, idx = basis.argmax(data_np.astype(np.float32))
+        out = torch.from_numpy(np.take(data_np, idx.cpu().numpy(), axis=0))
+        return (out, {"basis": basis, "indices": idx.cpu(), "values": val.cpu()}) if return_info else out
+    num_data = data_np.shape[0]
+    samples = torch.zeros((count, num_data), dtype=torch.float32, device=dev)            # pes.py:33
+    for i in range(num_data // batch_size):                                             # pes.py:35-38
+        first, last = i * batch_size, (i + 1) * batch_size
+        fs = model.predict_f_samples(data_np[first:last], count)
+        samples[:, first:last] = _common.as_f32_device(fs, dev).reshape(count, batch_size)
+    samples_argmax = _argmax_rows_device(samples, dev)                                  # pes.py:40
+    out = torch.from_numpy(np.take(data_np, samples_argmax, axis=0))                    # pes.py:41
+    return (out, {"indices": torch.from_numpy(samples_argmax)}) if return_info else out
+
+
+def sample_maximizers_simple(model, count, num_discrete_points, *, rff_features=None, device=None):
+    """Grid-argmax maximiser sampling on ``num_discrete_points`` points of [0, 1] -> (count, 1).     [pes.py:9-21]
+    One joint draw ``model.predict_f_samples(xx, count)`` at all grid points (no batching in the reference)."""
+    import torch
     xx = np.linspace(0.0, 1.0, num_discrete_points).reshape(num_discrete_points, 1)
-    return sample_maximizers_discrete(model, count, xx, D=D, device=device)
+    if rff_features is not None:
+        return sample_maximizers_discrete(model, count, xx, rff_features=rff_features, device=device)
+    dev = _common.device_of(device)
+    samples = _common.as_f32_device(model.predict_f_samples(xx, count), dev).reshape(count, num_discrete_points)
+    return torch.from_numpy(np.take(xx, _argmax_rows_device(samples, dev))[:, None])     # pes.py:20-21
 
 
 # ---- the building blocks of I (pes.py:44-89): kept for API parity, plain torch float64 on the tensors' device; the

@@ -19,13 +19,14 @@ int basis_destroy(tkbo_handle_t h, tkbo_basis_t bs);
 int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b, const double* Theta, int transposed,
               cudaStream_t stream);
 int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg);
-int rff_argmax_streamed(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t rows_per_chunk,
-                        unsigned int* ready_flag, float* out_val, int64_t* out_idx, cudaStream_t stream);
+int rff_argmax_streamed(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, int64_t rows_per_chunk,
+                        unsigned int* ready_flag, void* const* peer_bufs, int world, int rank, uint64_t epoch,
+                        float* out_val, int64_t* out_idx, cudaStream_t stream);
 size_t peer_buffer_words(int world, int S);
 int peer_push_keys(tkbo_handle_t h, const int64_t* keys, int S, void* const* peer_bufs, int world, int rank, uint64_t epoch,
                    cudaStream_t stream);
 int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs,
-                    int world, int rank, uint64_t epoch, cudaStream_t stream);
+                    int world, int rank, uint64_t epoch, float* out_val, int64_t* out_idx, cudaStream_t stream);
 int merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int S, uint64_t epoch, float* out_val, int64_t* out_idx,
                     cudaStream_t stream);
 int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, float* out_val,
@@ -152,6 +153,16 @@ int tkbo_create(tkbo_handle_t* out, int device) {
     set_error(std::string("cudaMalloc (handle): ") + cudaGetErrorString(e));
     return TKBO_ERR_NOMEM;
   }
+  if (cudaHostAlloc(&h->peer_status_host, sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
+    *h->peer_status_host = 0u;
+    if (cudaHostGetDevicePointer(&h->peer_status_dev, h->peer_status_host, 0) != cudaSuccess) h->peer_status_dev = nullptr;
+  }
+  // per-call scratch comes from cudaMallocAsync: keep freed blocks in the pool instead of returning them at every sync
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   cudaSetDevice(prev);
   *out = h;
   return TKBO_OK;
@@ -163,8 +174,7 @@ int tkbo_destroy(tkbo_handle_t h) {
     DeviceGuard g(h);
     host_path_release(h);
     cudaFree(h->done_counter);
-    cudaFree(h->mpes_scratch);
-    cudaFree(h->mpes_parts);
+    if (h->peer_status_host) cudaFreeHost(h->peer_status_host);
   }
   delete h;
   return TKBO_OK;
@@ -245,9 +255,17 @@ int64_t tkbo_peer_buffer_bytes(int world, int S) {
   return static_cast<int64_t>(peer_buffer_words(world, S) * sizeof(unsigned long long));
 }
 int tkbo_rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t basis, const float* X, int64_t N, int64_t idx_offset,
-                         void* const* peer_bufs, int world, int rank, uint64_t epoch, void* stream) {
+                         void* const* peer_bufs, int world, int rank, uint64_t epoch, float* out_val, int64_t* out_idx,
+                         void* stream) {
   TKBO_ENTER(h);
-  return rff_argmax_peer(h, basis, X, N, idx_offset, peer_bufs, world, rank, epoch, as_stream(stream));
+  return rff_argmax_peer(h, basis, X, N, idx_offset, peer_bufs, world, rank, epoch, out_val, out_idx, as_stream(stream));
+}
+int64_t tkbo_peer_status(tkbo_handle_t h) {
+  if (!h) return TKBO_ERR_INVALID;
+  if (!h->peer_status_host) return 0;
+  const unsigned int v = *reinterpret_cast<volatile unsigned int*>(h->peer_status_host);
+  if (v != 0u) *reinterpret_cast<volatile unsigned int*>(h->peer_status_host) = 0u;
+  return static_cast<int64_t>(v);
 }
 int tkbo_peer_push_keys(tkbo_handle_t h, const int64_t* keys, int S, void* const* peer_bufs, int world, int rank,
                         uint64_t epoch, void* stream) {
@@ -260,9 +278,77 @@ int tkbo_merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int 
   return merge_peer_keys(h, local_buf, world, S, epoch, out_val, out_idx, as_stream(stream));
 }
 
-int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
-                         const float* X, int64_t N, float* out_val, int64_t* out_idx) {
-  TKBO_ENTER(h);
+}  // extern "C"
+
+// One attempt of the host-buffer path.  streamed: the launch goes out right after the basis is prepared and consumes the
+// candidate chunks while their copies land; otherwise every copy is queued first and the launch waits for them (what a
+// tool that serialises kernels against copies needs, and the automatic retry after a streamed attempt that timed out).
+// *chunk_lost = 1 when the kernel gave up waiting for a chunk.
+static int host_argmax_attempt(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
+                               const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs, int world, int rank,
+                               uint64_t epoch, bool streamed, float* out_val, int64_t* out_idx, int* chunk_lost) {
+  auto& hp = h->host;
+  *chunk_lost = 0;
+  const size_t out_bytes = static_cast<size_t>(S) * 12 + 8;
+  long long* didx = reinterpret_cast<long long*>(hp.dout);
+  float* dval = reinterpret_cast<float*>(hp.dout + static_cast<size_t>(S) * 8);
+  unsigned int* dflag = reinterpret_cast<unsigned int*>(hp.dout + static_cast<size_t>(S) * 12);
+  // chunks of whole 128-candidate tiles, about 2^16 candidates each (a few hundred KB: ~10 us of PCIe time before the
+  // kernel can start on the first one)
+  int chunks = static_cast<int>(std::min<int64_t>(kHostChunksMax, std::max<int64_t>(1, N >> 16)));
+  const int64_t per = (((N + chunks - 1) / chunks) + 127) / 128 * 128;
+  chunks = static_cast<int>((N + per - 1) / per);
+  cudaStream_t sx = hp.exec_stream, sc = hp.copy_stream;
+  double* dW = hp.dbasis;
+  double* db = dW + static_cast<size_t>(D) * d;
+  double* dT = db + D;
+  auto copy_chunk = [&](int k) -> cudaError_t {
+    const int64_t n0 = static_cast<int64_t>(k) * per, nk = std::min<int64_t>(per, N - n0);
+    cudaError_t e = cudaMemcpyAsync(hp.dX + n0 * d, X + n0 * d, sizeof(float) * nk * d, cudaMemcpyHostToDevice, sc);
+    // stream order: the counter moves only after the chunk's bytes are in device memory
+    return e ? e : cudaMemcpyAsync(dflag, hp.hflag + k, sizeof(unsigned int), cudaMemcpyHostToDevice, sc);
+  };
+  TKBO_CUDA_CHECK(cudaMemsetAsync(dflag, 0, 2 * sizeof(unsigned int), sx));
+  TKBO_CUDA_CHECK(cudaEventRecord(hp.flag_reset, sx));
+  TKBO_CUDA_CHECK(cudaStreamWaitEvent(sc, hp.flag_reset, 0));
+  // the first chunk goes out before the basis so that the copy engine is busy while the basis is prepared; the rest is
+  // queued after the kernel launch, so that pageable (host-synchronous) candidate copies do not delay the launch
+  TKBO_CUDA_CHECK(copy_chunk(0));
+  if (!streamed) {
+    for (int k = 1; k < chunks; ++k) TKBO_CUDA_CHECK(copy_chunk(k));
+    TKBO_CUDA_CHECK(cudaEventRecord(hp.flag_reset, sc));
+    TKBO_CUDA_CHECK(cudaStreamWaitEvent(sx, hp.flag_reset, 0));
+  }
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(dW, W, sizeof(double) * D * d, cudaMemcpyHostToDevice, sx));
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(db, b, sizeof(double) * D, cudaMemcpyHostToDevice, sx));
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(dT, Theta, sizeof(double) * D * S, cudaMemcpyHostToDevice, sx));
+  int rc = basis_set(h, hp.basis, dW, db, dT, 0, sx);
+  if (rc == TKBO_OK)
+    rc = rff_argmax_streamed(h, hp.basis, hp.dX, N, idx_offset, per, dflag, peer_bufs, world, rank, epoch, dval,
+                             reinterpret_cast<int64_t*>(didx), sx);
+  cudaError_t ce = cudaSuccess;
+  for (int k = 1; streamed && k < chunks && ce == cudaSuccess; ++k) ce = copy_chunk(k);
+  if (rc != TKBO_OK || ce != cudaSuccess) {
+    // a launched kernel may be waiting for chunks that were never queued: let its bounded wait expire rather than leave it
+    cudaStreamSynchronize(sc); cudaStreamSynchronize(sx);
+    if (rc == TKBO_OK) { set_error(std::string("candidate copy: ") + cudaGetErrorString(ce)); rc = TKBO_ERR_CUDA; }
+    return rc;
+  }
+  TKBO_CUDA_CHECK(cudaMemcpyAsync(hp.hout, hp.dout, out_bytes, cudaMemcpyDeviceToHost, sx));
+  TKBO_CUDA_CHECK(cudaStreamSynchronize(sx));
+  TKBO_CUDA_CHECK(cudaStreamSynchronize(sc));
+  memcpy(out_idx, hp.hout, static_cast<size_t>(S) * 8);
+  memcpy(out_val, hp.hout + static_cast<size_t>(S) * 8, static_cast<size_t>(S) * 4);
+  unsigned int report;
+  memcpy(&report, hp.hout + static_cast<size_t>(S) * 12 + 4, sizeof(report));
+  *chunk_lost = report != 0u;
+  return TKBO_OK;
+}
+
+// Shared body of tkbo_rff_argmax_host / tkbo_rff_argmax_host_peer (peer_bufs == nullptr: single rank).
+static int host_argmax(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
+                       const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs, int world, int rank,
+                       uint64_t epoch, float* out_val, int64_t* out_idx) {
   if (!W || !b || !Theta || !X || !out_val || !out_idx) { set_error("null pointer"); return TKBO_ERR_INVALID; }
   if (N < 1) { set_error("N must be >= 1"); return TKBO_ERR_INVALID; }
   if (N >= (int64_t(1) << 32) - 256) { set_error("N must be below 2^32 - 256"); return TKBO_ERR_INVALID; }
@@ -282,83 +368,67 @@ int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, cons
   }
   const size_t nb = static_cast<size_t>(D) * d + D + static_cast<size_t>(D) * S;
   if (hp.dbasis_doubles < nb) {
-    cudaFree(hp.dbasis); hp.dbasis = nullptr; hp.dbasis_doubles = 0;
+    if (hp.dbasis) TKBO_CUDA_CHECK(cudaFree(hp.dbasis));
+    hp.dbasis = nullptr; hp.dbasis_doubles = 0;
     TKBO_CUDA_CHECK(cudaMalloc(&hp.dbasis, nb * sizeof(double)));
     hp.dbasis_doubles = nb;
   }
   const size_t out_bytes = static_cast<size_t>(S) * 12 + 8;
   if (hp.out_S < S) {
-    cudaFree(hp.dout); hp.dout = nullptr;
-    if (hp.hout) { cudaFreeHost(hp.hout); hp.hout = nullptr; }
+    if (hp.dout) TKBO_CUDA_CHECK(cudaFree(hp.dout));
+    hp.dout = nullptr;
+    if (hp.hout) { TKBO_CUDA_CHECK(cudaFreeHost(hp.hout)); hp.hout = nullptr; }
     hp.out_S = 0;
     TKBO_CUDA_CHECK(cudaMalloc(&hp.dout, out_bytes));
     TKBO_CUDA_CHECK(cudaHostAlloc(&hp.hout, out_bytes, cudaHostAllocDefault));
     hp.out_S = S;
   }
-  long long* didx = reinterpret_cast<long long*>(hp.dout);
-  float* dval = reinterpret_cast<float*>(hp.dout + static_cast<size_t>(S) * 8);
-  unsigned int* dflag = reinterpret_cast<unsigned int*>(hp.dout + static_cast<size_t>(S) * 12);
-  // chunks of whole 128-candidate tiles, about 2^16 candidates each (a few hundred KB: ~10 us of PCIe time before the
-  // kernel can start on the first one)
-  int chunks = static_cast<int>(std::min<int64_t>(kHostChunksMax, std::max<int64_t>(1, N >> 16)));
-  const int64_t per = (((N + chunks - 1) / chunks) + 127) / 128 * 128;
-  chunks = static_cast<int>((N + per - 1) / per);
   if (hp.dX_floats < static_cast<size_t>(N) * d) {
-    cudaFree(hp.dX); hp.dX = nullptr; hp.dX_floats = 0;
+    if (hp.dX) TKBO_CUDA_CHECK(cudaFree(hp.dX));
+    hp.dX = nullptr; hp.dX_floats = 0;
     TKBO_CUDA_CHECK(cudaMalloc(&hp.dX, sizeof(float) * N * d));
     hp.dX_floats = static_cast<size_t>(N) * d;
   }
-  cudaStream_t sx = hp.exec_stream, sc = hp.copy_stream;
-  double* dW = hp.dbasis;
-  double* db = dW + static_cast<size_t>(D) * d;
-  double* dT = db + D;
-  auto copy_chunk = [&](int k) -> cudaError_t {
-    const int64_t n0 = static_cast<int64_t>(k) * per, nk = std::min<int64_t>(per, N - n0);
-    cudaError_t e = cudaMemcpyAsync(hp.dX + n0 * d, X + n0 * d, sizeof(float) * nk * d, cudaMemcpyHostToDevice, sc);
-    // stream order: the counter moves only after the chunk's bytes are in device memory
-    return e ? e : cudaMemcpyAsync(dflag, hp.hflag + k, sizeof(unsigned int), cudaMemcpyHostToDevice, sc);
-  };
-  TKBO_CUDA_CHECK(cudaMemsetAsync(dflag, 0, 2 * sizeof(unsigned int), sx));
-  TKBO_CUDA_CHECK(cudaEventRecord(hp.flag_reset, sx));
-  TKBO_CUDA_CHECK(cudaStreamWaitEvent(sc, hp.flag_reset, 0));
-  // the first chunk goes out before the basis so that the copy engine is busy while the basis is prepared; the rest is
-  // queued after the kernel launch, so that pageable (host-synchronous) candidate copies do not delay the launch
-  TKBO_CUDA_CHECK(copy_chunk(0));
-  // Tools that serialise kernels against copies (ncu, compute-sanitizer) would leave the kernel waiting for chunks whose
-  // copies they hold back until its bounded wait expires: TKBO_HOST_STREAMED=0 queues every copy first and launches behind them.
+  // Streaming needs copies that run WHILE the kernel runs.  CUDA_LAUNCH_BLOCKING=1 makes every launch synchronous (the
+  // later chunks would never be queued), profilers / sanitizers serialise kernels against copies: TKBO_HOST_STREAMED=0
+  // (or CUDA_LAUNCH_BLOCKING) selects the copy-everything-first ordering up front, and a streamed attempt whose kernel
+  // reports a lost chunk (one bounded wait of ~10 s in total, rff_fused.cuh) is repeated once in that ordering instead of
+  // failing.  A peer-merged launch is never repeated: its keys of this epoch have already been delivered.
   const char* streamed_env = getenv("TKBO_HOST_STREAMED");
-  const bool streamed = !(streamed_env != nullptr && atoi(streamed_env) == 0);
-  if (!streamed) {
-    for (int k = 1; k < chunks; ++k) TKBO_CUDA_CHECK(copy_chunk(k));
-    TKBO_CUDA_CHECK(cudaEventRecord(hp.flag_reset, sc));
-    TKBO_CUDA_CHECK(cudaStreamWaitEvent(sx, hp.flag_reset, 0));
-  }
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(dW, W, sizeof(double) * D * d, cudaMemcpyHostToDevice, sx));
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(db, b, sizeof(double) * D, cudaMemcpyHostToDevice, sx));
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(dT, Theta, sizeof(double) * D * S, cudaMemcpyHostToDevice, sx));
-  int rc = basis_set(h, hp.basis, dW, db, dT, 0, sx);
-  if (rc == TKBO_OK)
-    rc = rff_argmax_streamed(h, hp.basis, hp.dX, N, per, dflag, dval, reinterpret_cast<int64_t*>(didx), sx);
-  cudaError_t ce = cudaSuccess;
-  for (int k = 1; streamed && k < chunks && ce == cudaSuccess; ++k) ce = copy_chunk(k);
-  if (rc != TKBO_OK || ce != cudaSuccess) {
-    // a launched kernel may be waiting for chunks that were never queued: let its bounded wait expire rather than leave it
-    cudaStreamSynchronize(sc); cudaStreamSynchronize(sx);
-    if (rc == TKBO_OK) { set_error(std::string("candidate copy: ") + cudaGetErrorString(ce)); rc = TKBO_ERR_CUDA; }
-    return rc;
-  }
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(hp.hout, hp.dout, out_bytes, cudaMemcpyDeviceToHost, sx));
-  TKBO_CUDA_CHECK(cudaStreamSynchronize(sx));
-  TKBO_CUDA_CHECK(cudaStreamSynchronize(sc));
-  memcpy(out_idx, hp.hout, static_cast<size_t>(S) * 8);
-  memcpy(out_val, hp.hout + static_cast<size_t>(S) * 8, static_cast<size_t>(S) * 4);
-  unsigned int report;
-  memcpy(&report, hp.hout + static_cast<size_t>(S) * 12 + 4, sizeof(report));
-  if (report != 0u) {
+  const char* blocking_env = getenv("CUDA_LAUNCH_BLOCKING");
+  bool streamed = !(streamed_env != nullptr && atoi(streamed_env) == 0) && !(blocking_env != nullptr && atoi(blocking_env) != 0);
+  int lost = 0;
+  int rc = host_argmax_attempt(h, W, b, Theta, D, d, S, X, N, idx_offset, peer_bufs, world, rank, epoch, streamed, out_val,
+                               out_idx, &lost);
+  if (rc == TKBO_OK && lost && streamed && peer_bufs == nullptr)
+    rc = host_argmax_attempt(h, W, b, Theta, D, d, S, X, N, idx_offset, peer_bufs, world, rank, epoch, false, out_val,
+                             out_idx, &lost);
+  if (rc != TKBO_OK) return rc;
+  if (lost) {
     set_error("tkbo_rff_argmax_host: a candidate chunk did not reach the device within the kernel's wait limit");
     return TKBO_ERR_CUDA;
   }
+  if (peer_bufs != nullptr && tkbo_peer_status(h) != 0) {
+    set_error("tkbo_rff_argmax_host_peer: a peer rank did not deliver its keys within the merge's wait limit (~10 s)");
+    return TKBO_ERR_CUDA;
+  }
   return TKBO_OK;
+}
+
+extern "C" {
+
+int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
+                         const float* X, int64_t N, float* out_val, int64_t* out_idx) {
+  TKBO_ENTER(h);
+  return host_argmax(h, W, b, Theta, D, d, S, X, N, 0, nullptr, 0, 0, 0, out_val, out_idx);
+}
+
+int tkbo_rff_argmax_host_peer(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
+                              const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs, int world, int rank,
+                              uint64_t epoch, float* out_val, int64_t* out_idx) {
+  TKBO_ENTER(h);
+  if (!peer_bufs) { set_error("null peer buffers"); return TKBO_ERR_INVALID; }
+  return host_argmax(h, W, b, Theta, D, d, S, X, N, idx_offset, peer_bufs, world, rank, epoch, out_val, out_idx);
 }
 
 int tkbo_rff_eval_batched(tkbo_handle_t h, const double* X, const double* W, const double* b, const double* theta,

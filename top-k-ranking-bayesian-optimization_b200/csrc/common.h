@@ -38,11 +38,12 @@ struct tkbo_handle_s {
   int64_t launches = 0;
   unsigned int* done_counter = nullptr;   // device, zero between calls
   void* encode_tiled = nullptr;           // cuTensorMapEncodeTiled entry point
-  // scratch for the MPES kernel (grown on demand)
-  void* mpes_scratch = nullptr;
-  size_t mpes_scratch_bytes = 0;
-  void* mpes_parts = nullptr;             // per-chunk partial sums of the all-permutations kernel
-  size_t mpes_parts_bytes = 0;
+  // (K2 scratch is allocated per call from the stream-ordered pool; tkbo_create raises the pool's release threshold so
+  // that steady-state calls reuse the same blocks without going back to the driver)
+  // merge over peer memory: one host-mapped word that a merge (kernel tail or tkbo_merge_peer_keys) sets to the epoch it
+  // gave up on; tkbo_peer_status() reads and clears it
+  unsigned int* peer_status_host = nullptr;
+  unsigned int* peer_status_dev = nullptr;
   // persistent state of the host-buffer entry point (tkbo_rff_argmax_host): basis + device staging, reused across calls
   struct HostPath {
     tkbo_basis_s* basis = nullptr;

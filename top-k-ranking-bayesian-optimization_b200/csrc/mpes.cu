@@ -13,6 +13,8 @@
 #include <cuda_fp16.h>
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -113,7 +115,7 @@ __device__ __forceinline__ void subset_reciprocals(const float (&e)[C], float (&
       s = first ? e[c] : s + e[c];
       first = false;
     }
-    rs[m] = fast_rcp(s);
+    rs[m] = fast_rcp(fmaxf(s, 1.17549435e-38f));          // all remaining choices flushed to zero: 0 * 2^126 = 0, not NaN
   }
 }
 
@@ -153,33 +155,79 @@ __host__ __device__ constexpr int mpes_warp_smem_bytes(int C, int P) {
   return ((kRing * 32 * C * 4 + P * 32 * 4 + kRing * 8 + 127) / 128) * 128;
 }
 
+// Accurate log(a) for the group fold.  MI is a difference of entropies of size ~log P with a result of 1e-9 .. 1e-1
+// (the eps-smoothed pes.I of a query that cannot move the maximiser is ~1e-9), so the per-group sums
+// sum_z a_z log a_z  need ~1e-12 relative accuracy; MUFU.LG2 (2^-22) is far short and a float64 log() per value would
+// cost a fifth of the kernel.  Instead: a = 2^E m, m in [1, 2); k = top 7 mantissa bits; r_k ~ 1 / (1 + (k + 1/2)/128)
+// with 9 significant bits; p = fl(m r_k), e = fma(m, r_k, -p) (the exact product error), xh = p - 1 (exact, |xh| < 0.006):
+//     log m = -log r_k (float64 table) + xh + [e (1 - xh) + xh^2 (-1/2 + xh/3 - xh^2/4)]
+// where the bracket is below 2e-5, so float32 is enough for it; everything else is added in float64.  ~20 instructions
+// per value, 4 of them on the float64 pipe; absolute error ~1e-12.
+struct LogTable {
+  float r[128];
+  double t[128];      // -log(r[k])
+};
+__device__ __forceinline__ void log_table_fill(LogTable& tab, int tid) {
+  if (tid < 128) {
+    const float r0 = 1.f / (1.f + (static_cast<float>(tid) + 0.5f) * (1.f / 128.f));
+    const float r = __uint_as_float(__float_as_uint(r0) & 0xFFFFC000u);       // 9 explicit mantissa bits
+    tab.r[tid] = r;
+    tab.t[tid] = -log(static_cast<double>(r));
+  }
+}
+// log(a) for a normal positive float a
+__device__ __forceinline__ double table_log(const LogTable& tab, float a) {
+  const uint32_t bits = __float_as_uint(a);
+  const int E = static_cast<int>(bits >> 23) - 127;
+  const uint32_t k = (bits >> 16) & 127u;
+  const float m = __uint_as_float((bits & 0x007FFFFFu) | 0x3F800000u);
+  const float r = tab.r[k];
+  const float p = __fmul_rn(m, r);
+  const float e = __fmaf_rn(m, r, -p);
+  const float xh = p - 1.f;
+  const float q = fmaf(xh, fmaf(xh, -0.25f, 0.33333334f), -0.5f);
+  const float rest = fmaf(xh * xh, q, fmaf(-e, xh, e));
+  return fma(static_cast<double>(E), 0.6931471805599453, tab.t[k] + (static_cast<double>(xh) + static_cast<double>(rest)));
+}
+
 // Work unit = (tile of 32 queries, chunk j of the maximiser groups), fetched dynamically from a global counter: a
 // whole tile (all S samples) is ~0.5 ms of work for one warp, far too coarse for a few thousand persistent warps.
 // For its chunk a unit produces
 //     A_j  = sum_{m in j} p_m sum_z c_zm log c_zm      (t1buf[j, q], float64)
 //     tot_j[z] = sum_{m in j} sum_{s in m} P_s(z)       (totbuf[j, z, q], float32)
-// and mpes_finish_kernel assembles  MI = sum_j A_j - sum_z p_z log p_z,  p_z = (sum_j tot_j[z] + M eps) / S.
-// Per group the entropy-like sum over the P orderings runs in float32 (two interleaved partial sums, logf), the
-// weighting by p_m and the sum over groups in float64; measured |dMI| stays below 1e-6 absolute.
+// and the LAST unit of a tile to finish (tile_done counter, threadfence + atomic) assembles
+//     MI = sum_j A_j - sum_z p_z log p_z,  p_z = (sum_j tot_j[z] + M eps) / S                 (float64)
+// summing j in order, so the result does not depend on which unit came last.  J == 1 keeps everything in the unit.
+// Per group: a_z = acc_z + eps, c_zm = a_z cm with cm = 1 / (S p_m), hence
+//     p_m sum_z c log c = (1/S) (sum_z a_z log a_z + log(cm) sum_z a_z)
+// with the two sums over z in float64 (table_log above).
 template <int C, int K, bool STAGED>
 __global__ void __launch_bounds__(32 * kMpesWarps, 4)
 mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ order, const int* __restrict__ group_start,
                       const int* __restrict__ chunk_group, int J, int S, long long Q, long long Qpad, int M, int mode,
-                      int tile_begin, int tile_end, unsigned int* __restrict__ unit_counter, float* __restrict__ totbuf,
-                      double* __restrict__ t1buf) {
+                      int tile_begin, int tile_end, unsigned int* __restrict__ unit_counter,
+                      unsigned int* __restrict__ tile_done, float* __restrict__ totbuf, double* __restrict__ t1buf,
+                      double* __restrict__ out_mi) {
   constexpr int P = perm_count(C, K);
   constexpr float kLog2e = 1.4426950408889634f;
+  // exponent offset: e_c = 2^((f_c - max) log2e + 120), so that choices up to 246 binades (170 nats) below the best one stay
+  // normal floats (the sums stay below 2^127, every stage factor e * rs is scale free); rank_pes.py:166 renormalises per
+  // stage, which this reproduces as long as the not-yet-ranked choices do not ALL flush to zero
+  constexpr float kExpBias = 120.f;
+  __shared__ LogTable logtab;
   // dynamic shared memory, one private slice per warp: ring | tot | mbarriers (see mpes_warp_smem_bytes)
   extern __shared__ __align__(128) unsigned char mpes_smem[];
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;                        // warps never synchronise with each other
+  const int wib = threadIdx.x >> 5;                        // after the table fill, warps never synchronise with each other
+  log_table_fill(logtab, threadIdx.x);
+  __syncthreads();
   unsigned char* slice = mpes_smem + static_cast<size_t>(wib) * mpes_warp_smem_bytes(C, P);
   float (*ring)[32 * C] = reinterpret_cast<float (*)[32 * C]>(slice);
   float (*tot)[32] = reinterpret_cast<float (*)[32]>(slice + kRing * 32 * C * 4);      // sum over the chunk's groups of acc
   uint64_t* full = reinterpret_cast<uint64_t*>(tot + P);
   const double invS = 1.0 / static_cast<double>(S);
   const double eps = (mode == TKBO_MPES_PES) ? kPesEps : 0.0;
-  const float epsf = static_cast<float>(eps);
+  const double meps = (mode == TKBO_MPES_PES) ? M * kPesEps : 0.0;
   const long long rowstride = Q * C;
   if constexpr (STAGED) {
     if (lane == 0)
@@ -253,7 +301,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
         float mx = f[0];
 #pragma unroll
         for (int c = 1; c < C; ++c) mx = fmaxf(mx, f[c]);
-        const float mxs = mx * kLog2e;
+        const float mxs = fmaf(mx, kLog2e, -kExpBias);
         float e[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) e[c] = fast_ex2(fmaf(f[c], kLog2e, -mxs));
@@ -270,44 +318,65 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
         int leaf = 0;
         PermWalk<C, K, 0>::run(e, rs, 0u, 1.f, acc, leaf);
       }
-      // fold group m:  A += p_m sum_z c_zm log c_zm  with c_zm = p(z | m)
+      // fold group m:  A += p_m sum_z c_zm log c_zm  with c_zm = p(z | m) = (acc_z + eps) cm
       const double pm = (mode == TKBO_MPES_PES)
                             ? (static_cast<double>(cnt) + kPesEps) / (static_cast<double>(S) + M * kPesEps)
                             : static_cast<double>(cnt) * invS;
-      const float cm = static_cast<float>(invS / pm);              // (acc + eps) * cm = p(z | m)
-      float tg0 = 0.f, tg1 = 0.f;
+      const double lcm = log(invS / pm);
+      double s1a = 0.0, s1b = 0.0, s0 = 0.0;              // two interleaved chains for the float64 pipe
 #pragma unroll
       for (int z = 0; z < P; ++z) {
-        const float c = (acc[z] + epsf) * cm;
-        const float t = (c > 0.f) ? c * __logf(c) : 0.f;          // lg2.approx: ~2e-7 relative
-        if (z & 1) tg1 += t; else tg0 += t;
+        // a = acc + eps in float64 (eps = 1e-7 is below float32 resolution of a sum of ~S/M probabilities, and pes.I of
+        // an uninformative query consists of nothing but these eps terms): log a = log(fl32(a)) + (a - fl32(a)) / fl32(a)
+        const double ad = static_cast<double>(acc[z]) + eps;
+        const float af = static_cast<float>(ad);
+        if (af >= 1e-30f) {                                // below: a log a < 7e-29, and no denormal handling needed
+          double la = table_log(logtab, af);
+          if (mode == TKBO_MPES_PES) la += (ad - static_cast<double>(af)) * static_cast<double>(fast_rcp(af));
+          const double t = ad * la;
+          if (z & 1) s1b += t; else s1a += t;
+          s0 += ad;
+        }
         tot[z][lane] += acc[z];
         acc[z] = 0.f;
       }
-      A += pm * (static_cast<double>(tg0) + static_cast<double>(tg1));
+      A += invS * ((s1a + s1b) + lcm * s0);
+    }
+    if (J == 1) {
+      // the unit saw every group: finish here, nothing goes through global memory
+      double mi = A;
+#pragma unroll
+      for (int z = 0; z < P; ++z) {
+        const double pz = (static_cast<double>(tot[z][lane]) + meps) * invS;
+        if (pz > 0.0) mi -= pz * log(pz);
+      }
+      if (valid) out_mi[q] = mi;
+      continue;
     }
 #pragma unroll
     for (int z = 0; z < P; ++z) totbuf[(static_cast<size_t>(j) * P + z) * Qpad + q] = tot[z][lane];
     t1buf[static_cast<size_t>(j) * Qpad + q] = A;
+    // last unit of the tile to get here assembles MI (release: partials before the counter; acquire: counter before reads)
+    __threadfence();
+    __syncwarp();
+    unsigned prev = 0;
+    if (lane == 0) prev = atomicAdd(tile_done + tile, 1u);
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev == static_cast<unsigned>(J - 1)) {
+      __threadfence();
+      double mi = 0.0;
+      for (int jj = 0; jj < J; ++jj) mi += __ldcg(t1buf + static_cast<size_t>(jj) * Qpad + q);
+#pragma unroll 4
+      for (int z = 0; z < P; ++z) {
+        double t = 0.0;
+        for (int jj = 0; jj < J; ++jj) t += static_cast<double>(__ldcg(totbuf + (static_cast<size_t>(jj) * P + z) * Qpad + q));
+        const double pz = (t + meps) * invS;
+        if (pz > 0.0) mi -= pz * log(pz);
+      }
+      if (valid) out_mi[q] = mi;
+      if (lane == 0) tile_done[tile] = 0u;               // ready for the next call that reuses the buffer
+    }
   }
-}
-
-// MI[q] = sum_j A_j[q] - sum_z p_z log p_z                                            (rank_pes.py:97-105, pes.py:115-123)
-__global__ void mpes_finish_kernel(const float* __restrict__ totbuf, const double* __restrict__ t1buf, int J, int P,
-                                   long long Q, long long Qpad, int S, int M, int mode, double* __restrict__ out_mi) {
-  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q >= Q) return;
-  const double invS = 1.0 / static_cast<double>(S);
-  const double meps = (mode == TKBO_MPES_PES) ? M * kPesEps : 0.0;
-  double mi = 0.0;
-  for (int j = 0; j < J; ++j) mi += t1buf[static_cast<size_t>(j) * Qpad + q];
-  for (int z = 0; z < P; ++z) {
-    double t = 0.0;
-    for (int j = 0; j < J; ++j) t += static_cast<double>(totbuf[(static_cast<size_t>(j) * P + z) * Qpad + q]);
-    const double pz = (t + meps) * invS;
-    if (pz > 0.0) mi -= pz * log(pz);
-  }
-  out_mi[q] = mi;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,7 +416,7 @@ mpes_table_kernel(const float* __restrict__ fchi, const int* __restrict__ order,
       float mx = fmine;
       for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));   // C <= 8
       mx = __shfl_sync(0xffffffffu, mx, 0);
-      const float emine = (lane < C) ? __expf(fmine - mx) : 0.f;
+      const float emine = (lane < C) ? __expf(fmine - mx + 80.f) : 0.f;   // recentred: choices down to e^-167 of the best stay normal
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
         const int p = lane + 32 * t;
@@ -364,7 +433,7 @@ mpes_table_kernel(const float* __restrict__ fchi, const int* __restrict__ order,
               if (!((used >> cc) & 1u)) rem += ev;
             }
             const float ec = __shfl_sync(0xffffffffu, emine, c);
-            prob *= ec / rem;
+            prob *= ec / fmaxf(rem, 1.17549435e-38f);
             used |= 1u << c;
           }
           if (act) acc[t] += prob;
@@ -502,14 +571,16 @@ __global__ void argmax_vec_kernel(const float* __restrict__ v, int n, long long*
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-// Partial results of the all-permutations kernel (one slab per sample chunk) and its two unit counters.
+// Partial results of the all-permutations kernel (one slab per sample chunk), its two unit counters and the per-tile
+// "units done" counters that elect the finishing unit.
 struct MpesParts {
   const int* chunk_group;   // [J + 1]
   int J;
   long long Qpad;           // queries rounded up to whole 32-query tiles
-  float* totbuf;            // [J, P, Qpad]
-  double* t1buf;            // [J, Qpad]
+  float* totbuf;            // [J, P, Qpad]   (J > 1 only)
+  double* t1buf;            // [J, Qpad]      (J > 1 only)
   unsigned int* counters;   // [2], zeroed before the launches
+  unsigned int* tile_done;  // [tiles], zeroed before the launches (J > 1 only)
 };
 
 template <int C, int K>
@@ -524,24 +595,21 @@ static void launch_all_perms(const float* fchi, const int* order, const int* gs,
   const int smem = kMpesWarps * mpes_warp_smem_bytes(C, P);
   cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaMemsetAsync(pt.counters, 0, 2 * sizeof(unsigned int), stream);
   if (staged_tiles > 0) {
     const int64_t units = staged_tiles * pt.J;
     const int grid = static_cast<int>(std::min<int64_t>(4 * sm_count, (units + kMpesWarps - 1) / kMpesWarps));
     mpes_all_perms_kernel<C, K, true><<<grid, threads, smem, stream>>>(fchi, order, gs, pt.chunk_group, pt.J, S, Q, pt.Qpad, M,
                                                                    mode, 0, static_cast<int>(staged_tiles), pt.counters,
-                                                                   pt.totbuf, pt.t1buf);
+                                                                   pt.tile_done, pt.totbuf, pt.t1buf, out);
   }
   if (staged_tiles < tiles) {
     const int64_t units = (tiles - staged_tiles) * pt.J;
     const int grid = static_cast<int>(std::min<int64_t>(4 * sm_count, (units + kMpesWarps - 1) / kMpesWarps));
     mpes_all_perms_kernel<C, K, false><<<grid, threads, smem, stream>>>(fchi, order, gs, pt.chunk_group, pt.J, S, Q, pt.Qpad, M,
                                                                     mode, static_cast<int>(staged_tiles),
-                                                                    static_cast<int>(tiles), pt.counters + 1, pt.totbuf,
-                                                                    pt.t1buf);
+                                                                    static_cast<int>(tiles), pt.counters + 1, pt.tile_done,
+                                                                    pt.totbuf, pt.t1buf, out);
   }
-  mpes_finish_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, stream>>>(pt.totbuf, pt.t1buf, pt.J, P, Q, pt.Qpad, S, M,
-                                                                            mode, out);
 }
 
 static bool dispatch_all_perms(int C, int K, const float* fchi, const int* order, const int* gs, int S, int64_t Q, int M,
@@ -579,6 +647,17 @@ static void full_table(int C, int k, std::vector<int>* out) {
   Rec::go(C, k, cur, used, out);
 }
 
+// Scratch of one call, allocated from the stream-ordered pool (cudaMallocAsync) so that calls on different streams or
+// threads never share buffers; freed on the same stream when the object goes out of scope.
+struct StreamScratch {
+  void* p = nullptr;
+  cudaStream_t stream;
+  explicit StreamScratch(cudaStream_t s) : stream(s) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, stream); }
+  ~StreamScratch() { if (p) cudaFreeAsync(p, stream); }
+};
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
 int mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, int S, int64_t Q, int C, int M,
               const int32_t* perms, int P, int k, int mode, double* out_mi, cudaStream_t stream) {
   TKBO_REQUIRE(h && fchi && fstar_argmax && out_mi, "null pointer");
@@ -586,40 +665,56 @@ int mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, i
   TKBO_REQUIRE(C >= 1 && C <= kGenMaxC && k >= 1 && k <= C, "need 1 <= k <= C <= 8");
   TKBO_REQUIRE(mode == TKBO_MPES_RANK || mode == TKBO_MPES_PES, "unknown mode");
   if (mode == TKBO_MPES_PES) TKBO_REQUIRE(k == 1 && perms == nullptr, "PES mode is top-1 with the implicit table");
-  const size_t need = sizeof(int) * (static_cast<size_t>(S) + M + 1) + sizeof(int) * kGenMaxP * kGenMaxC;
-  if (h->mpes_scratch_bytes < need) {
-    if (h->mpes_scratch) TKBO_CUDA_CHECK(cudaFree(h->mpes_scratch));
-    h->mpes_scratch = nullptr; h->mpes_scratch_bytes = 0;
-    TKBO_CUDA_CHECK(cudaMalloc(&h->mpes_scratch, need));
-    h->mpes_scratch_bytes = need;
-  }
-  int* order = static_cast<int*>(h->mpes_scratch);
-  int* gs = order + S;
-  int* dperm = gs + M + 1;
-  bool done = false;
-  if (perms == nullptr && has_all_perms_kernel(C, k)) {
-    // sample chunks: as many as keep the partial buffers below 256 MiB, at most kMaxChunks and one per group
-    const int Pn = perm_count(C, k);
-    MpesParts pt;
-    pt.Qpad = ((Q + 31) / 32) * 32;
-    const size_t per_chunk = static_cast<size_t>(pt.Qpad) * (static_cast<size_t>(Pn) * sizeof(float) + sizeof(double));
-    pt.J = static_cast<int>(std::max<size_t>(1, std::min<size_t>(std::min(kMaxChunks, M), (size_t(256) << 20) / per_chunk)));
-    const size_t need2 = per_chunk * pt.J + sizeof(int) * (kMaxChunks + 2) + 64;
-    if (h->mpes_parts_bytes < need2) {
-      if (h->mpes_parts) TKBO_CUDA_CHECK(cudaFree(h->mpes_parts));
-      h->mpes_parts = nullptr; h->mpes_parts_bytes = 0;
-      TKBO_CUDA_CHECK(cudaMalloc(&h->mpes_parts, need2));
-      h->mpes_parts_bytes = need2;
+  const bool fast = perms == nullptr && has_all_perms_kernel(C, k);
+  // layout of the call's scratch: order[S] | group_start[M + 1] | table[kGenMaxP * kGenMaxC] | chunk_group[kMaxChunks + 2] |
+  // counters[2] | tile_done[tiles] | t1buf[J, Qpad] f64 | totbuf[J, P, Qpad] f32
+  const int64_t tiles = (Q + 31) / 32;
+  MpesParts pt;
+  pt.Qpad = tiles * 32;
+  pt.J = 1;
+  const int Pn = fast ? perm_count(C, k) : 0;
+  size_t per_chunk = 0;
+  if (fast) {
+    // sample chunks: enough (tile, chunk) units for ~8 rounds of the persistent warps, at most kMaxChunks, one per
+    // maximiser, and partial buffers below 256 MiB; a large batch needs none (J = 1: no partial buffers at all)
+    per_chunk = static_cast<size_t>(pt.Qpad) * (static_cast<size_t>(Pn) * sizeof(float) + sizeof(double));
+    const int64_t warps = static_cast<int64_t>(h->sm_count) * 4 * kMpesWarps;
+    int64_t J = (8 * warps + tiles - 1) / tiles;
+    J = std::min<int64_t>(J, std::min(kMaxChunks, M));
+    J = std::min<int64_t>(J, static_cast<int64_t>((size_t(256) << 20) / per_chunk));
+    pt.J = static_cast<int>(std::max<int64_t>(1, J));
+    if (const char* env = getenv("TKBO_MPES_CHUNKS")) {
+      const int t = atoi(env);
+      if (t >= 1 && t <= std::min(kMaxChunks, M)) pt.J = t;
     }
-    pt.t1buf = static_cast<double*>(h->mpes_parts);
-    pt.totbuf = reinterpret_cast<float*>(pt.t1buf + static_cast<size_t>(pt.J) * pt.Qpad);
-    pt.counters = reinterpret_cast<unsigned int*>(pt.totbuf + static_cast<size_t>(pt.J) * Pn * pt.Qpad);
-    int* chunk_group = reinterpret_cast<int*>(pt.counters + 2);
+  }
+  const size_t o_order = 0;
+  const size_t o_gs = o_order + align256(sizeof(int) * S);
+  const size_t o_table = o_gs + align256(sizeof(int) * (M + 1));
+  const size_t o_cg = o_table + align256(fast ? 0 : sizeof(int) * kGenMaxP * kGenMaxC);
+  const size_t o_cnt = o_cg + align256(sizeof(int) * (kMaxChunks + 2));
+  const size_t o_done = o_cnt + 256;
+  const size_t o_t1 = o_done + align256((fast && pt.J > 1) ? sizeof(unsigned int) * tiles : 0);
+  const size_t o_tot = o_t1 + align256(pt.J > 1 ? sizeof(double) * pt.J * pt.Qpad : 0);
+  const size_t total = o_tot + align256(pt.J > 1 ? sizeof(float) * pt.J * Pn * pt.Qpad : 0);
+  StreamScratch sc(stream);
+  TKBO_CUDA_CHECK(sc.alloc(total));
+  unsigned char* base = static_cast<unsigned char*>(sc.p);
+  int* order = reinterpret_cast<int*>(base + o_order);
+  int* gs = reinterpret_cast<int*>(base + o_gs);
+  int* dperm = reinterpret_cast<int*>(base + o_table);
+  bool done = false;
+  if (fast) {
+    int* chunk_group = reinterpret_cast<int*>(base + o_cg);
     pt.chunk_group = chunk_group;
+    pt.counters = reinterpret_cast<unsigned int*>(base + o_cnt);
+    pt.tile_done = reinterpret_cast<unsigned int*>(base + o_done);
+    pt.t1buf = reinterpret_cast<double*>(base + o_t1);
+    pt.totbuf = reinterpret_cast<float*>(base + o_tot);
+    TKBO_CUDA_CHECK(cudaMemsetAsync(base + o_cnt, 0, o_t1 - o_cnt, stream));      // unit counters + tile_done
     group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs, pt.J, chunk_group);
     h->launches += 1;
     done = dispatch_all_perms(C, k, fchi, order, gs, S, Q, M, mode, h->sm_count, pt, out_mi, stream);
-    h->launches += 1;                                     // + the finishing kernel (the main one is counted below)
   } else {
     group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs);
     h->launches += 1;
@@ -655,15 +750,10 @@ int mpes_indiff(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax,
   TKBO_REQUIRE(S >= 1 && Q >= 1 && Q < (int64_t(1) << 31) && M >= 1, "S, Q, M must be >= 1 and Q < 2^31");
   TKBO_REQUIRE(C >= 1 && C <= kGenMaxC, "need 1 <= C <= 8");
   TKBO_REQUIRE(threshold >= 0.0 && threshold < 80.0, "indifference threshold must be in [0, 80)");
-  const size_t need = sizeof(int) * (static_cast<size_t>(S) + M + 1) + sizeof(int) * kGenMaxP * kGenMaxC;
-  if (h->mpes_scratch_bytes < need) {
-    if (h->mpes_scratch) TKBO_CUDA_CHECK(cudaFree(h->mpes_scratch));
-    h->mpes_scratch = nullptr; h->mpes_scratch_bytes = 0;
-    TKBO_CUDA_CHECK(cudaMalloc(&h->mpes_scratch, need));
-    h->mpes_scratch_bytes = need;
-  }
-  int* order = static_cast<int*>(h->mpes_scratch);
-  int* gs = order + S;
+  StreamScratch sc(stream);
+  TKBO_CUDA_CHECK(sc.alloc(align256(sizeof(int) * S) + sizeof(int) * (M + 1)));
+  int* order = static_cast<int*>(sc.p);
+  int* gs = reinterpret_cast<int*>(static_cast<unsigned char*>(sc.p) + align256(sizeof(int) * S));
   group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs);
   mpes_indiff_kernel<<<static_cast<unsigned>((Q + 127) / 128), 128, 0, stream>>>(fchi, order, gs, S, Q, C, M,
                                                                             static_cast<float>(exp(threshold)), out_mi);

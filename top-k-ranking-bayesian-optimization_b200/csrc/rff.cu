@@ -448,13 +448,10 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
       }
     }
   }
-  // Precision of the contraction (include/tkbo.h): the e4m3 correction form saves a third of the tensor work and costs
-  // the feature producers ~20 % more instructions, so AUTO takes it where the tensor pipe binds (wide sample chunks).
-  if (const char* env = getenv("TKBO_PRECISION")) {
-    if (precision == TKBO_PRECISION_AUTO)
-      precision = !strcmp(env, "fast") ? TKBO_PRECISION_FAST : (!strcmp(env, "fp32") ? TKBO_PRECISION_FP32 : precision);
-  }
-  bs->corr8 = precision == TKBO_PRECISION_FAST || (precision == TKBO_PRECISION_AUTO && bs->SC >= 128);
+  // Precision of the contraction (include/tkbo.h).  AUTO is the fp32-emulating three-MMA form: the e4m3 correction form
+  // (two thirds of the tensor work, ~3e-5 of max|f| on well-posed weights) is only safe when ||theta'|| / max|f| is small,
+  // which the library cannot know -- callers that can bound it (fourier_features.SharedBasis) ask for FAST explicitly.
+  bs->corr8 = precision == TKBO_PRECISION_FAST;
   cudaError_t e = cudaSuccess;
   e = e ? e : cudaMalloc(&bs->Wproj, static_cast<size_t>(bs->Dpad) * proj_k_alloc(DT) * sizeof(uint16_t));
   e = e ? e : cudaMalloc(&bs->theta_hi, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
@@ -547,6 +544,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->out_val = nullptr; p->out_idx = nullptr; p->out_key = nullptr; p->out_F = nullptr; p->ldf = 0; p->idx_offset = 0;
   p->duel_n = 0; p->duel_j0 = 0; p->duel_nj = 0; p->score_fix = nullptr;
   p->peer_world = 0; p->peer_rank = 0; p->peer_epoch = 0; p->ready_flag = nullptr; p->rows_per_chunk = 0;
+  p->peer_merge = 0; p->peer_status = nullptr;
   for (int r = 0; r < 8; ++r) p->peer_buf[r] = nullptr;
   p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
   p->n_slabs = bs->Dpad / kSlabK;
@@ -576,19 +574,33 @@ int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int6
 }
 
 // X is being filled by H2D copies on another stream, `rows_per_chunk` (multiple of 128) rows at a time; ready_flag[0]
-// counts the chunks that have landed (see RffParams::ready_flag).
-int rff_argmax_streamed(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t rows_per_chunk,
-                        unsigned int* ready_flag, float* out_val, int64_t* out_idx, cudaStream_t stream) {
+// counts the chunks that have landed (see RffParams::ready_flag).  With peer_bufs != nullptr the launch also delivers its
+// keys to every rank and merges in its last CTA (out_val / out_idx are then the GLOBAL results).
+int rff_argmax_streamed(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, int64_t rows_per_chunk,
+                        unsigned int* ready_flag, void* const* peer_bufs, int world, int rank, uint64_t epoch,
+                        float* out_val, int64_t* out_idx, cudaStream_t stream) {
   RffParams p;
   int grid = 0;
   int rc = fill_params(h, bs, X, N, &p, &grid);
   if (rc != TKBO_OK) return rc;
-  TKBO_REQUIRE(out_val && out_idx && ready_flag, "null pointer");
-  TKBO_REQUIRE(rows_per_chunk >= kTileM && rows_per_chunk % kTileM == 0, "rows_per_chunk must be a multiple of 128");
+  TKBO_REQUIRE(out_val && out_idx, "null pointer");
+  if (ready_flag != nullptr)
+    TKBO_REQUIRE(rows_per_chunk >= kTileM && rows_per_chunk % kTileM == 0, "rows_per_chunk must be a multiple of 128");
   p.out_val = out_val;
   p.out_idx = reinterpret_cast<long long*>(out_idx);
+  p.idx_offset = idx_offset;
   p.ready_flag = ready_flag;
   p.rows_per_chunk = rows_per_chunk;
+  if (peer_bufs != nullptr) {
+    TKBO_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && epoch >= 1, "bad peer arguments");
+    TKBO_REQUIRE(idx_offset >= 0 && idx_offset + N <= (int64_t(1) << 32) - 1, "global index must stay below 2^32 - 1 for the key form");
+    for (int r = 0; r < world; ++r) {
+      TKBO_REQUIRE(peer_bufs[r] != nullptr, "null peer buffer");
+      p.peer_buf[r] = static_cast<unsigned long long*>(peer_bufs[r]);
+    }
+    p.peer_world = world; p.peer_rank = rank; p.peer_epoch = epoch;
+    p.peer_merge = 1; p.peer_status = h->peer_status_dev;
+  }
   return dispatch_fused<0>(h, bs, p, grid, stream);
 }
 
@@ -620,7 +632,7 @@ struct RffPeer {
 };
 
 int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs,
-                    int world, int rank, uint64_t epoch, cudaStream_t stream) {
+                    int world, int rank, uint64_t epoch, float* out_val, int64_t* out_idx, cudaStream_t stream) {
   RffParams p;
   int grid = 0;
   int rc = fill_params(h, bs, X, N, &p, &grid);
@@ -633,6 +645,13 @@ int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N,
   }
   p.peer_world = world; p.peer_rank = rank; p.peer_epoch = epoch;
   p.idx_offset = idx_offset;
+  TKBO_REQUIRE((out_val == nullptr) == (out_idx == nullptr), "pass both out_val and out_idx (merge in the kernel) or neither");
+  if (out_val != nullptr) {
+    p.out_val = out_val;
+    p.out_idx = reinterpret_cast<long long*>(out_idx);
+    p.peer_merge = 1;
+    p.peer_status = h->peer_status_dev;
+  }
   return dispatch_fused<0>(h, bs, p, grid, stream);
 }
 
@@ -669,7 +688,8 @@ int peer_push_keys(tkbo_handle_t h, const int64_t* keys, int S, void* const* pee
 // One block per 256 samples; its first `world` threads wait for the flags (bounded: ~10 s, then every index of the block
 // reads -2 so that a lost peer shows up as an error instead of a hang).
 __global__ void merge_peer_keys_kernel(const unsigned long long* __restrict__ buf, int world, int S, unsigned long long epoch,
-                                       float* __restrict__ out_val, long long* __restrict__ out_idx) {
+                                       float* __restrict__ out_val, long long* __restrict__ out_idx,
+                                       unsigned int* __restrict__ status) {
   __shared__ int timed_out;
   if (threadIdx.x == 0) timed_out = 0;
   __syncthreads();
@@ -687,7 +707,11 @@ __global__ void merge_peer_keys_kernel(const unsigned long long* __restrict__ bu
   __syncthreads();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
-  if (timed_out) { out_val[s] = __int_as_float(0x7fc00000); out_idx[s] = -2; return; }
+  if (timed_out) {
+    out_val[s] = __int_as_float(0x7fc00000); out_idx[s] = -2;
+    if (s == 0 && status != nullptr) *reinterpret_cast<volatile unsigned int*>(status) = static_cast<unsigned int>(epoch);
+    return;
+  }
   long long best = kEmptyKey;
   const unsigned long long* keys = buf + static_cast<size_t>(epoch & 1ull) * world * S;
   for (int r = 0; r < world; ++r) {
@@ -707,7 +731,8 @@ int merge_peer_keys(tkbo_handle_t h, const void* local_buf, int world, int S, ui
   TKBO_REQUIRE(h && local_buf && out_val && out_idx, "null pointer");
   TKBO_REQUIRE(world >= 1 && world <= 8 && S >= 1 && epoch >= 1, "bad peer arguments");
   merge_peer_keys_kernel<<<(S + 255) / 256, 256, 0, stream>>>(static_cast<const unsigned long long*>(local_buf), world, S, epoch,
-                                                               out_val, reinterpret_cast<long long*>(out_idx));
+                                                               out_val, reinterpret_cast<long long*>(out_idx),
+                                                               h->peer_status_dev);
   h->launches += 1;
   TKBO_CUDA_CHECK(cudaGetLastError());
   return TKBO_OK;
@@ -821,6 +846,7 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   p.stages = bs->stages; p.ring = bs->ring; p.acc_bufs = bs->acc_bufs; p.xa_bufs = bs->xa_bufs;
   p.proj_warps = bs->proj_warps; p.wstages = bs->wstages; p.coop = bs->coop;
   p.peer_world = 0; p.peer_rank = 0; p.peer_epoch = 0; p.ready_flag = nullptr; p.rows_per_chunk = 0;
+  p.peer_merge = 0; p.peer_status = nullptr;
   for (int r = 0; r < 8; ++r) p.peer_buf[r] = nullptr;
   p.duel_n = n; p.duel_j0 = j_begin; p.duel_nj = j_end - j_begin;
   p.score_fix = reinterpret_cast<unsigned long long*>(fix);

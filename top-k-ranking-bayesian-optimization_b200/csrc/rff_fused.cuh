@@ -88,6 +88,12 @@ struct RffParams {
   unsigned long long* peer_buf[8];
   int peer_world, peer_rank;
   unsigned long long peer_epoch;
+  // peer_merge = 1: the last CTA also does the merge -- after its own delivery it acquires the `peer_world` flags of its
+  // OWN buffer (peer_buf[peer_rank]), takes the per-sample maximum over the slots and writes the global (value, index) to
+  // out_val / out_idx: one launch per rank and iteration.  A peer that does not deliver within ~10 s gives index -2 for
+  // every sample and the epoch in *peer_status (host-mapped word, may be null).
+  int peer_merge;
+  unsigned int* peer_status;
   // streamed candidates (tkbo_rff_argmax_host): X arrives in chunks of `rows_per_chunk` rows by H2D copies on another
   // stream while this launch runs; ready_flag[0] = number of chunks landed so far (written by a copy queued behind each
   // chunk), ready_flag[1] = set by the kernel if a chunk never arrived.  Null: all of X is resident.
@@ -240,6 +246,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   __shared__ uint64_t bars[kNumBars];
   __shared__ uint32_t tmem_base_smem;
   __shared__ int is_last_cta;
+  __shared__ int peer_timed_out;
   __shared__ __align__(16) float thr_s[256];       // per column of the current chunk: running maxima (MODE 0) / unscale (MODE 1, 2)
 
   const int warp = threadIdx.x >> 5;
@@ -607,7 +614,12 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             unsigned got;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(p.ready_flag) : "memory");
             if (got >= need) break;
-            if (clock64() - t0 > 20000000000ll) { atomicExch(p.ready_flag + 1, 1u); break; }   // ~10 s: report, do not hang
+            // a wait that has expired anywhere (this or another warp / CTA) ends every later wait at once: the launch is
+            // already lost, the host reports it, so the total stall is bounded by ONE time limit (~10 s), not one per tile
+            unsigned lost;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(lost) : "l"(p.ready_flag + 1) : "memory");
+            if (lost != 0u) break;
+            if (clock64() - t0 > 20000000000ll) { atomicExch(p.ready_flag + 1, 1u); break; }
             __nanosleep(100);
           }
         }
@@ -812,6 +824,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     if (threadIdx.x == 0) {
       const unsigned prev = atomicAdd(p.done_counter, 1u);
       is_last_cta = (prev == gridDim.x - 1);
+      peer_timed_out = 0;
     }
     __syncthreads();
     if (is_last_cta) {
@@ -827,7 +840,11 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           const long long key = none ? kEmptyKey : argmax_key(v, static_cast<uint32_t>(gi));
           if (p.out_key != nullptr) p.out_key[s] = key;
           const size_t slot = (static_cast<size_t>(p.peer_epoch & 1ull) * p.peer_world + p.peer_rank) * p.S + s;
-          for (int r = 0; r < p.peer_world; ++r) p.peer_buf[r][slot] = static_cast<unsigned long long>(key);
+          // remote ranks first: their merges wait for us over NVLink, ours reads the local copy last
+          for (int r = 1; r <= p.peer_world; ++r) {
+            const int dst = (p.peer_rank + r) % p.peer_world;
+            p.peer_buf[dst][slot] = static_cast<unsigned long long>(key);
+          }
         } else {
           p.out_val[s] = v;
           p.out_idx[s] = gi;
@@ -840,6 +857,40 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         if (threadIdx.x < p.peer_world) {
           unsigned long long* flag = p.peer_buf[threadIdx.x] + 2ull * p.peer_world * p.S + p.peer_rank;
           asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(p.peer_epoch) : "memory");
+        }
+        if (p.peer_merge) {
+          // merge here instead of in a second launch: acquire every rank's flag in the local buffer (bounded wait), then
+          // per sample the maximum over the `world` slots; max commutes, so every rank computes the same bits
+          const unsigned long long* local = p.peer_buf[p.peer_rank];
+          if (threadIdx.x < p.peer_world) {
+            const unsigned long long* flag = local + 2ull * p.peer_world * p.S + threadIdx.x;
+            const long long t0 = clock64();
+            for (;;) {
+              unsigned long long f;
+              asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(flag) : "memory");
+              if (f >= p.peer_epoch) break;
+              if (clock64() - t0 > 20000000000ll) { peer_timed_out = 1; break; }
+              __nanosleep(64);
+            }
+          }
+          __syncthreads();
+          const unsigned long long* keys = local + static_cast<size_t>(p.peer_epoch & 1ull) * p.peer_world * p.S;
+          for (int s = threadIdx.x; s < p.S; s += blockDim.x) {
+            if (peer_timed_out) { p.out_val[s] = __int_as_float(0x7fc00000); p.out_idx[s] = -2; continue; }
+            long long best = kEmptyKey;
+            for (int r = 0; r < p.peer_world; ++r) {
+              unsigned long long k;
+              asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(k) : "l"(keys + static_cast<size_t>(r) * p.S + s) : "memory");
+              best = max(best, static_cast<long long>(k));
+            }
+            float bv;
+            long long bi;
+            argmax_unkey(best, &bv, &bi);
+            p.out_val[s] = bv;
+            p.out_idx[s] = bi;
+          }
+          if (peer_timed_out && threadIdx.x == 0 && p.peer_status != nullptr)
+            *reinterpret_cast<volatile unsigned int*>(p.peer_status) = static_cast<unsigned int>(p.peer_epoch);
         }
       }
     }

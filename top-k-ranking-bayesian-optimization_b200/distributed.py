@@ -134,23 +134,54 @@ class PeerMerge:
             ptrs = [self.buf.data_ptr()]
         self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
         self._nat = nat
+        self._dead = False
+        self._stream = None
 
-    def argmax(self, basis, X_local, idx_offset):
+    def check(self):
+        """Raise if a merge of this rank gave up waiting for a peer (its outputs then hold index -2 / NaN).  The status word
+        is host-mapped: it is current once the stream that ran the merge has been synchronised; ``argmax`` also looks at
+        it at the start of every call, so a timeout surfaces at the latest on the following call.  After a timeout the
+        epoch bookkeeping of the group is void (a late peer may deliver into a slot that has been reused): the object
+        refuses further use and the group has to build a new PeerMerge behind a barrier."""
+        if self._dead:
+            raise self._nat.TkboError("PeerMerge: a previous merge timed out; create a new PeerMerge on all ranks")
+        ep = int(self._nat.lib().tkbo_peer_status(self._nat.handle(self.device.index)))
+        if ep != 0:
+            self._dead = True
+            raise self._nat.TkboError(f"PeerMerge: a peer did not deliver its keys for epoch {ep} within ~10 s "
+                                      "(index -2 was returned for that call)")
+
+    def _same_stream(self):
+        import torch
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        if self._stream is None:
+            self._stream = st
+        elif st != self._stream:
+            raise self._nat.TkboError("PeerMerge: all calls of one object must be issued on the same CUDA stream "
+                                      "(the two-slot epoch scheme orders a rank's launches by stream order)")
+
+    def argmax(self, basis, X_local, idx_offset, fused=True):
         """(val[S], idx[S]) over all ranks' shards; X_local are rows [idx_offset, idx_offset + N_local); an empty shard
-        delivers "no candidate" so that the peers do not wait for it."""
+        delivers "no candidate" so that the peers do not wait for it.  ``fused`` (default): ONE launch per call - the
+        kernel's last CTA delivers the keys and merges; otherwise delivery + the separate ``tkbo_merge_peer_keys`` launch."""
         import ctypes
         import torch
         nat = self._nat
         assert basis.S == self.S
+        self.check()
+        self._same_stream()
         self.epoch += 1
+        val = torch.empty(self.S, dtype=torch.float32, device=self.device)
+        idx = torch.empty(self.S, dtype=torch.int64, device=self.device)
         if X_local.shape[0] == 0:
             nat.check(nat.lib().tkbo_peer_push_keys(nat.handle(self.device.index), None, self.S, self._ptrs, self.world,
                                                     self.rank, self.epoch, nat.current_stream_ptr(self.device)),
                       "tkbo_peer_push_keys")
+        elif fused:
+            basis.argmax_peer(X_local, idx_offset, self._ptrs, self.rank, self.epoch, val, idx)
+            return val, idx
         else:
             basis.argmax_peer(X_local, idx_offset, self._ptrs, self.rank, self.epoch)
-        val = torch.empty(self.S, dtype=torch.float32, device=self.device)
-        idx = torch.empty(self.S, dtype=torch.int64, device=self.device)
         nat.check(nat.lib().tkbo_merge_peer_keys(nat.handle(self.device.index), ctypes.c_void_p(self.buf.data_ptr()), self.world,
                                                  self.S, self.epoch, nat.ptr(val), nat.ptr(idx),
                                                  nat.current_stream_ptr(self.device)), "tkbo_merge_peer_keys")

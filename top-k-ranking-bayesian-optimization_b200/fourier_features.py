@@ -214,12 +214,15 @@ def sample_maximizers(X, count, n_init, D, model, min_val, max_val, num_steps=30
 # ---------------------------------------------------------------------------------------------------
 # shared-basis fast path
 # ---------------------------------------------------------------------------------------------------
-def argmax_host(W, b, Theta, X, device=0, out_val=None, out_idx=None):
+def argmax_host(W, b, Theta, X, device=0, out_val=None, out_idx=None, peer=None, idx_offset=0):
     """End-to-end host-buffer call (C ABI ``tkbo_rff_argmax_host``): W (D, d), b (D,), Theta (D, S) float64 and the
     candidates X (N, d) float32 are HOST arrays (NumPy, or CPU torch tensors - with pinned memory the single kernel
     launch consumes the candidate chunks while their H2D copies are still landing); returns (val[S] float32,
     idx[S] int64) NumPy arrays.
-    Device staging and the basis layout are cached on the handle between calls of the same shape."""
+    Device staging and the basis layout are cached on the handle between calls of the same shape.
+    ``peer`` (a distributed.PeerMerge) + ``idx_offset``: X is this rank's shard of a sharded candidate set and the results
+    are the GLOBAL ones (``tkbo_rff_argmax_host_peer``: the same single launch also delivers the keys to the peers and
+    merges; every rank of the group must make the call)."""
     def host(a, dtype):
         if hasattr(a, "data_ptr"):
             assert a.device.type == "cpu" and a.is_contiguous()
@@ -238,9 +241,17 @@ def argmax_host(W, b, Theta, X, device=0, out_val=None, out_idx=None):
     vp = val.data_ptr() if hasattr(val, "data_ptr") else val.ctypes.data
     ip = idx.data_ptr() if hasattr(idx, "data_ptr") else idx.ctypes.data
     dev = device if isinstance(device, int) else _device(device).index
-    nat.check(nat.lib().tkbo_rff_argmax_host(nat.handle(dev), ctypes.c_void_p(Wp), ctypes.c_void_p(bp), ctypes.c_void_p(Tp),
-                                             int(D), int(d), int(S), ctypes.c_void_p(Xp), int(Xs[0]), ctypes.c_void_p(vp),
-                                             ctypes.c_void_p(ip)), "tkbo_rff_argmax_host")
+    if peer is None:
+        nat.check(nat.lib().tkbo_rff_argmax_host(nat.handle(dev), ctypes.c_void_p(Wp), ctypes.c_void_p(bp), ctypes.c_void_p(Tp),
+                                                 int(D), int(d), int(S), ctypes.c_void_p(Xp), int(Xs[0]), ctypes.c_void_p(vp),
+                                                 ctypes.c_void_p(ip)), "tkbo_rff_argmax_host")
+    else:
+        peer.epoch += 1
+        nat.check(nat.lib().tkbo_rff_argmax_host_peer(nat.handle(dev), ctypes.c_void_p(Wp), ctypes.c_void_p(bp),
+                                                      ctypes.c_void_p(Tp), int(D), int(d), int(S), ctypes.c_void_p(Xp),
+                                                      int(Xs[0]), int(idx_offset), peer._ptrs, peer.world, peer.rank,
+                                                      peer.epoch, ctypes.c_void_p(vp), ctypes.c_void_p(ip)),
+                  "tkbo_rff_argmax_host_peer")
     return val, idx
 
 
@@ -249,11 +260,16 @@ class SharedBasis:
     the fused kernel's operand layout.  ``argmax`` / ``eval`` stream any number of candidates through it."""
 
     PRECISIONS = {"auto": 0, "fp32": 1, "fast": 2}
+    FAST_ERROR_PER_NORM = 1e-4      # |f_fast - f_fp64| <= this * ||sqrt(2/D) theta_s||_2 (measured <= ~1.5e-5; see error_bound)
+    FAST_BUDGET = 0.3e-4            # share of the path's 1e-4 tolerance the fast form may use, relative to max|f_s|
 
-    def __init__(self, W, b, Theta, device=None, precision="auto"):
+    def __init__(self, W, b, Theta, device=None, precision="auto", f_scale=None):
         """``precision``: "fp32" = three fp16 tensor-core products per term (fp32 emulation, ~2e-6 of max|f|); "fast" =
-        fp16 hi*hi + one e4m3 product for both correction terms (~3e-5 of max|f|, inside the path's 1e-4 tolerance, two
-        thirds of the tensor work); "auto" = fast where the tensor pipe binds (sample chunks >= 128)."""
+        fp16 hi*hi + one e4m3 product for both correction terms (two thirds of the tensor work; error proportional to
+        ||sqrt(2/D) theta_s||, ~3e-5 of max|f| on a well-posed regression); "auto" = fast only if it is provably inside
+        the tolerance: the caller passes ``f_scale`` (S,) = a lower bound of max|f_s| (``sample`` uses the q-samples the
+        weights interpolate, ff.py:74) and FAST_ERROR_PER_NORM * ||theta'_s|| <= FAST_BUDGET * f_scale_s holds for every
+        sample, and the sample count is in the tensor-bound regime (> 96); fp32 otherwise."""
         torch = nat.require_cuda()
         self.device = _device(device)
         self.W, self.b, self.Theta = _f64(W, self.device), _f64(b, self.device).reshape(-1), _f64(Theta, self.device)
@@ -261,18 +277,44 @@ class SharedBasis:
         self.S = self.Theta.shape[1]
         assert self.Theta.shape[0] == self.D and self.b.shape[0] == self.D, "SharedBasis: shape mismatch"
         self._h = nat.handle(self.device.index)
+        self._torch = torch
+        self._requested = precision
         self._basis = ctypes.c_void_p()
+        self.precision = self._choose_precision(precision, f_scale)
+        self._create()
+
+    def _choose_precision(self, precision, f_scale):
+        if precision != "auto":
+            assert precision in self.PRECISIONS, "precision must be 'auto', 'fp32' or 'fast'"
+            return precision
+        if f_scale is None or self.S <= 96:
+            return "fp32"
+        torch = self._torch
+        fs = torch.as_tensor(np.asarray(to_numpy(f_scale)).reshape(-1)).to(self.device)
+        norm = (self.Theta * float(np.sqrt(2.0 / self.D))).norm(dim=0)
+        ok = bool((self.FAST_ERROR_PER_NORM * norm <= self.FAST_BUDGET * fs).all())
+        return "fast" if ok else "fp32"
+
+    def _create(self):
+        if self._basis:
+            nat.lib().tkbo_rff_basis_destroy(self._h, self._basis)
+            self._basis = ctypes.c_void_p()
         nat.check(nat.lib().tkbo_rff_basis_create_ex(self._h, ctypes.byref(self._basis), self.D, self.d, self.S,
-                                                     self.PRECISIONS[precision]), "tkbo_rff_basis_create_ex")
+                                                     self.PRECISIONS[self.precision]), "tkbo_rff_basis_create_ex")
         nat.check(nat.lib().tkbo_rff_basis_set(self._h, self._basis, nat.ptr(self.W), nat.ptr(self.b), nat.ptr(self.Theta), 0,
                                                nat.current_stream_ptr(self.device)), "tkbo_rff_basis_set")
-        self._torch = torch
 
-    def set(self, W, b, Theta):
-        """Load a new draw of the same shape (next BO iteration) without reallocating the device layout."""
+    def set(self, W, b, Theta, f_scale=None):
+        """Load a new draw of the same shape (next BO iteration) without reallocating the device layout (with
+        precision="auto" the form is re-decided for the new weights; a change of form rebuilds the layout)."""
         W, b, Theta = _f64(W, self.device), _f64(b, self.device).reshape(-1), _f64(Theta, self.device)
         assert W.shape == (self.D, self.d) and b.shape == (self.D,) and Theta.shape == (self.D, self.S)
         self.W, self.b, self.Theta = W, b, Theta
+        want = self._choose_precision(self._requested, f_scale)
+        if want != self.precision:
+            self.precision = want
+            self._create()
+            return self
         nat.check(nat.lib().tkbo_rff_basis_set(self._h, self._basis, nat.ptr(W), nat.ptr(b), nat.ptr(Theta), 0,
                                                nat.current_stream_ptr(self.device)), "tkbo_rff_basis_set")
         return self
@@ -286,7 +328,7 @@ class SharedBasis:
             pass
 
     @classmethod
-    def sample(cls, X_train, model, D, count, device=None, rng=None):
+    def sample(cls, X_train, model, D, count, device=None, rng=None, precision="auto"):
         """Shared-basis analogue of sample_features_weights: draw (W, b) once, fit theta_s = T q_s for
         s < count with T the ff.py:80-82 transform on the training features; retry on singular (ff.py:92-105)."""
         dev = _device(device)
@@ -302,7 +344,9 @@ class SharedBasis:
                 Z = _f64(rng.standard_normal((count, n)), dev)
                 Q = _f64(model.q_sqrt, dev).reshape(n, n) @ Z.T + _f64(model.q_mu, dev).reshape(n, 1)   # (n, count)
                 Theta = _regression_transform(phi) @ Q                                    # (D, count)
-                return cls(W[0], b[0, :, 0], Theta, device=dev)
+                # the weights interpolate the q-samples on the training inputs (ff.py:80-84), so max_i |q_is| is a lower
+                # bound of max|f_s|: the scale the 1e-4 tolerance is measured against
+                return cls(W[0], b[0, :, 0], Theta, device=dev, precision=precision, f_scale=Q.abs().amax(dim=0))
             except SingularMatrixError as err:
                 print(err)
                 print("Resampling phi, W, b, theta")
@@ -318,9 +362,10 @@ class SharedBasis:
         in the worst case and ~rel_feature_error * ||sqrt(2/D) theta_s||_2 in practice (independent errors).
         A well-posed posterior has ||sqrt(2/D) theta_s|| ~ max|f_s|, i.e. ~1e-6 relative; an ill-posed
         regression (ff.py:80-82 inverts phi phi^T without jitter) can inflate it by orders of magnitude.
-        With the e4m3 correction form (precision "fast") the per-product error is ~2^-12 * 2^-4 instead: 1e-4 here."""
+        With the e4m3 correction form (precision "fast") the per-product error is ~2^-12 * 2^-4 instead: FAST_ERROR_PER_NORM
+        (1e-4; measured <= 1.5e-5 per unit norm, the rest is margin for the tail over 2^24 x S values)."""
         if rel_feature_error is None:
-            rel_feature_error = 1e-4 if self.config(1)["e4m3_corrections"] else 4e-6
+            rel_feature_error = self.FAST_ERROR_PER_NORM if self.config(1)["e4m3_corrections"] else 4e-6
         return rel_feature_error * (self.Theta * float(np.sqrt(2.0 / self.D))).norm(dim=0)
 
     def config(self, N):
@@ -355,13 +400,15 @@ class SharedBasis:
                                                 nat.current_stream_ptr(self.device)), "tkbo_rff_argmax_key")
         return key
 
-    def argmax_peer(self, X, idx_offset, peer_ptrs, rank, epoch):
+    def argmax_peer(self, X, idx_offset, peer_ptrs, rank, epoch, out_val=None, out_idx=None):
         """Fused kernel + merge push: this rank's S keys go straight into slot (epoch & 1, rank) of every rank's peer
         buffer (``peer_ptrs`` = ctypes array of the buffers as mapped here), followed by a release of flag[rank] = epoch;
+        with ``out_val`` / ``out_idx`` the same launch's last CTA also merges all ranks' keys into them;
         see distributed.PeerMerge, include/tkbo.h tkbo_rff_argmax_peer."""
         X = self._candidates(X)
         nat.check(nat.lib().tkbo_rff_argmax_peer(self._h, self._basis, nat.ptr(X), X.shape[0], int(idx_offset), peer_ptrs,
-                                                 len(peer_ptrs), int(rank), int(epoch), nat.current_stream_ptr(self.device)),
+                                                 len(peer_ptrs), int(rank), int(epoch), nat.ptr(out_val), nat.ptr(out_idx),
+                                                 nat.current_stream_ptr(self.device)),
                   "tkbo_rff_argmax_peer")
 
     def unpack_key(self, key):
