@@ -516,7 +516,15 @@ def mpes_block(ctx, args):
     Wq, bq, Tq = make_basis_arrays(1024, dq, Sm, 0.2, 0.0, 1.0, seed=4)
     bq_basis = pkg.fourier_features.SharedBasis(Wq, bq, Tq, device=dev, precision="fp32")
     chi_h = rngq.uniform(0, 1, size=(Q * C, dq)).astype(np.float32)
-    xst_h = rngq.uniform(0, 1, size=(M, dq)).astype(np.float32)
+    # the maximisers x* are posterior maximiser samples, as in MPES_Forr.py:295-306 (sample_maximizers, then I_batch): the
+    # arg max of each of the S sampled functions over 2^16 candidates (K1), the M most frequent distinct winners
+    cand_h = rngq.uniform(0, 1, size=(1 << 16, dq)).astype(np.float32)
+    _, widx = bq_basis.argmax(torch.from_numpy(cand_h).to(dev))
+    uniq, counts = np.unique(widx.cpu().numpy(), return_counts=True)
+    top = uniq[np.argsort(-counts, kind="stable")][:M]
+    xst_h = cand_h[top]
+    if xst_h.shape[0] < M:
+        xst_h = np.concatenate([xst_h, rngq.uniform(0, 1, size=(M - xst_h.shape[0], dq)).astype(np.float32)])
     chi, xst = torch.from_numpy(chi_h).to(dev), torch.from_numpy(xst_h).to(dev)
     F_chi = torch.empty((Sm, Q * C), dtype=torch.float32, device=dev)
     bq_basis.eval(chi, out=F_chi)
@@ -576,11 +584,13 @@ def mpes_block(ctx, args):
         tc = time.perf_counter() - tc0
         mi_cpu = np.concatenate(parts)
         mi_gpu = mi[:Qc].cpu().numpy()
+        groups = np.bincount(np.argmax(s_cpu, axis=1), minlength=M)
         out["cpu_baseline"] = {"value": Qc / tc, "unit": "acq evals/s", "cores": threads, "kind": "port",
                                "sample": f"{Qc} of the {Q} query sets (NumPy restatement of rank_pes.py:10-108, {threads} threads)"}
         out["parity"] = {"queries": Qc, "mi_min": float(mi_cpu.min()), "mi_median": float(np.median(mi_cpu)),
                          "mi_max": float(mi_cpu.max()),
-                         "max_rel_diff": float(np.max(np.abs(mi_gpu - mi_cpu) / np.abs(mi_cpu))),
+                         "max_rel_diff": float(np.max(np.abs(mi_gpu - mi_cpu) / np.maximum(np.abs(mi_cpu), 1e-300))),
+                         "samples_won_per_maximiser": [int(g) for g in groups],
                          "max_abs_diff": float(np.max(np.abs(mi_gpu - mi_cpu))), "tolerance": "1e-4 relative",
                          "ok": bool(np.allclose(mi_gpu, mi_cpu, rtol=1e-4, atol=1e-9))}
 

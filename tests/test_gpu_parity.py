@@ -517,9 +517,7 @@ def test_rank_pes_matches_reference_golden(pbo, golden, tag, capsys):
     ref = g[f"{tag}_mi"]
     np.testing.assert_allclose(mi.numpy(), ref, rtol=1e-4, atol=1e-9)
     if tag in ("gp_small", "gp_tiny"):
-        # the same through the explicit-table kernel (the reference's > 1000-permutation path) and with every chunk count
-        # of the fast kernel's work split (units of one sample chunk; J = 1 finishes inside the unit)
-        import os
+        # the same through the explicit-table kernel (the reference's > 1000-permutation path)
         from importlib import import_module
         common = import_module("top-k-ranking-bayesian-optimization_b200.acquisitions._common")
         fs = torch.from_numpy(g[f"{tag}_fsample_all"]).cuda()
@@ -527,13 +525,34 @@ def test_rank_pes_matches_reference_golden(pbo, golden, tag, capsys):
         table = mpes_oracle.all_permutations_k_in_n(C, k)
         np.testing.assert_allclose(common.mpes_from_device_samples(fchi, fstar, k, 0, table).cpu().numpy(), ref,
                                    rtol=1e-4, atol=1e-9)
-        for J in ("1", "3", "8"):
-            os.environ["TKBO_MPES_CHUNKS"] = J
-            try:
-                got = common.mpes_from_device_samples(fchi, fstar, k, 0, None).cpu().numpy()
-            finally:
-                del os.environ["TKBO_MPES_CHUNKS"]
-            np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-9)
+        # bitwise repeatable (the block-wide group sums are integer reductions), also for a ragged / unaligned batch
+        a1 = common.mpes_from_device_samples(fchi, fstar, k, 0, None)
+        a2 = common.mpes_from_device_samples(fchi, fstar, k, 0, None)
+        assert torch.equal(a1, a2)
+        odd = fchi[:, :Q - 3, :].contiguous()
+        np.testing.assert_allclose(common.mpes_from_device_samples(odd, fstar, k, 0, None).cpu().numpy(), ref[:Q - 3],
+                                   rtol=1e-4, atol=1e-9)
+
+
+def test_mpes_skewed_groups_large_batch(pbo):
+    """One maximiser wins most samples (the usual state late in a BO run) and several win none: every warp of a block takes
+    an equal share of the samples whatever the group sizes; result against the oracle on a slice, bitwise repeatable."""
+    rng = np.random.default_rng(8)
+    S, Q, C, k, M = 1024, 4000, 5, 3, 20
+    basis = rng.standard_normal((Q * C, 5)).astype(np.float32)
+    fchi_h = (rng.standard_normal((S, 5)).astype(np.float32) @ basis.T * 0.4).reshape(S, Q, C)
+    fstar_h = rng.standard_normal((S, M)).astype(np.float32)
+    fstar_h[:, 0] += 2.0                                     # maximiser 0 wins ~3/4 of the samples
+    fstar_h[:, 15:] -= 10.0                                  # the last five never win
+    counts = np.bincount(np.argmax(fstar_h, axis=1), minlength=M)
+    assert counts[0] > 0.6 * S and (counts[15:] == 0).all()
+    common = pbo.acquisitions._common
+    fchi, fstar = torch.from_numpy(fchi_h).cuda(), torch.from_numpy(fstar_h).cuda()
+    mi = common.mpes_from_device_samples(fchi, fstar, k, pbo._native.MPES_RANK)
+    assert torch.equal(mi, common.mpes_from_device_samples(fchi, fstar, k, pbo._native.MPES_RANK))
+    sl = slice(1000, 1200)
+    ref = mpes_oracle.rank_mpes_from_samples(fchi_h[:, sl].astype(np.float64), fstar_h.astype(np.float64), topk=k)
+    np.testing.assert_allclose(mi[sl].cpu().numpy(), ref, rtol=1e-4, atol=1e-9)
 
 
 def test_rank_pes_log_likelihood_matches_reference_golden(pbo, golden):
@@ -870,7 +889,9 @@ def test_c3_shape_regression_weights_both_forms(pbo):
     norm_ratio = float((np.linalg.norm(Theta * np.sqrt(2.0 / D), axis=0) / scale).max())
     print(f"c3-shape regression weights: max|dv|/max|f| fp32 {errs['fp32']:.2e} fast {errs['fast']:.2e}, ties {ties}, "
           f"||theta'|| / max|f| <= {norm_ratio:.2f}")
-    assert errs["fp32"] < 1e-5 and errs["fast"] < VAL_RTOL
+    # at D = 4096 the error of BOTH forms is set by the tensor core's truncating fp32 accumulation (a bias towards zero of
+    # ~1.2e-8 max|f| per accumulator update, tools/acc_bias_probe.py): 3 D / 16 updates in the fp32 form, 2 D / 16 in the fast
+    assert errs["fp32"] < 1e-5 + 2.5e-8 * 3 * D / 16 and errs["fast"] < 1e-5 + 2.5e-8 * 2 * D / 16 + 1e-5
     assert ties["fp32"] <= 2 and ties["fast"] <= 8
     # auto: the regression interpolates q on the training inputs, ||theta'|| / max|q| ~ 2-3 here -> fp32
     q_scale = scale                                                       # max|f| >= max|q|; be generous to the fast form

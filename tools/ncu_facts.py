@@ -1,0 +1,52 @@
+"""profiles/r02_ncu_facts.json from an ncu --set full report of tools/profile_cmd.py: per dominant kernel instance the
+per-launch DRAM bytes, tensor-pipe / issue / xu / fma utilisation and duration (last captured launch of each instance).
+    python tools/ncu_facts.py gpurun_out/prof_r02.ncu-rep profiles/r02_ncu_facts.json"""
+import csv
+import json
+import subprocess
+import sys
+
+rep, out = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+col = {h: i for i, h in enumerate(hdr)}
+
+
+def num(r, name):
+    if name not in col or r[col[name]] in ("", "n/a"):
+        return None
+    v = float(r[col[name]].replace(",", ""))
+    u = units[col[name]]
+    scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(u, 1.0)
+    return v * scale
+
+
+KEYS = {"rff_fused_kernel<6, 0, 2, false>": "k1_c3_fp32", "rff_fused_kernel<6, 0, 2, true>": "k1_c3_fast",
+        "rff_fused_kernel<2, 0, 4, false>": "k1_c2_fp32", "rff_fused_kernel<4, 2, 2, true>": "k1_c4d",
+        "mpes_all_perms_kernel<5, 3, true>": "k2_c5"}
+facts = {}
+for r in rows[2:]:
+    name = r[col["Kernel Name"]]
+    key = next((v for k, v in KEYS.items() if name.replace(" ", "").startswith(("tkbo::" + k).replace(" ", "")) or
+                k.replace(" ", "") in name.replace(" ", "")), None)
+    if key is None:
+        continue
+    rd, wr = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum")
+    facts[key] = {
+        "kernel": name, "source": f"ncu --set full --clock-control none, tools/profile_cmd.py ({rep.split('/')[-1]})",
+        "duration_ms": num(r, "gpu__time_duration.sum"),
+        "dram_bytes_read": rd, "dram_bytes_write": wr,
+        "dram_bytes_per_launch": (rd or 0.0) + (wr or 0.0),
+        "tensor_pipe_active_pct": num(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+        "issue_active_pct": num(r, "sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
+        "xu_pct": num(r, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+        "fma_pct": num(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+        "fp64_pct": num(r, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+        "lts_throughput_pct": num(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+        "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+        "registers_per_thread": num(r, "launch__registers_per_thread"),
+        "sm_cycles": num(r, "sm__cycles_elapsed.avg")}
+with open(out, "w") as fh:
+    json.dump(facts, fh, indent=1)
+print(json.dumps(facts, indent=1))

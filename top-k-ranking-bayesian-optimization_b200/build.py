@@ -97,7 +97,26 @@ def build_trace():
     return out
 
 
+def build_variant(name, defines):
+    """libtkbo_<name>.so: the same library compiled with extra -D defines (tuning sweeps, e.g. TKBO_POLY_MASK=0x1111u);
+    select it at run time with TKBO_LIB=<path>."""
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = nvcc_path()
+    extra = tuple("-D" + d for d in defines)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(lambda s: _compile_one(nvcc, s, extra, "_" + name), sources()))
+    out = os.path.join(HERE, f"libtkbo_{name}.so")
+    r = subprocess.run([nvcc, "-shared", "-o", out, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
     if "--trace" in sys.argv:
         print(build_trace())
+    for a in sys.argv[1:]:
+        if a.startswith("--variant="):          # --variant=name:DEF1=x,DEF2=y
+            vname, _, defs = a[len("--variant="):].partition(":")
+            print(build_variant(vname, [d for d in defs.split(",") if d]))

@@ -29,10 +29,9 @@ constexpr double kPesEps = 1e-7;   // tf.keras.backend.epsilon(), pes.py:68,87
 // stable counting sort of the sample indices by winning maximiser
 // ------------------------------------------------------------------------------------------------
 // order[group_start[m] .. group_start[m+1]) = samples with fstar_argmax == m, ascending.
-// chunk_group[0 .. J]: the groups split into J contiguous chunks of roughly equal sample counts (work units of the
-// all-permutations kernel; a chunk may be empty).
+// group_const[2 m] = p_m (rank_pes.py:40-41; pes.py:66-70 with the eps smoothing), group_const[2 m + 1] = log(1 / (S p_m)).
 __global__ void group_samples_kernel(const int* __restrict__ arg, int S, int M, int* __restrict__ order,
-                                     int* __restrict__ group_start, int J = 0, int* __restrict__ chunk_group = nullptr) {
+                                     int* __restrict__ group_start, int mode = 0, double* __restrict__ group_const = nullptr) {
   extern __shared__ int cnt[];           // [M + 1]
   for (int m = threadIdx.x; m <= M; m += blockDim.x) cnt[m] = 0;
   __syncthreads();
@@ -45,15 +44,13 @@ __global__ void group_samples_kernel(const int* __restrict__ arg, int S, int M, 
     for (int m = 0; m < M; ++m) cnt[m + 1] += cnt[m];
   __syncthreads();
   for (int m = threadIdx.x; m <= M; m += blockDim.x) group_start[m] = cnt[m];
-  if (threadIdx.x == 0 && chunk_group != nullptr) {
-    int m = 0;
-    chunk_group[0] = 0;
-    for (int j = 1; j < J; ++j) {
-      const long long target = static_cast<long long>(cnt[M]) * j / J;
-      while (m < M && cnt[m + 1] <= target) ++m;       // groups wholly below the j-th cut
-      chunk_group[j] = m;
+  if (group_const != nullptr) {
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+      const double c = static_cast<double>(cnt[m + 1] - cnt[m]);
+      const double pm = (mode == TKBO_MPES_PES) ? (c + kPesEps) / (static_cast<double>(S) + M * kPesEps) : c / static_cast<double>(S);
+      group_const[2 * m] = pm;
+      group_const[2 * m + 1] = (pm > 0.0) ? log(1.0 / (static_cast<double>(S) * pm)) : 0.0;
     }
-    chunk_group[J] = M;
   }
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     int w = cnt[m];
@@ -115,7 +112,7 @@ __device__ __forceinline__ void subset_reciprocals(const float (&e)[C], float (&
       s = first ? e[c] : s + e[c];
       first = false;
     }
-    rs[m] = fast_rcp(fmaxf(s, 1.17549435e-38f));          // all remaining choices flushed to zero: 0 * 2^126 = 0, not NaN
+    rs[m] = fast_rcp(s);                                  // s > 0: the callers keep every e[c] >= 2^-126
   }
 }
 
@@ -142,17 +139,18 @@ struct PermWalk {
 };
 
 // ------------------------------------------------------------------------------------------------
-// fast kernel: one thread per query, all K-permutations of C in registers.  Blocks of four independent warps
-// (one per SM sub-partition), three blocks per SM, persistent over 32-query tiles: an equal warp count on every
-// sub-partition matters because the loop is issue / MUFU bound.  Each warp streams its 32 queries' sample rows
-// (32*C contiguous floats per sample) through a private shared-memory ring filled by 1-D bulk copies (TMA)
-// kRing rows ahead, or by plain loads when the rows are not 16-byte aligned / the tile is ragged (STAGED = false).
+// fast kernel: one thread per query, all K-permutations of C in registers.  A block of kMpesWarps warps owns one tile of
+// 32 queries at a time (tiles are handed out by a global counter); its warps split the SAMPLES of the tile: warp w takes
+// positions w, w + W, w + 2W, ... of the grouped sample order, whatever group they fall in, so the split is even however
+// skewed the groups are (a maximiser that wins 70 % of the samples is the normal case late in a BO run).  Each warp streams
+// its samples' rows (32*C contiguous floats per sample) through a private shared-memory ring filled by 1-D bulk copies
+// (TMA) kRing rows ahead, or by plain loads when the rows are not 16-byte aligned / the tile is ragged (STAGED = false).
+// At every group boundary the warps add their partial sums into a block-shared accumulator and the group is folded once.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRing = 4;
-constexpr int kMpesWarps = 4;
-constexpr int kMaxChunks = 8;
-__host__ __device__ constexpr int mpes_warp_smem_bytes(int C, int P) {
-  return ((kRing * 32 * C * 4 + P * 32 * 4 + kRing * 8 + 127) / 128) * 128;
+constexpr int kMpesWarps = 8;
+__host__ __device__ constexpr int mpes_warp_smem_bytes(int C) {
+  return ((kRing * 32 * C * 4 + kRing * 8 + 127) / 128) * 128;
 }
 
 // Accurate log(a) for the group fold.  MI is a difference of entropies of size ~log P with a result of 1e-9 .. 1e-1
@@ -166,6 +164,7 @@ __host__ __device__ constexpr int mpes_warp_smem_bytes(int C, int P) {
 struct LogTable {
   float r[128];
   double t[128];      // -log(r[k])
+  double rd[128];     // r[k] 2^-31: for integers normalised to [2^31, 2^32)
 };
 __device__ __forceinline__ void log_table_fill(LogTable& tab, int tid) {
   if (tid < 128) {
@@ -173,7 +172,18 @@ __device__ __forceinline__ void log_table_fill(LogTable& tab, int tid) {
     const float r = __uint_as_float(__float_as_uint(r0) & 0xFFFFC000u);       // 9 explicit mantissa bits
     tab.r[tid] = r;
     tab.t[tid] = -log(static_cast<double>(r));
+    tab.rd[tid] = static_cast<double>(r) * (1.0 / 2147483648.0);
   }
+}
+// log(n) for an integer n >= 1, all in float64 (about 1e-15): n = 2^E v 2^-31 with v in [2^31, 2^32), k = the 7 bits below
+// v's leading one, x = v rd[k] - 1 exactly (32 x 9 bits), log1p(x) = x (1 - x/2 + x^2/3 - x^3/4) up to x^5/5 < 2e-12.
+__device__ __forceinline__ double table_log_uint(const LogTable& tab, unsigned int n) {
+  const int lz = __clz(static_cast<int>(n));
+  const unsigned int v = n << lz;
+  const unsigned int k = (v >> 24) & 127u;
+  const double x = fma(static_cast<double>(v), tab.rd[k], -1.0);
+  const double p = fma(x, fma(x, fma(x, -0.25, 0.3333333333333333), -0.5), 1.0);
+  return fma(static_cast<double>(31 - lz), 0.6931471805599453, fma(x, p, tab.t[k]));
 }
 // log(a) for a normal positive float a
 __device__ __forceinline__ double table_log(const LogTable& tab, float a) {
@@ -190,191 +200,245 @@ __device__ __forceinline__ double table_log(const LogTable& tab, float a) {
   return fma(static_cast<double>(E), 0.6931471805599453, tab.t[k] + (static_cast<double>(xh) + static_cast<double>(rest)));
 }
 
-// Work unit = (tile of 32 queries, chunk j of the maximiser groups), fetched dynamically from a global counter: a
-// whole tile (all S samples) is ~0.5 ms of work for one warp, far too coarse for a few thousand persistent warps.
-// For its chunk a unit produces
-//     A_j  = sum_{m in j} p_m sum_z c_zm log c_zm      (t1buf[j, q], float64)
-//     tot_j[z] = sum_{m in j} sum_{s in m} P_s(z)       (totbuf[j, z, q], float32)
-// and the LAST unit of a tile to finish (tile_done counter, threadfence + atomic) assembles
-//     MI = sum_j A_j - sum_z p_z log p_z,  p_z = (sum_j tot_j[z] + M eps) / S                 (float64)
-// summing j in order, so the result does not depend on which unit came last.  J == 1 keeps everything in the unit.
-// Per group: a_z = acc_z + eps, c_zm = a_z cm with cm = 1 / (S p_m), hence
-//     p_m sum_z c log c = (1/S) (sum_z a_z log a_z + log(cm) sum_z a_z)
-// with the two sums over z in float64 (table_log above).
+// Per group m the block needs  a_z = sum_{s in m} P_s(z)  over ALL its warps' samples.  Every warp rounds its partial sum
+// to a 2^-F grid (F = 31 - ceil(log2 S): sums are at most S) and adds it, as an integer, into gacc[z][lane] with a shared
+// memory reduction: integer sums commute, so the result is bitwise independent of warp timing.  After one block barrier
+// warp w folds the orderings z = w, w + W, ...:
+//     p_m sum_z c log c = (1/S) (sum_z a_z log a_z + log(cm) sum_z a_z),   c = a cm,  cm = 1 / (S p_m)
+// (float64 sums, table_log above) and keeps  tot_z = sum_m a_z  for its orderings in registers - again as integers.
+// Consistency of p(z) with the joint matters: MI = sum J log(J / (p_m p_z)) is insensitive to first order to errors in J
+// only if p_z is EXACTLY sum_m J_zm; a float32 running sum of the group values breaks that at the 1e-7 level, which is
+// 1e-4 of a typical MI.  The grid value is what the fold uses AND what is summed into tot_z.
+// At the end of the tile  MI = sum_w A_w  with  A_w = sum_m (fold terms of w's orderings) - sum_{z of w} p_z log p_z.
 template <int C, int K, bool STAGED>
-__global__ void __launch_bounds__(32 * kMpesWarps, 4)
+__global__ void __launch_bounds__(32 * kMpesWarps, 2)
 mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ order, const int* __restrict__ group_start,
-                      const int* __restrict__ chunk_group, int J, int S, long long Q, long long Qpad, int M, int mode,
-                      int tile_begin, int tile_end, unsigned int* __restrict__ unit_counter,
-                      unsigned int* __restrict__ tile_done, float* __restrict__ totbuf, double* __restrict__ t1buf,
-                      double* __restrict__ out_mi) {
+                      const double* __restrict__ group_const, int S, long long Q, int M, int mode, int tile_begin,
+                      int tile_end, unsigned int* __restrict__ tile_counter, double* __restrict__ out_mi) {
   constexpr int P = perm_count(C, K);
+  constexpr int W = kMpesWarps;
+  constexpr int kOwn = (P + W - 1) / W;                    // orderings folded by one warp
   constexpr float kLog2e = 1.4426950408889634f;
   // exponent offset: e_c = 2^((f_c - max) log2e + 120), so that choices up to 246 binades (170 nats) below the best one stay
   // normal floats (the sums stay below 2^127, every stage factor e * rs is scale free); rank_pes.py:166 renormalises per
   // stage, which this reproduces as long as the not-yet-ranked choices do not ALL flush to zero
   constexpr float kExpBias = 120.f;
   __shared__ LogTable logtab;
-  // dynamic shared memory, one private slice per warp: ring | tot | mbarriers (see mpes_warp_smem_bytes)
+  __shared__ unsigned int gacc[2][P][32];                  // block-wide group sums (fixed point), double-buffered by group
+  __shared__ double a_red[W][32];
+  __shared__ uint64_t gbar[2];                             // "every warp has delivered its share" per gacc buffer
+  __shared__ int tile_sh;
+  // dynamic shared memory, one private slice per warp: ring | mbarriers (see mpes_warp_smem_bytes)
   extern __shared__ __align__(128) unsigned char mpes_smem[];
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;                        // after the table fill, warps never synchronise with each other
+  const int wib = threadIdx.x >> 5;
   log_table_fill(logtab, threadIdx.x);
-  __syncthreads();
-  unsigned char* slice = mpes_smem + static_cast<size_t>(wib) * mpes_warp_smem_bytes(C, P);
+  for (int i = threadIdx.x; i < 2 * P * 32; i += blockDim.x) (&gacc[0][0][0])[i] = 0u;
+  unsigned char* slice = mpes_smem + static_cast<size_t>(wib) * mpes_warp_smem_bytes(C);
   float (*ring)[32 * C] = reinterpret_cast<float (*)[32 * C]>(slice);
-  float (*tot)[32] = reinterpret_cast<float (*)[32]>(slice + kRing * 32 * C * 4);      // sum over the chunk's groups of acc
-  uint64_t* full = reinterpret_cast<uint64_t*>(tot + P);
+  uint64_t* full = reinterpret_cast<uint64_t*>(slice + kRing * 32 * C * 4);
   const double invS = 1.0 / static_cast<double>(S);
   const double eps = (mode == TKBO_MPES_PES) ? kPesEps : 0.0;
   const double meps = (mode == TKBO_MPES_PES) ? M * kPesEps : 0.0;
+  int fix_bits = 31;
+  while (fix_bits > 0 && (static_cast<long long>(S) << fix_bits) > (1ll << 31)) --fix_bits;   // S 2^F <= 2^31
+  const float fix_scale = __int_as_float((127 + fix_bits) << 23);                              // 2^F
+  const double fix_unit = 1.0 / static_cast<double>(1ll << fix_bits);                          // 2^-F
   const long long rowstride = Q * C;
+  const int i1 = group_start[M];                           // samples with a valid winner
   if constexpr (STAGED) {
     if (lane == 0)
       for (int i = 0; i < kRing; ++i) mbar_init(&full[i], 1);
-    fence_mbar_init();
-    __syncwarp();
   }
+  if (threadIdx.x == 0) {
+    mbar_init(&gbar[0], W);
+    mbar_init(&gbar[1], W);
+  }
+  fence_mbar_init();
   uint32_t ring_phase = 0;                                 // bit i = parity to wait for on slot i
-  const unsigned n_units = static_cast<unsigned>(tile_end - tile_begin) * static_cast<unsigned>(J);
+  uint32_t g = 0;                                          // groups delivered so far by this block (runs across tiles)
 
   for (;;) {
-    unsigned unit = 0;
-    if (lane == 0) unit = atomicAdd(unit_counter, 1u);
-    unit = __shfl_sync(0xffffffffu, unit, 0);
-    if (unit >= n_units) break;
-    const int tile = tile_begin + static_cast<int>(unit / J);
-    const int j = static_cast<int>(unit % J);
-    const int m0 = chunk_group[j], m1 = chunk_group[j + 1];
-    const int i0 = group_start[m0], i1 = group_start[m1];  // this unit's range of the grouped sample order
+    if (threadIdx.x == 0) tile_sh = tile_begin + static_cast<int>(atomicAdd(tile_counter, 1u));
+    __syncthreads();                                       // tile_sh visible; a_red / gacc of the previous tile are done with
+    const int tile = tile_sh;
+    if (tile >= tile_end) break;
     const long long q = static_cast<long long>(tile) * 32 + lane;
     const bool valid = q < Q;
     const float* base = fchi + (valid ? q : Q - 1) * C;                          // direct path
     const float* tile_base = fchi + static_cast<long long>(tile) * 32 * C;       // staged path
-#pragma unroll
-    for (int z = 0; z < P; ++z) tot[z][lane] = 0.f;
     float acc[P];
 #pragma unroll
     for (int z = 0; z < P; ++z) acc[z] = 0.f;
+    unsigned int tot_own[kOwn];
+#pragma unroll
+    for (int t = 0; t < kOwn; ++t) tot_own[t] = 0u;
     double A = 0.0;
 
-    if constexpr (STAGED) {                                // prime the ring with the unit's first kRing rows
+    if constexpr (STAGED) {                                // prime the ring with this warp's first kRing rows
       if (lane == 0) {
-        for (int r = 0; r < kRing && i0 + r < i1; ++r) {
+        for (int r = 0; r < kRing && wib + r * W < i1; ++r) {
           mbar_arrive_expect_tx(&full[r], 32 * C * 4);
-          bulk_load_1d(ring[r], tile_base + static_cast<long long>(order[i0 + r]) * rowstride, 32 * C * 4, &full[r]);
+          bulk_load_1d(ring[r], tile_base + static_cast<long long>(order[wib + r * W]) * rowstride, 32 * C * 4, &full[r]);
         }
       }
       __syncwarp();
     }
     float fnext[C];
     if constexpr (!STAGED) {
-      if (i0 < i1) {
-        const float* r = base + static_cast<long long>(order[i0]) * rowstride;
+      if (wib < i1) {
+        const float* r = base + static_cast<long long>(order[wib]) * rowstride;
 #pragma unroll
         for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
       }
     }
 
-    int i = i0;                                            // position in the grouped sample order
-    for (int m = m0; m < m1; ++m) {
-      const int hi = group_start[m + 1];
-      const int cnt = hi - group_start[m];
-      if (cnt == 0 && mode == TKBO_MPES_RANK) continue;    // rank_pes.py:86-93 drops empty groups
-      for (; i < hi; ++i) {
-        float f[C];
-        if constexpr (STAGED) {
-          const int slot = (i - i0) % kRing;
-          mbar_wait(&full[slot], (ring_phase >> slot) & 1u);
-          ring_phase ^= 1u << slot;
+    int i = wib;                                           // position in the grouped sample order
+    int n = 0;                                             // samples this warp has consumed (ring slot = n % kRing)
+    // Software pipeline over the groups: a warp delivers its share of group m and goes straight on to the samples of the
+    // next group; it folds group m only after those (by then the other warps have delivered too, so the wait on gbar is
+    // normally already satisfied).  Order per warp: samples(m), [wait + fold(previous)], deliver(m), arrive.  Buffer reuse:
+    // deliver(m + 2) follows this warp's wait for group m + 1, i.e. every warp's arrive(m + 1), which each warp issues after
+    // its fold(m) has read and cleared the buffer.
+    int prev = -1;                                         // group delivered but not folded yet
+    for (int m = 0; m <= M; ++m) {
+      const bool tail = (m == M);                          // one extra pass to fold the last group
+      int n_before = n;
+      if (!tail) {
+        const int hi = group_start[m + 1];
+        if (hi == group_start[m] && mode == TKBO_MPES_RANK) continue;   // rank_pes.py:86-93 drops empty groups (block-uniform)
+        for (; i < hi; i += W, ++n) {
+          float f[C];
+          if constexpr (STAGED) {
+            const int slot = n % kRing;
+            mbar_wait(&full[slot], (ring_phase >> slot) & 1u);
+            ring_phase ^= 1u << slot;
 #pragma unroll
-          for (int c = 0; c < C; ++c) f[c] = ring[slot][lane * C + c];
+            for (int c = 0; c < C; ++c) f[c] = ring[slot][lane * C + c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) f[c] = fnext[c];
+            if (i + W < i1) {
+              const float* r = base + static_cast<long long>(order[i + W]) * rowstride;
+#pragma unroll
+              for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
+            }
+          }
+          float mx = f[0];
+#pragma unroll
+          for (int c = 1; c < C; ++c) mx = fmaxf(mx, f[c]);
+          const float mxs = fmaf(mx, kLog2e, -kExpBias);
+          float e[C];
+#pragma unroll
+          // floor at the smallest normal: a set of remaining choices that has underflowed entirely (> 170 nats below the
+          // best) then shares its (negligible) mass evenly instead of producing 0 * inf
+          for (int c = 0; c < C; ++c) e[c] = fmaxf(fast_ex2(fmaf(f[c], kLog2e, -mxs)), 1.17549435e-38f);
+          if constexpr (STAGED) {
+            __syncwarp();                                  // every lane has consumed its slot values
+            if (lane == 0 && i + kRing * W < i1) {
+              const int slot = n % kRing;
+              mbar_arrive_expect_tx(&full[slot], 32 * C * 4);
+              bulk_load_1d(ring[slot], tile_base + static_cast<long long>(order[i + kRing * W]) * rowstride, 32 * C * 4, &full[slot]);
+            }
+          }
+          float rs[1 << C];
+          subset_reciprocals<C, K>(e, rs);
+          int leaf = 0;
+          PermWalk<C, K, 0>::run(e, rs, 0u, 1.f, acc, leaf);
+        }
+      }
+      if (prev >= 0) {
+        // fold the orderings this warp owns of group `prev`:  A += p_m sum_z c_zm log c_zm,  c_zm = p(z | m) = (a_z + eps) cm
+        const uint32_t gp = g - 1u;
+        const int buf = static_cast<int>(gp & 1u);
+        mbar_wait(&gbar[buf], (gp >> 1) & 1u);
+        const double lcm = group_const[2 * prev + 1];      // log cm = log(1 / (S p_m))
+        double s1 = 0.0, s0 = 0.0;
+        if (mode == TKBO_MPES_RANK) {
+          // eps = 0: a_z = fx 2^-F, so  sum a log a = 2^-F (sum fx log fx - F ln2 sum fx)  with an all-float64 integer log
+          unsigned int isum = 0u;
+#pragma unroll
+          for (int t = 0; t < kOwn; ++t) {
+            const int z = wib + t * W;
+            if (z < P) {
+              const unsigned int fx = gacc[buf][z][lane];
+              gacc[buf][z][lane] = 0u;                     // free for the group after next
+              if (fx != 0u) s1 = fma(static_cast<double>(fx), table_log_uint(logtab, fx), s1);
+              isum += fx;                                  // <= S 2^F <= 2^31 over ALL orderings
+              tot_own[t] += fx;
+            }
+          }
+          s0 = static_cast<double>(isum) * fix_unit;
+          s1 = fma(-static_cast<double>(fix_bits) * 0.6931471805599453, static_cast<double>(isum), s1) * fix_unit;
         } else {
 #pragma unroll
-          for (int c = 0; c < C; ++c) f[c] = fnext[c];
-          if (i + 1 < i1) {
-            const float* r = base + static_cast<long long>(order[i + 1]) * rowstride;
-#pragma unroll
-            for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
+          for (int t = 0; t < kOwn; ++t) {
+            const int z = wib + t * W;
+            if (z < P) {
+              const unsigned int fx = gacc[buf][z][lane];
+              gacc[buf][z][lane] = 0u;
+              // a = grid sum + eps in float64 (eps = 1e-7 is below float32 resolution of a sum of ~S/M probabilities, and
+              // pes.I of an uninformative query consists of nothing but these eps terms):
+              // log a = log(fl32(a)) + (a - fl32(a)) / fl32(a)
+              const double ad = static_cast<double>(fx) * fix_unit + eps;
+              const float af = static_cast<float>(ad);
+              if (af >= 1e-30f) {                          // below: a log a < 7e-29, and no denormal handling needed
+                const double la = table_log(logtab, af) + (ad - static_cast<double>(af)) * static_cast<double>(fast_rcp(af));
+                s1 += ad * la;
+                s0 += ad;
+              }
+              tot_own[t] += fx;
+            }
           }
         }
-        float mx = f[0];
+        A += invS * (s1 + lcm * s0);
+        prev = -1;
+      }
+      if (tail) break;
+      // deliver this warp's share of group m (integers: the block sum does not depend on the order of arrival); a warp
+      // that saw no sample of the group (groups smaller than the block) only arrives
+      const int buf = static_cast<int>(g & 1u);
+      if (n != n_before) {
 #pragma unroll
-        for (int c = 1; c < C; ++c) mx = fmaxf(mx, f[c]);
-        const float mxs = fmaf(mx, kLog2e, -kExpBias);
-        float e[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) e[c] = fast_ex2(fmaf(f[c], kLog2e, -mxs));
-        if constexpr (STAGED) {
-          __syncwarp();                                    // every lane has consumed its slot values
-          if (lane == 0 && i + kRing < i1) {
-            const int slot = (i - i0) % kRing;
-            mbar_arrive_expect_tx(&full[slot], 32 * C * 4);
-            bulk_load_1d(ring[slot], tile_base + static_cast<long long>(order[i + kRing]) * rowstride, 32 * C * 4, &full[slot]);
-          }
+        for (int z = 0; z < P; ++z) {
+          atomicAdd(&gacc[buf][z][lane], __float2uint_rn(acc[z] * fix_scale));
+          acc[z] = 0.f;
         }
-        float rs[1 << C];
-        subset_reciprocals<C, K>(e, rs);
-        int leaf = 0;
-        PermWalk<C, K, 0>::run(e, rs, 0u, 1.f, acc, leaf);
       }
-      // fold group m:  A += p_m sum_z c_zm log c_zm  with c_zm = p(z | m) = (acc_z + eps) cm
-      const double pm = (mode == TKBO_MPES_PES)
-                            ? (static_cast<double>(cnt) + kPesEps) / (static_cast<double>(S) + M * kPesEps)
-                            : static_cast<double>(cnt) * invS;
-      const double lcm = log(invS / pm);
-      double s1a = 0.0, s1b = 0.0, s0 = 0.0;              // two interleaved chains for the float64 pipe
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gbar[buf]);
+      prev = m;
+      ++g;
+    }
+    // - sum_z p_z log p_z over this warp's orderings, then the block sum of the W partial results
+    if (mode == TKBO_MPES_RANK) {      // p_z = tot 2^-F / S: integer log again
+      const double shift = static_cast<double>(fix_bits) * 0.6931471805599453 + log(static_cast<double>(S));
+      double acc_t = 0.0;
+      unsigned int isum = 0u;
 #pragma unroll
-      for (int z = 0; z < P; ++z) {
-        // a = acc + eps in float64 (eps = 1e-7 is below float32 resolution of a sum of ~S/M probabilities, and pes.I of
-        // an uninformative query consists of nothing but these eps terms): log a = log(fl32(a)) + (a - fl32(a)) / fl32(a)
-        const double ad = static_cast<double>(acc[z]) + eps;
-        const float af = static_cast<float>(ad);
-        if (af >= 1e-30f) {                                // below: a log a < 7e-29, and no denormal handling needed
-          double la = table_log(logtab, af);
-          if (mode == TKBO_MPES_PES) la += (ad - static_cast<double>(af)) * static_cast<double>(fast_rcp(af));
-          const double t = ad * la;
-          if (z & 1) s1b += t; else s1a += t;
-          s0 += ad;
+      for (int t = 0; t < kOwn; ++t) {
+        if (wib + t * W < P && tot_own[t] != 0u) {
+          acc_t = fma(static_cast<double>(tot_own[t]), table_log_uint(logtab, tot_own[t]), acc_t);
+          isum += tot_own[t];
         }
-        tot[z][lane] += acc[z];
-        acc[z] = 0.f;
       }
-      A += invS * ((s1a + s1b) + lcm * s0);
-    }
-    if (J == 1) {
-      // the unit saw every group: finish here, nothing goes through global memory
-      double mi = A;
+      A -= (acc_t - shift * static_cast<double>(isum)) * fix_unit * invS;
+    } else {
 #pragma unroll
-      for (int z = 0; z < P; ++z) {
-        const double pz = (static_cast<double>(tot[z][lane]) + meps) * invS;
-        if (pz > 0.0) mi -= pz * log(pz);
+      for (int t = 0; t < kOwn; ++t) {
+        if (wib + t * W < P) {
+          const double pz = (static_cast<double>(tot_own[t]) * fix_unit + meps) * invS;
+          if (pz > 0.0) A -= pz * log(pz);
+        }
       }
-      if (valid) out_mi[q] = mi;
-      continue;
     }
-#pragma unroll
-    for (int z = 0; z < P; ++z) totbuf[(static_cast<size_t>(j) * P + z) * Qpad + q] = tot[z][lane];
-    t1buf[static_cast<size_t>(j) * Qpad + q] = A;
-    // last unit of the tile to get here assembles MI (release: partials before the counter; acquire: counter before reads)
-    __threadfence();
-    __syncwarp();
-    unsigned prev = 0;
-    if (lane == 0) prev = atomicAdd(tile_done + tile, 1u);
-    prev = __shfl_sync(0xffffffffu, prev, 0);
-    if (prev == static_cast<unsigned>(J - 1)) {
-      __threadfence();
+    a_red[wib][lane] = A;
+    __syncthreads();
+    if (wib == 0 && valid) {
       double mi = 0.0;
-      for (int jj = 0; jj < J; ++jj) mi += __ldcg(t1buf + static_cast<size_t>(jj) * Qpad + q);
-#pragma unroll 4
-      for (int z = 0; z < P; ++z) {
-        double t = 0.0;
-        for (int jj = 0; jj < J; ++jj) t += static_cast<double>(__ldcg(totbuf + (static_cast<size_t>(jj) * P + z) * Qpad + q));
-        const double pz = (t + meps) * invS;
-        if (pz > 0.0) mi -= pz * log(pz);
-      }
-      if (valid) out_mi[q] = mi;
-      if (lane == 0) tile_done[tile] = 0u;               // ready for the next call that reuses the buffer
+#pragma unroll
+      for (int w = 0; w < W; ++w) mi += a_red[w][lane];
+      out_mi[q] = mi;
     }
   }
 }
@@ -403,9 +467,10 @@ mpes_table_kernel(const float* __restrict__ fchi, const int* __restrict__ order,
   const double eps = (mode == TKBO_MPES_PES) ? kPesEps : 0.0;
   const float* base = fchi + q * C;
   const long long rowstride = Q * C;
-  float acc[32], tot[32];
+  float acc[32];
+  double tot[32];                                   // exact sum of the group values: p_z must equal sum_m J_zm (see above)
 #pragma unroll
-  for (int i = 0; i < 32; ++i) { acc[i] = 0.f; tot[i] = 0.f; }
+  for (int i = 0; i < 32; ++i) { acc[i] = 0.f; tot[i] = 0.0; }
   double mi = 0.0;
   for (int m = 0; m < M; ++m) {
     const int lo = group_start[m], hi = group_start[m + 1];
@@ -449,7 +514,7 @@ mpes_table_kernel(const float* __restrict__ fchi, const int* __restrict__ order,
       if (lane + 32 * t < P) {
         const double J = (static_cast<double>(acc[t]) + eps) * invS;
         if (J > 0.0) mi += J * (log(J) - log_pm);
-        tot[t] += acc[t];
+        tot[t] += static_cast<double>(acc[t]);
       }
       acc[t] = 0.f;
     }
@@ -457,7 +522,7 @@ mpes_table_kernel(const float* __restrict__ fchi, const int* __restrict__ order,
 #pragma unroll
   for (int t = 0; t < 32; ++t) {
     if (lane + 32 * t < P) {
-      const double pz = (static_cast<double>(tot[t]) + M * eps) * invS;
+      const double pz = (tot[t] + M * eps) * invS;
       if (pz > 0.0) mi -= pz * log(pz);
     }
   }
@@ -479,9 +544,10 @@ mpes_indiff_kernel(const float* __restrict__ fchi, const int* __restrict__ order
   const float* base = fchi + q * C;
   const long long rowstride = Q * C;
   const double invS = 1.0 / static_cast<double>(S);
-  float acc[kGenMaxC + 1], tot[kGenMaxC + 1];
+  float acc[kGenMaxC + 1];
+  double tot[kGenMaxC + 1];                         // exact sum of the group values (p_z == sum_m J_zm)
 #pragma unroll
-  for (int z = 0; z <= kGenMaxC; ++z) { acc[z] = 0.f; tot[z] = 0.f; }
+  for (int z = 0; z <= kGenMaxC; ++z) { acc[z] = 0.f; tot[z] = 0.0; }
   double mi = 0.0;
   for (int m = 0; m < M; ++m) {
     const int lo = group_start[m], hi = group_start[m + 1];
@@ -514,7 +580,7 @@ mpes_indiff_kernel(const float* __restrict__ fchi, const int* __restrict__ order
       if (z < C || z == kGenMaxC) {
         const double J = static_cast<double>(acc[z]) * invS;
         if (J > 0.0) mi += J * (log(J) - log_pm);
-        tot[z] += acc[z];
+        tot[z] += static_cast<double>(acc[z]);
       }
       acc[z] = 0.f;
     }
@@ -522,7 +588,7 @@ mpes_indiff_kernel(const float* __restrict__ fchi, const int* __restrict__ order
 #pragma unroll
   for (int z = 0; z <= kGenMaxC; ++z) {
     if (z < C || z == kGenMaxC) {
-      const double pz = static_cast<double>(tot[z]) * invS;
+      const double pz = tot[z] * invS;
       if (pz > 0.0) mi -= pz * log(pz);
     }
   }
@@ -571,51 +637,32 @@ __global__ void argmax_vec_kernel(const float* __restrict__ v, int n, long long*
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-// Partial results of the all-permutations kernel (one slab per sample chunk), its two unit counters and the per-tile
-// "units done" counters that elect the finishing unit.
-struct MpesParts {
-  const int* chunk_group;   // [J + 1]
-  int J;
-  long long Qpad;           // queries rounded up to whole 32-query tiles
-  float* totbuf;            // [J, P, Qpad]   (J > 1 only)
-  double* t1buf;            // [J, Qpad]      (J > 1 only)
-  unsigned int* counters;   // [2], zeroed before the launches
-  unsigned int* tile_done;  // [tiles], zeroed before the launches (J > 1 only)
-};
-
 template <int C, int K>
-static void launch_all_perms(const float* fchi, const int* order, const int* gs, int S, int64_t Q, int M, int mode,
-                             int sm_count, const MpesParts& pt, double* out, cudaStream_t stream) {
+static void launch_all_perms(const float* fchi, const int* order, const int* gs, const double* gconst, int S, int64_t Q, int M,
+                             int mode, int sm_count, unsigned int* counters, double* out, cudaStream_t stream) {
   const int64_t tiles = (Q + 31) / 32;
   // the bulk-copy path needs 16-byte aligned rows (Q*C % 4 == 0, base aligned) and full 32-query tiles
   const bool aligned = ((Q * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(fchi) & 15) == 0);
   const int64_t staged_tiles = aligned ? Q / 32 : 0;
   const int threads = 32 * kMpesWarps;
-  constexpr int P = perm_count(C, K);
-  const int smem = kMpesWarps * mpes_warp_smem_bytes(C, P);
-  cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = kMpesWarps * mpes_warp_smem_bytes(C);
   if (staged_tiles > 0) {
-    const int64_t units = staged_tiles * pt.J;
-    const int grid = static_cast<int>(std::min<int64_t>(4 * sm_count, (units + kMpesWarps - 1) / kMpesWarps));
-    mpes_all_perms_kernel<C, K, true><<<grid, threads, smem, stream>>>(fchi, order, gs, pt.chunk_group, pt.J, S, Q, pt.Qpad, M,
-                                                                   mode, 0, static_cast<int>(staged_tiles), pt.counters,
-                                                                   pt.tile_done, pt.totbuf, pt.t1buf, out);
+    const int grid = static_cast<int>(std::min<int64_t>(2 * sm_count, staged_tiles));
+    mpes_all_perms_kernel<C, K, true><<<grid, threads, smem, stream>>>(fchi, order, gs, gconst, S, Q, M, mode, 0,
+                                                                   static_cast<int>(staged_tiles), counters, out);
   }
   if (staged_tiles < tiles) {
-    const int64_t units = (tiles - staged_tiles) * pt.J;
-    const int grid = static_cast<int>(std::min<int64_t>(4 * sm_count, (units + kMpesWarps - 1) / kMpesWarps));
-    mpes_all_perms_kernel<C, K, false><<<grid, threads, smem, stream>>>(fchi, order, gs, pt.chunk_group, pt.J, S, Q, pt.Qpad, M,
-                                                                    mode, static_cast<int>(staged_tiles),
-                                                                    static_cast<int>(tiles), pt.counters + 1, pt.tile_done,
-                                                                    pt.totbuf, pt.t1buf, out);
+    const int grid = static_cast<int>(std::min<int64_t>(2 * sm_count, tiles - staged_tiles));
+    mpes_all_perms_kernel<C, K, false><<<grid, threads, smem, stream>>>(fchi, order, gs, gconst, S, Q, M, mode,
+                                                                    static_cast<int>(staged_tiles), static_cast<int>(tiles),
+                                                                    counters + 1, out);
   }
 }
 
-static bool dispatch_all_perms(int C, int K, const float* fchi, const int* order, const int* gs, int S, int64_t Q, int M,
-                               int mode, int sm, const MpesParts& pt, double* out, cudaStream_t st) {
+static bool dispatch_all_perms(int C, int K, const float* fchi, const int* order, const int* gs, const double* gconst, int S,
+                               int64_t Q, int M, int mode, int sm, unsigned int* counters, double* out, cudaStream_t st) {
 #define TKBO_CASE(c, k) \
-  if (C == c && K == k) { launch_all_perms<c, k>(fchi, order, gs, S, Q, M, mode, sm, pt, out, st); return true; }
+  if (C == c && K == k) { launch_all_perms<c, k>(fchi, order, gs, gconst, S, Q, M, mode, sm, counters, out, st); return true; }
   TKBO_CASE(2, 1) TKBO_CASE(2, 2)
   TKBO_CASE(3, 1) TKBO_CASE(3, 2) TKBO_CASE(3, 3)
   TKBO_CASE(4, 1) TKBO_CASE(4, 2) TKBO_CASE(4, 3) TKBO_CASE(4, 4)
@@ -666,58 +713,27 @@ int mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, i
   TKBO_REQUIRE(mode == TKBO_MPES_RANK || mode == TKBO_MPES_PES, "unknown mode");
   if (mode == TKBO_MPES_PES) TKBO_REQUIRE(k == 1 && perms == nullptr, "PES mode is top-1 with the implicit table");
   const bool fast = perms == nullptr && has_all_perms_kernel(C, k);
-  // layout of the call's scratch: order[S] | group_start[M + 1] | table[kGenMaxP * kGenMaxC] | chunk_group[kMaxChunks + 2] |
-  // counters[2] | tile_done[tiles] | t1buf[J, Qpad] f64 | totbuf[J, P, Qpad] f32
-  const int64_t tiles = (Q + 31) / 32;
-  MpesParts pt;
-  pt.Qpad = tiles * 32;
-  pt.J = 1;
-  const int Pn = fast ? perm_count(C, k) : 0;
-  size_t per_chunk = 0;
-  if (fast) {
-    // sample chunks: enough (tile, chunk) units for ~8 rounds of the persistent warps, at most kMaxChunks, one per
-    // maximiser, and partial buffers below 256 MiB; a large batch needs none (J = 1: no partial buffers at all)
-    per_chunk = static_cast<size_t>(pt.Qpad) * (static_cast<size_t>(Pn) * sizeof(float) + sizeof(double));
-    const int64_t warps = static_cast<int64_t>(h->sm_count) * 4 * kMpesWarps;
-    int64_t J = (8 * warps + tiles - 1) / tiles;
-    J = std::min<int64_t>(J, std::min(kMaxChunks, M));
-    J = std::min<int64_t>(J, static_cast<int64_t>((size_t(256) << 20) / per_chunk));
-    pt.J = static_cast<int>(std::max<int64_t>(1, J));
-    if (const char* env = getenv("TKBO_MPES_CHUNKS")) {
-      const int t = atoi(env);
-      if (t >= 1 && t <= std::min(kMaxChunks, M)) pt.J = t;
-    }
-  }
+  // layout of the call's scratch: order[S] | group_start[M + 1] | group_const[2 M] f64 | table[kGenMaxP * kGenMaxC] | tile counters[2]
   const size_t o_order = 0;
   const size_t o_gs = o_order + align256(sizeof(int) * S);
-  const size_t o_table = o_gs + align256(sizeof(int) * (M + 1));
-  const size_t o_cg = o_table + align256(fast ? 0 : sizeof(int) * kGenMaxP * kGenMaxC);
-  const size_t o_cnt = o_cg + align256(sizeof(int) * (kMaxChunks + 2));
-  const size_t o_done = o_cnt + 256;
-  const size_t o_t1 = o_done + align256((fast && pt.J > 1) ? sizeof(unsigned int) * tiles : 0);
-  const size_t o_tot = o_t1 + align256(pt.J > 1 ? sizeof(double) * pt.J * pt.Qpad : 0);
-  const size_t total = o_tot + align256(pt.J > 1 ? sizeof(float) * pt.J * Pn * pt.Qpad : 0);
+  const size_t o_gc = o_gs + align256(sizeof(int) * (M + 1));
+  const size_t o_table = o_gc + align256(sizeof(double) * 2 * M);
+  const size_t o_cnt = o_table + align256(fast ? 0 : sizeof(int) * kGenMaxP * kGenMaxC);
+  const size_t total = o_cnt + 256;
   StreamScratch sc(stream);
   TKBO_CUDA_CHECK(sc.alloc(total));
   unsigned char* base = static_cast<unsigned char*>(sc.p);
   int* order = reinterpret_cast<int*>(base + o_order);
   int* gs = reinterpret_cast<int*>(base + o_gs);
   int* dperm = reinterpret_cast<int*>(base + o_table);
+  double* gconst = reinterpret_cast<double*>(base + o_gc);
+  group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs, mode, gconst);
+  h->launches += 1;
   bool done = false;
   if (fast) {
-    int* chunk_group = reinterpret_cast<int*>(base + o_cg);
-    pt.chunk_group = chunk_group;
-    pt.counters = reinterpret_cast<unsigned int*>(base + o_cnt);
-    pt.tile_done = reinterpret_cast<unsigned int*>(base + o_done);
-    pt.t1buf = reinterpret_cast<double*>(base + o_t1);
-    pt.totbuf = reinterpret_cast<float*>(base + o_tot);
-    TKBO_CUDA_CHECK(cudaMemsetAsync(base + o_cnt, 0, o_t1 - o_cnt, stream));      // unit counters + tile_done
-    group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs, pt.J, chunk_group);
-    h->launches += 1;
-    done = dispatch_all_perms(C, k, fchi, order, gs, S, Q, M, mode, h->sm_count, pt, out_mi, stream);
-  } else {
-    group_samples_kernel<<<1, 256, sizeof(int) * (M + 1), stream>>>(fstar_argmax, S, M, order, gs);
-    h->launches += 1;
+    TKBO_CUDA_CHECK(cudaMemsetAsync(base + o_cnt, 0, 256, stream));                // tile counters
+    done = dispatch_all_perms(C, k, fchi, order, gs, gconst, S, Q, M, mode, h->sm_count,
+                              reinterpret_cast<unsigned int*>(base + o_cnt), out_mi, stream);
   }
   if (!done) {
     const int32_t* table = perms;

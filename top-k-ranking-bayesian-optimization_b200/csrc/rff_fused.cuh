@@ -159,12 +159,41 @@ __device__ __forceinline__ float feature_cos(uint32_t arg_bits, bool skip) {
   return __cosf(__uint_as_float(arg_bits));
 }
 
+// cos on the FMA pipe: Cody-Waite reduction to [-pi, pi] (magic-number rint, 2 pi in two parts) and a degree-6 minimax
+// polynomial in r^2 (max error 3.3e-7, MUFU.COS: ~5e-7): 11 FMA-pipe instructions and no XU slot.  Meant for the shapes
+// the feature map binds (sample chunks <= 64: XU 74 % busy, FMA 25 %): a share of the features of every slab would take
+// this route so that both pipes fill up; kPolyMask = which of 16 consecutive features (bit e = element e).
+// MEASURED (B200, c2, same box): 0/16 features 0.369 ms, 4/16 0.420, 5/16 0.438, 6/16 0.452, 8/16 0.487 -- the
+// producers are bound by issue slots / dependent-instruction latency, not by the XU pipe alone, and every polynomial
+// costs nine instructions more than FMUL + MUFU.  Kept compiled out (mask 0) as a documented negative result.
+#ifndef TKBO_POLY_MASK
+#define TKBO_POLY_MASK 0x0u         // off: measured slower, see the comment above (0x4924u = elements 2, 5, 8, 11, 14)
+#endif
+constexpr uint32_t kPolyMask = TKBO_POLY_MASK;
+__device__ __forceinline__ float poly_cos(float x) {
+  const float nm = fmaf(x, 0.15915494309189535f, 12582912.f);      // + 1.5 * 2^23: the integer nearest to x / 2 pi
+  const float n = nm - 12582912.f;
+  float r = fmaf(n, -6.2831854820251465f, x);                        // 2 pi = 6.2831854820251465 - 1.7484555e-7
+  r = fmaf(n, 1.7484555e-7f, r);
+  const float u = r * r;
+  float p = fmaf(u, 1.724442811e-09f, -2.707885187e-07f);
+  p = fmaf(u, p, 2.476986447e-05f);
+  p = fmaf(u, p, -1.388780307e-03f);
+  p = fmaf(u, p, 4.166648909e-02f);
+  p = fmaf(u, p, -4.999998808e-01f);
+  return fmaf(u, p, 1.f);
+}
+
 // 16 projection values (fp32 bits) -> 8 packed fp16x2 hi words followed by 8 lo words: five instructions per feature
-// (FMUL.RZ + MUFU.COS, half an F2FP for hi, one FHFMA for the residual, half an F2FP for lo).
+// (FMUL.RZ + MUFU.COS, half an F2FP for hi, one FHFMA for the residual, half an F2FP for lo).  POLY: the features in
+// kPolyMask evaluate their cos on the FMA pipe instead.
+template <bool POLY = false>
 __device__ __forceinline__ void cos_split16(const uint32_t* __restrict__ arg, uint32_t (&out)[16], bool skip) {
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
-    const float c0 = feature_cos(arg[2 * jj], skip), c1 = feature_cos(arg[2 * jj + 1], skip);
+    const float c0 = (POLY && ((kPolyMask >> (2 * jj)) & 1u)) ? poly_cos(__uint_as_float(arg[2 * jj])) : feature_cos(arg[2 * jj], skip);
+    const float c1 = (POLY && ((kPolyMask >> (2 * jj + 1)) & 1u)) ? poly_cos(__uint_as_float(arg[2 * jj + 1]))
+                                                                  : feature_cos(arg[2 * jj + 1], skip);
     const __half2 h = __floats2half2_rn(c0, c1);
     const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
     float l0, l1;
@@ -517,7 +546,8 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const bool skip = (p.debug & 2) != 0;
     auto split16 = [](const uint32_t* a, uint32_t (&o)[16], bool sk) {
-      if constexpr (C8) cos_split16_c8(a, o, sk); else cos_split16(a, o, sk);
+      // four producer groups = the shapes bound by the feature map (XU pipe): part of the cos goes to the FMA pipe
+      if constexpr (C8) cos_split16_c8(a, o, sk); else cos_split16<NPG == 4>(a, o, sk);
     };
     if (NPG == 2 && p.coop) {
       // latency form: every slab is converted by both groups, group g taking columns [32 g, 32 g + 32)
