@@ -464,12 +464,12 @@ def k1_block(ctx, name, args, precision, steps, warmup, with_e2e, long_run, fact
 
         def e2e_step(i):
             if ctx.world == 1:
-                ff.argmax_host(W_h, b_h, T_h, host, device=ctx.local, out_val=res_val, out_idx=res_idx)
+                ff.argmax_host(W_h, b_h, T_h, host, device=ctx.local, out_val=res_val, out_idx=res_idx, precision=form)
             elif peer2 is not None:
                 ff.argmax_host(W_h, b_h, T_h, host, device=ctx.local, out_val=res_val, out_idx=res_idx, peer=peer2,
-                               idx_offset=lo_row)
+                               idx_offset=lo_row, precision=form)
             else:      # no peer mapping on this box: per-rank host call, then one all_reduce(MAX) of keys
-                ff.argmax_host(W_h, b_h, T_h, host, device=ctx.local, out_val=res_val, out_idx=res_idx)
+                ff.argmax_host(W_h, b_h, T_h, host, device=ctx.local, out_val=res_val, out_idx=res_idx, precision=form)
                 key = pkg.distributed.pack_argmax_key(res_val, res_idx + lo_row).to(ctx.dev, non_blocking=True)
                 ctx.dist.all_reduce(key, op=ctx.dist.ReduceOp.MAX)
                 key.cpu()
@@ -477,9 +477,9 @@ def k1_block(ctx, name, args, precision, steps, warmup, with_e2e, long_run, fact
 
         e2e_steps = max(3, min(steps, 20))
         e2e_ms = time_wall(ctx, e2e_step, e2e_steps, min(3, warmup))
-        # the host path's AUTO is the fp32 form; it must reproduce the device-resident result of the same buffer
+        # same contraction form as the device-resident loop: it must reproduce that result of the same buffer bit for bit
         same = None
-        if ctx.rank == 0 and form == "fp32":
+        if ctx.rank == 0:
             ref_v, ref_i = (peer.argmax(basis, dev_bufs[0], lo_row) if peer is not None else
                             (pkg.distributed.sharded_argmax_fast(basis, dev_bufs[0], lo_row) if ctx.world > 1
                              else basis.argmax(dev_bufs[0], idx_offset=lo_row)))

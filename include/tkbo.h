@@ -133,22 +133,23 @@ int tkbo_merge_argmax(tkbo_handle_t h, const float* vals, const int64_t* idx, in
                       float* out_val, int64_t* out_idx, void* stream);
 
 /* Host-buffer convenience wrapper around basis_set + argmax (copies inside, synchronous):
- * the end-to-end call a non-torch caller would make. All arrays are HOST pointers.  The fused kernel is launched once,
+ * the end-to-end call a non-torch caller would make. All arrays are HOST pointers.  `precision` = TKBO_PRECISION_* as for
+ * tkbo_rff_basis_create_ex (AUTO = FP32; a caller that can bound ||theta'|| / max|f| passes FAST).  The fused kernel is launched once,
  * right after the basis is prepared, and consumes the candidates in up to 16 chunks while their H2D copies (second
  * stream) are still landing -- pass pinned X for that overlap; pageable X works, its copies then run host-synchronously
  * behind the launch.  Returns TKBO_ERR_CUDA if a chunk fails to arrive within ~10 s (the kernel does not hang).
  * Profilers / sanitizers that serialise kernels against copies defeat the overlap (every launch would sit out its wait
  * limit): set TKBO_HOST_STREAMED=0 in the environment to queue all copies before the launch. */
 int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, const double* Theta,
-                         int D, int d, int S, const float* X, int64_t N, float* out_val, int64_t* out_idx);
+                         int D, int d, int S, const float* X, int64_t N, int precision, float* out_val, int64_t* out_idx);
 /* The same for one rank of a candidate-sharded job on one NVSwitch node: X [N, d] is this rank's shard (rows idx_offset ..
  * idx_offset + N of the global set), peer_bufs / world / rank / epoch as in tkbo_rff_argmax_peer.  One fused launch per call:
  * it streams the shard in, delivers this rank's keys to every peer, merges in its last CTA, and the GLOBAL S results come
  * back with a single D2H copy -- no collective call, no second launch.  Synchronous; returns TKBO_ERR_CUDA if a chunk or a
  * peer fails to arrive within ~10 s.  Every rank of the group must make the call with the same epoch. */
 int tkbo_rff_argmax_host_peer(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
-                              const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs, int world, int rank,
-                              uint64_t epoch, float* out_val, int64_t* out_idx);
+                              const float* X, int64_t N, int precision, int64_t idx_offset, void* const* peer_bufs, int world,
+                              int rank, uint64_t epoch, float* out_val, int64_t* out_idx);
 
 /* ---- per-sample-basis RFF (reference-exact shapes, float64 end to end) ----------------------------
  * X [count, n, d], W [count, D, d], b [count, D], theta [count, D]:

@@ -304,9 +304,20 @@ def test_rff_argmax_host_entry_point(pbo):
     idx = np.empty(40, dtype=np.int64)
     as_p = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
     Wc, bc, Tc = np.ascontiguousarray(W), np.ascontiguousarray(b), np.ascontiguousarray(Theta)
-    nat.check(nat.lib().tkbo_rff_argmax_host(nat.handle(0), as_p(Wc), as_p(bc), as_p(Tc), 128, 2, 40, as_p(X), 2500,
+    nat.check(nat.lib().tkbo_rff_argmax_host(nat.handle(0), as_p(Wc), as_p(bc), as_p(Tc), 128, 2, 40, as_p(X), 2500, 0,
                                              as_p(val), as_p(idx)), "argmax_host")
     _check_argmax(torch.from_numpy(val), torch.from_numpy(idx), X, W, b, Theta)
+    # the CUDA_LAUNCH_BLOCKING / profiler ordering (every copy queued before the launch) gives the same result
+    import os
+    os.environ["TKBO_HOST_STREAMED"] = "0"
+    try:
+        val2, idx2 = np.empty(40, dtype=np.float32), np.empty(40, dtype=np.int64)
+        nat.check(nat.lib().tkbo_rff_argmax_host(nat.handle(0), as_p(Wc), as_p(bc), as_p(Tc), 128, 2, 40, as_p(X), 2500, 0,
+                                                 as_p(val2), as_p(idx2)), "argmax_host")
+    finally:
+        del os.environ["TKBO_HOST_STREAMED"]
+    np.testing.assert_array_equal(val, val2)
+    np.testing.assert_array_equal(idx, idx2)
 
 
 def test_rff_argmax_host_chunked_pipeline(pbo):
@@ -325,6 +336,12 @@ def test_rff_argmax_host_chunked_pipeline(pbo):
         np.testing.assert_array_equal(v, val.cpu().numpy())
     # the winners sit in late chunks too: a kernel that read a chunk before it landed would miss them
     assert (idx.cpu().numpy() > 200000).any()
+    # explicit fast form through the host path == the device-resident fast form
+    fast = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0", precision="fast")
+    vf, if_ = fast.argmax(X)
+    v, i = pbo.fourier_features.argmax_host(W, b, Theta, Xp, precision="fast")
+    np.testing.assert_array_equal(i, if_.cpu().numpy())
+    np.testing.assert_array_equal(v, vf.cpu().numpy())
     X2, W2, b2, Theta2 = _basis_inputs(rng, 3000, 64, 3, 20, 0.0, 1.0, 0.4)
     v, i = pbo.fourier_features.argmax_host(W2, b2, Theta2, X2)
     val2, idx2 = pbo.fourier_features.SharedBasis(W2, b2, Theta2, device="cuda:0").argmax(X2)

@@ -40,9 +40,25 @@ def main():
         mine = Xl if rank < world - 1 else Xl[:0]
         val, idx = pm.argmax(basis, mine, lo)
         assert torch.equal(val, exp_val) and torch.equal(idx, exp_idx), f"rank {rank}: empty-shard merge differs"
-    # timing: merge overhead per iteration, both ways
+    # delivery + separate merge launch gives the same bits as the merge in the kernel's last CTA
+    for it in range(3):
+        val, idx = pm.argmax(basis, Xl, lo, fused=False)
+        assert torch.equal(val, ref_val) and torch.equal(idx, ref_idx), f"rank {rank}: two-launch peer merge differs"
+    # host-buffer form (tkbo_rff_argmax_host_peer): pinned shard + fp64 basis in, global results out, one launch per rank
+    pm2 = pkg.distributed.PeerMerge(S, dev)
+    Xh = torch.from_numpy(X[lo:hi].copy()).pin_memory()
+    precise = pkg.fourier_features.SharedBasis(W, b, T, device=dev, precision="fp32")      # the host path's form
+    pv, pi = precise.argmax(torch.from_numpy(X).to(dev))
+    for it in range(4):
+        hv, hi_ = pkg.fourier_features.argmax_host(W, b, T, Xh, device=local, peer=pm2, idx_offset=lo)
+        assert np.array_equal(hv, pv.cpu().numpy()) and np.array_equal(hi_, pi.cpu().numpy()), f"rank {rank}: host_peer differs"
+    torch.cuda.synchronize()
+    pm.check()
+    pm2.check()
+    # timing: merge overhead per iteration, three ways
     out = {}
-    for name, fn in (("peer", lambda: pm.argmax(basis, Xl, lo)), ("nccl", lambda: pkg.distributed.sharded_argmax_fast(basis, Xl, lo))):
+    for name, fn in (("peer_fused", lambda: pm.argmax(basis, Xl, lo)), ("peer_two_launches", lambda: pm.argmax(basis, Xl, lo, fused=False)),
+                     ("nccl", lambda: pkg.distributed.sharded_argmax_fast(basis, Xl, lo))):
         for _ in range(5):
             fn()
         dist.barrier(); torch.cuda.synchronize()

@@ -44,7 +44,7 @@ _SIGNATURES = {
     "tkbo_peer_buffer_bytes": (c_i64, [c_i, c_i]),
     "tkbo_rff_argmax_peer": (c_i, [c_p, c_p, c_p, c_i64, c_i64, ctypes.POINTER(c_p), c_i, c_i, ctypes.c_uint64, c_p, c_p, c_p]),
     "tkbo_peer_status": (c_i64, [c_p]),
-    "tkbo_rff_argmax_host_peer": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i64, c_i64, ctypes.POINTER(c_p), c_i, c_i,
+    "tkbo_rff_argmax_host_peer": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i64, c_i, c_i64, ctypes.POINTER(c_p), c_i, c_i,
                                         ctypes.c_uint64, c_p, c_p]),
     "tkbo_merge_peer_keys": (c_i, [c_p, c_p, c_i, c_i, ctypes.c_uint64, c_p, c_p, c_p]),
     "tkbo_peer_push_keys": (c_i, [c_p, c_p, c_i, ctypes.POINTER(c_p), c_i, c_i, ctypes.c_uint64, c_p]),
@@ -54,7 +54,7 @@ _SIGNATURES = {
     "tkbo_unpack_argmax_key": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p]),
     "tkbo_rff_eval": (c_i, [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p]),
     "tkbo_merge_argmax": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
-    "tkbo_rff_argmax_host": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i64, c_p, c_p]),
+    "tkbo_rff_argmax_host": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i64, c_i, c_p, c_p]),
     "tkbo_rff_eval_batched": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "tkbo_rff_features_batched": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "tkbo_rff_ascent_batched": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, c_i, c_d, c_d, c_d,

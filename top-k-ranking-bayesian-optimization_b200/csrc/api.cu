@@ -347,11 +347,12 @@ static int host_argmax_attempt(tkbo_handle_t h, const double* W, const double* b
 
 // Shared body of tkbo_rff_argmax_host / tkbo_rff_argmax_host_peer (peer_bufs == nullptr: single rank).
 static int host_argmax(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
-                       const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs, int world, int rank,
-                       uint64_t epoch, float* out_val, int64_t* out_idx) {
+                       const float* X, int64_t N, int precision, int64_t idx_offset, void* const* peer_bufs, int world,
+                       int rank, uint64_t epoch, float* out_val, int64_t* out_idx) {
   if (!W || !b || !Theta || !X || !out_val || !out_idx) { set_error("null pointer"); return TKBO_ERR_INVALID; }
   if (N < 1) { set_error("N must be >= 1"); return TKBO_ERR_INVALID; }
   if (N >= (int64_t(1) << 32) - 256) { set_error("N must be below 2^32 - 256"); return TKBO_ERR_INVALID; }
+  if (precision < TKBO_PRECISION_AUTO || precision > TKBO_PRECISION_FAST) { set_error("unknown precision"); return TKBO_ERR_INVALID; }
   auto& hp = h->host;
   if (!hp.exec_stream) {
     TKBO_CUDA_CHECK(cudaStreamCreateWithFlags(&hp.exec_stream, cudaStreamNonBlocking));
@@ -360,11 +361,11 @@ static int host_argmax(tkbo_handle_t h, const double* W, const double* b, const 
     TKBO_CUDA_CHECK(cudaHostAlloc(&hp.hflag, kHostChunksMax * sizeof(unsigned int), cudaHostAllocDefault));
     for (int k = 0; k < kHostChunksMax; ++k) hp.hflag[k] = static_cast<unsigned int>(k + 1);
   }
-  if (!hp.basis || hp.D != D || hp.d != d || hp.S != S) {
+  if (!hp.basis || hp.D != D || hp.d != d || hp.S != S || hp.precision != precision) {
     if (hp.basis) { basis_destroy(h, hp.basis); hp.basis = nullptr; }
-    int rc = basis_create(h, &hp.basis, D, d, S, TKBO_PRECISION_AUTO);
+    int rc = basis_create(h, &hp.basis, D, d, S, precision);
     if (rc != TKBO_OK) return rc;
-    hp.D = D; hp.d = d; hp.S = S;
+    hp.D = D; hp.d = d; hp.S = S; hp.precision = precision;
   }
   const size_t nb = static_cast<size_t>(D) * d + D + static_cast<size_t>(D) * S;
   if (hp.dbasis_doubles < nb) {
@@ -418,17 +419,17 @@ static int host_argmax(tkbo_handle_t h, const double* W, const double* b, const 
 extern "C" {
 
 int tkbo_rff_argmax_host(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
-                         const float* X, int64_t N, float* out_val, int64_t* out_idx) {
+                         const float* X, int64_t N, int precision, float* out_val, int64_t* out_idx) {
   TKBO_ENTER(h);
-  return host_argmax(h, W, b, Theta, D, d, S, X, N, 0, nullptr, 0, 0, 0, out_val, out_idx);
+  return host_argmax(h, W, b, Theta, D, d, S, X, N, precision, 0, nullptr, 0, 0, 0, out_val, out_idx);
 }
 
 int tkbo_rff_argmax_host_peer(tkbo_handle_t h, const double* W, const double* b, const double* Theta, int D, int d, int S,
-                              const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs, int world, int rank,
-                              uint64_t epoch, float* out_val, int64_t* out_idx) {
+                              const float* X, int64_t N, int precision, int64_t idx_offset, void* const* peer_bufs, int world,
+                              int rank, uint64_t epoch, float* out_val, int64_t* out_idx) {
   TKBO_ENTER(h);
   if (!peer_bufs) { set_error("null peer buffers"); return TKBO_ERR_INVALID; }
-  return host_argmax(h, W, b, Theta, D, d, S, X, N, idx_offset, peer_bufs, world, rank, epoch, out_val, out_idx);
+  return host_argmax(h, W, b, Theta, D, d, S, X, N, precision, idx_offset, peer_bufs, world, rank, epoch, out_val, out_idx);
 }
 
 int tkbo_rff_eval_batched(tkbo_handle_t h, const double* X, const double* W, const double* b, const double* theta,

@@ -47,7 +47,7 @@ struct tkbo_handle_s {
   // persistent state of the host-buffer entry point (tkbo_rff_argmax_host): basis + device staging, reused across calls
   struct HostPath {
     tkbo_basis_s* basis = nullptr;
-    int D = 0, d = 0, S = 0;
+    int D = 0, d = 0, S = 0, precision = 0;
     double* dbasis = nullptr;            // W | b | Theta as float64
     size_t dbasis_doubles = 0;
     float* dX = nullptr;                 // all N candidates; filled chunk by chunk while the kernel already runs

@@ -214,7 +214,7 @@ def sample_maximizers(X, count, n_init, D, model, min_val, max_val, num_steps=30
 # ---------------------------------------------------------------------------------------------------
 # shared-basis fast path
 # ---------------------------------------------------------------------------------------------------
-def argmax_host(W, b, Theta, X, device=0, out_val=None, out_idx=None, peer=None, idx_offset=0):
+def argmax_host(W, b, Theta, X, device=0, out_val=None, out_idx=None, peer=None, idx_offset=0, precision="auto"):
     """End-to-end host-buffer call (C ABI ``tkbo_rff_argmax_host``): W (D, d), b (D,), Theta (D, S) float64 and the
     candidates X (N, d) float32 are HOST arrays (NumPy, or CPU torch tensors - with pinned memory the single kernel
     launch consumes the candidate chunks while their H2D copies are still landing); returns (val[S] float32,
@@ -222,7 +222,8 @@ def argmax_host(W, b, Theta, X, device=0, out_val=None, out_idx=None, peer=None,
     Device staging and the basis layout are cached on the handle between calls of the same shape.
     ``peer`` (a distributed.PeerMerge) + ``idx_offset``: X is this rank's shard of a sharded candidate set and the results
     are the GLOBAL ones (``tkbo_rff_argmax_host_peer``: the same single launch also delivers the keys to the peers and
-    merges; every rank of the group must make the call)."""
+    merges; every rank of the group must make the call).  ``precision``: "auto" / "fp32" = the fp32-emulating form,
+    "fast" = the e4m3 correction form (see SharedBasis; the caller vouches for ||theta'|| / max|f|)."""
     def host(a, dtype):
         if hasattr(a, "data_ptr"):
             assert a.device.type == "cpu" and a.is_contiguous()
@@ -243,13 +244,15 @@ def argmax_host(W, b, Theta, X, device=0, out_val=None, out_idx=None, peer=None,
     dev = device if isinstance(device, int) else _device(device).index
     if peer is None:
         nat.check(nat.lib().tkbo_rff_argmax_host(nat.handle(dev), ctypes.c_void_p(Wp), ctypes.c_void_p(bp), ctypes.c_void_p(Tp),
-                                                 int(D), int(d), int(S), ctypes.c_void_p(Xp), int(Xs[0]), ctypes.c_void_p(vp),
+                                                 int(D), int(d), int(S), ctypes.c_void_p(Xp), int(Xs[0]),
+                                                 SharedBasis.PRECISIONS[precision], ctypes.c_void_p(vp),
                                                  ctypes.c_void_p(ip)), "tkbo_rff_argmax_host")
     else:
         peer.epoch += 1
         nat.check(nat.lib().tkbo_rff_argmax_host_peer(nat.handle(dev), ctypes.c_void_p(Wp), ctypes.c_void_p(bp),
                                                       ctypes.c_void_p(Tp), int(D), int(d), int(S), ctypes.c_void_p(Xp),
-                                                      int(Xs[0]), int(idx_offset), peer._ptrs, peer.world, peer.rank,
+                                                      int(Xs[0]), SharedBasis.PRECISIONS[precision], int(idx_offset), peer._ptrs,
+                                                      peer.world, peer.rank,
                                                       peer.epoch, ctypes.c_void_p(vp), ctypes.c_void_p(ip)),
                   "tkbo_rff_argmax_host_peer")
     return val, idx
