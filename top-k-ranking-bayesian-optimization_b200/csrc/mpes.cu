@@ -148,7 +148,11 @@ struct PermWalk {
 // At every group boundary the warps add their partial sums into a block-shared accumulator and the group is folded once.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRing = 4;
-constexpr int kMpesWarps = 8;
+#ifndef TKBO_MPES_WARPS
+#define TKBO_MPES_WARPS 4           // measured on B200 at c5 (skewed groups, same box): 4 warps 1.25 ms, 8 warps 1.34 ms
+#endif
+constexpr int kMpesWarps = TKBO_MPES_WARPS;
+constexpr int kMpesBlocksPerSm = 16 / kMpesWarps;     // 16 warps of 128 registers fill the register file
 __host__ __device__ constexpr int mpes_warp_smem_bytes(int C) {
   return ((kRing * 32 * C * 4 + kRing * 8 + 127) / 128) * 128;
 }
@@ -211,7 +215,7 @@ __device__ __forceinline__ double table_log(const LogTable& tab, float a) {
 // 1e-4 of a typical MI.  The grid value is what the fold uses AND what is summed into tot_z.
 // At the end of the tile  MI = sum_w A_w  with  A_w = sum_m (fold terms of w's orderings) - sum_{z of w} p_z log p_z.
 template <int C, int K, bool STAGED>
-__global__ void __launch_bounds__(32 * kMpesWarps, 2)
+__global__ void __launch_bounds__(32 * kMpesWarps, kMpesBlocksPerSm)
 mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ order, const int* __restrict__ group_start,
                       const double* __restrict__ group_const, int S, long long Q, int M, int mode, int tile_begin,
                       int tile_end, unsigned int* __restrict__ tile_counter, double* __restrict__ out_mi) {
@@ -646,13 +650,15 @@ static void launch_all_perms(const float* fchi, const int* order, const int* gs,
   const int64_t staged_tiles = aligned ? Q / 32 : 0;
   const int threads = 32 * kMpesWarps;
   const int smem = kMpesWarps * mpes_warp_smem_bytes(C);
+  cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (staged_tiles > 0) {
-    const int grid = static_cast<int>(std::min<int64_t>(2 * sm_count, staged_tiles));
+    const int grid = static_cast<int>(std::min<int64_t>(kMpesBlocksPerSm * sm_count, staged_tiles));
     mpes_all_perms_kernel<C, K, true><<<grid, threads, smem, stream>>>(fchi, order, gs, gconst, S, Q, M, mode, 0,
                                                                    static_cast<int>(staged_tiles), counters, out);
   }
   if (staged_tiles < tiles) {
-    const int grid = static_cast<int>(std::min<int64_t>(2 * sm_count, tiles - staged_tiles));
+    const int grid = static_cast<int>(std::min<int64_t>(kMpesBlocksPerSm * sm_count, tiles - staged_tiles));
     mpes_all_perms_kernel<C, K, false><<<grid, threads, smem, stream>>>(fchi, order, gs, gconst, S, Q, M, mode,
                                                                     static_cast<int>(staged_tiles), static_cast<int>(tiles),
                                                                     counters + 1, out);
