@@ -861,7 +861,8 @@ def test_large_shape_properties_tensor_bound_form(pbo):
     X = torch.rand((N, d), device="cuda:0")
     basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0", precision="fast")
     cfg = basis.config(N)
-    assert cfg["e4m3_corrections"] == 1 and cfg["w_stages"] >= 2 and cfg["S_chunk"] == 256 and cfg["stages"] == 3
+    assert cfg["e4m3_corrections"] == 1 and cfg["S_chunk"] == 256
+    assert (cfg["cta_pairs"] == 1 and cfg["stages"] >= 5) or (cfg["w_stages"] >= 2 and cfg["stages"] == 3)
     val, idx = basis.argmax(X)
     perm = torch.randperm(N, device="cuda:0")
     val_p, idx_p = basis.argmax(X[perm].contiguous())

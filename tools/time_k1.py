@@ -15,6 +15,9 @@ from oracle import rff_oracle  # noqa: E402
 pkg = importlib.import_module("top-k-ranking-bayesian-optimization_b200")
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 form = sys.argv[2] if len(sys.argv) > 2 else "fp32"
+if name.startswith("custom:"):          # custom:N,d,D,S  (uniform candidates in [0, 1]^d, lengthscale 0.2)
+    cn, cd, cD, cS = (int(v) for v in name[7:].split(","))
+    bench.WORKLOADS[name] = dict(N=cn, d=cd, D=cD, S=cS, lo=0.0, hi=1.0, ls=0.2, desc=name)
 w = bench.WORKLOADS[name]
 rows = int(sys.argv[3]) if len(sys.argv) > 3 else min(w["N"], 1 << 21)
 dev = torch.device("cuda", 0)

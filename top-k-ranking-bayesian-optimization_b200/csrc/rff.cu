@@ -18,6 +18,8 @@ namespace cg = cooperative_groups;
 
 namespace tkbo {
 
+constexpr bool kPairDefault = true;     // CTA pairs (cta_group::2) wherever they apply: 4-18 % faster on B200; TKBO_PAIR=0 switches them off
+
 // ------------------------------------------------------------------------------------------------
 // operand preparation (once per BO iteration; not the hot path)
 // ------------------------------------------------------------------------------------------------
@@ -313,11 +315,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // [Salloc, Dpad] fp16 (or, bytes = true, the [Salloc, 2 Dpad] e4m3 correction tile); box = SC rows x 128 bytes.
-static int make_theta_map(tkbo_handle_t h, CUtensorMap* map, void* base, int Salloc, int Dpad, int SC, bool bytes = false) {
+static int make_theta_map(tkbo_handle_t h, CUtensorMap* map, void* base, int Salloc, int Dpad, int box_rows, bool bytes = false) {
   auto fn = reinterpret_cast<EncodeTiledFn>(h->encode_tiled);
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(bytes ? 2 * Dpad : Dpad), static_cast<cuuint64_t>(Salloc)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Dpad) * sizeof(__half)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(bytes ? 2 * kSlabK : kSlabK), static_cast<cuuint32_t>(SC)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(bytes ? 2 * kSlabK : kSlabK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estride[2] = {1, 1};
   CUresult r = fn(map, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstride, box, estride,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -331,13 +333,13 @@ static int make_theta_map(tkbo_handle_t h, CUtensorMap* map, void* base, int Sal
 
 // (W | b) projection rows: [Dpad, KA] bf16, box = one slab (64 features) x one 64-wide (or narrower) K block,
 // swizzle span = the box row.
-static int make_wproj_map(tkbo_handle_t h, CUtensorMap* map, uint16_t* base, int Dpad, int DT) {
+static int make_wproj_map(tkbo_handle_t h, CUtensorMap* map, uint16_t* base, int Dpad, int DT, int box_rows = kSlabK) {
   auto fn = reinterpret_cast<EncodeTiledFn>(h->encode_tiled);
   const int KA = proj_k_alloc(DT);
   const int row_bytes = proj_row_bytes(DT);
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(KA), static_cast<cuuint64_t>(Dpad)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(KA) * sizeof(uint16_t)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(row_bytes / 2), static_cast<cuuint32_t>(kSlabK)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(row_bytes / 2), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estride[2] = {1, 1};
   const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -448,6 +450,32 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
       }
     }
   }
+  // CTA pairs (rff_fused.cuh, PAIR): two CTAs of a cluster share every tcgen05.mma (M = 256), each fetching half of the B
+  // operands.  Needs the split candidate rows in TMEM (not the four-group form) and an even SM count; a stage is half as
+  // large, so the combined ring is deep enough without the separate (W | b) ring.  TKBO_PAIR=0/1 overrides the default.
+  bs->pair = 0;
+  {
+    const char* env = getenv("TKBO_PAIR");
+    const bool want = env != nullptr ? atoi(env) != 0 : kPairDefault;
+    if (want && bs->npg != 4 && bs->SC >= 64 && h->sm_count % 2 == 0) {
+      // the halved stages leave room for the split candidate rows in shared memory (two buffers), which frees their TMEM
+      // columns for one more ring slot: the cross-CTA hand-offs add latency to the projection -> producers -> main MMA
+      // loop, and that loop has to fit in ring x slab time
+      const int stride_p = pair_stage_stride_bytes(bs->SC, DT);
+      int st = std::min(kMaxStages, (smem_limit - 2 * proj_x_bytes(DT)) / stride_p);
+      const int ring = std::min(kMaxRing, (kTmemCols - bs->acc_bufs * bs->SC) / kSlabK);
+      if (st >= 3 && ring >= 3) {
+        bs->pair = 1; bs->stages = st; bs->wstages = 0; bs->proj_warps = 1; bs->coop = 0; bs->xa_bufs = 2;
+        bs->ring = std::min(ring, st);
+        // three producer groups once the ring has a slot for each; at the widest chunk (one accumulator, ring of 4) two
+        // groups measured 1 % faster
+        bs->npg = (bs->ring >= 5 || (bs->ring == 4 && bs->SC <= 192)) ? 3 : 2;
+        if (const char* e2 = getenv("TKBO_NPG")) { const int t = atoi(e2); if (t == 2 || t == 3) bs->npg = t; }
+        if (const char* e3 = getenv("TKBO_COOP")) bs->coop = (bs->npg == 2 && atoi(e3) != 0) ? 1 : 0;
+        bs->smem_bytes = st * stride_p + 2 * proj_x_bytes(DT) + 1024;
+      }
+    }
+  }
   // Precision of the contraction (include/tkbo.h).  AUTO is the fp32-emulating three-MMA form: the e4m3 correction form
   // (two thirds of the tensor work, ~3e-5 of max|f| on well-posed weights) is only safe when ||theta'|| / max|f| is small,
   // which the library cannot know -- callers that can bound it (fourier_features.SharedBasis) ask for FAST explicitly.
@@ -466,9 +494,10 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
     free_basis(bs);
     return TKBO_ERR_NOMEM;
   }
-  int rc = make_theta_map(h, &bs->tm_hi, bs->theta_hi, bs->Salloc, bs->Dpad, bs->SC);
-  if (rc == TKBO_OK) rc = make_theta_map(h, &bs->tm_lo, bs->theta_lo, bs->Salloc, bs->Dpad, bs->SC, bs->corr8 != 0);
-  if (rc == TKBO_OK) rc = make_wproj_map(h, &bs->tm_w, bs->Wproj, bs->Dpad, DT);
+  const int th_rows = bs->pair ? bs->SC / 2 : bs->SC;
+  int rc = make_theta_map(h, &bs->tm_hi, bs->theta_hi, bs->Salloc, bs->Dpad, th_rows);
+  if (rc == TKBO_OK) rc = make_theta_map(h, &bs->tm_lo, bs->theta_lo, bs->Salloc, bs->Dpad, th_rows, bs->corr8 != 0);
+  if (rc == TKBO_OK) rc = make_wproj_map(h, &bs->tm_w, bs->Wproj, bs->Dpad, DT, bs->pair ? kSlabK / 2 : kSlabK);
   if (rc != TKBO_OK) {
     free_basis(bs);
     return rc;
@@ -498,6 +527,26 @@ int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b
 
 template <int DT, int MODE, int NPG, bool C8>
 static int launch_fused_c(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  if constexpr (NPG != 4) {
+    if (bs->pair) {
+      // clusters of two CTAs (one TPC): an even grid, one item stream per pair
+      auto kern = rff_fused_kernel<DT, MODE, NPG, C8, true>;
+      TKBO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs->smem_bytes));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+      cfg.blockDim = dim3(kNumThreadsFor(NPG), 1, 1);
+      cfg.dynamicSmemBytes = static_cast<size_t>(bs->smem_bytes);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      TKBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, bs->tm_hi, bs->tm_lo, bs->tm_w, p));
+      h->launches += 1;
+      return TKBO_OK;
+    }
+  }
   auto kern = rff_fused_kernel<DT, MODE, NPG, C8>;
   TKBO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs->smem_bytes));
   kern<<<grid, kNumThreadsFor(NPG), bs->smem_bytes, stream>>>(bs->tm_hi, bs->tm_lo, bs->tm_w, p);
@@ -535,6 +584,12 @@ static int dispatch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, 
   return TKBO_ERR_UNSUPPORTED;
 }
 
+// CTAs of a launch over `mt` candidate tiles: one per SM and item, or (pairs) two per pair of tiles and chunk, always even
+static int fused_grid(tkbo_handle_t h, tkbo_basis_t bs, int64_t mt) {
+  if (bs->pair) return static_cast<int>(std::min<int64_t>(h->sm_count & ~1, 2 * ((mt + 1) / 2) * bs->n_chunks));
+  return static_cast<int>(std::min<int64_t>(h->sm_count, mt * bs->n_chunks));
+}
+
 static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, RffParams* p, int* grid) {
   TKBO_REQUIRE(h && bs && X, "null pointer");
   TKBO_REQUIRE(bs->is_set, "basis has no data: call tkbo_rff_basis_set first");
@@ -556,7 +611,8 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->debug = 0;
   if (const char* env = getenv("TKBO_DEBUG")) p->debug = atoi(env);
   p->trace = h->trace; p->trace_cap = h->trace_cap;
-  *grid = static_cast<int>(std::min<int64_t>(h->sm_count, mt * bs->n_chunks));
+  p->pair = bs->pair;
+  *grid = fused_grid(h, bs, mt);
   return TKBO_OK;
 }
 
@@ -852,7 +908,8 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   p.score_fix = reinterpret_cast<unsigned long long*>(fix);
   p.debug = 0;
   p.trace = nullptr; p.trace_cap = 0;
-  const int grid = static_cast<int>(std::min<int64_t>(h->sm_count, mt * bs->n_chunks));
+  p.pair = bs->pair;
+  const int grid = fused_grid(h, bs, mt);
   return dispatch_fused<2>(h, bs, p, grid, stream);
 }
 
@@ -886,8 +943,8 @@ int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg) {
   const int64_t mt = (N + kTileM - 1) / kTileM;
   cfg[0] = bs->SC; cfg[1] = bs->n_chunks; cfg[2] = bs->Dpad / kSlabK; cfg[3] = bs->stages; cfg[4] = bs->acc_bufs;
   cfg[5] = bs->DT; cfg[6] = bs->smem_bytes;
-  cfg[7] = static_cast<int32_t>(std::min<int64_t>(h->sm_count, std::max<int64_t>(1, mt) * bs->n_chunks));
-  cfg[8] = bs->ring; cfg[9] = kNumThreadsFor(bs->npg); cfg[10] = bs->xa_bufs; cfg[11] = bs->npg; cfg[12] = bs->proj_warps; cfg[13] = bs->corr8; cfg[14] = bs->wstages; cfg[15] = bs->coop;
+  cfg[7] = fused_grid(h, bs, std::max<int64_t>(1, mt));
+  cfg[8] = bs->ring; cfg[9] = kNumThreadsFor(bs->npg); cfg[10] = bs->xa_bufs; cfg[11] = bs->npg; cfg[12] = bs->proj_warps; cfg[13] = bs->corr8; cfg[14] = bs->wstages; cfg[15] = bs->coop + 2 * bs->pair;
   return TKBO_OK;
 }
 

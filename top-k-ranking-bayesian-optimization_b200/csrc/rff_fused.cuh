@@ -69,7 +69,14 @@ __host__ __device__ constexpr int stage_stride_bytes(int SC, int DT) {
   return ((stage_tx_bytes(SC, DT) + 1023) / 1024) * 1024;
 }
 
-// With four producer groups (small sample chunks, where the SFU binds) the split candidate rows live in shared memory
+// CTA pairs (PAIR, cta_group::2): every CTA holds HALF of a stage's Theta rows (SC / 2) and half of the slab's (W | b)
+// rows (32 features); the pair's MMAs of M = 256 read both halves.
+__host__ __device__ constexpr int pair_stage_tx_bytes(int SC, int DT) { return SC * 128 + proj_w_bytes(DT) / 2; }
+__host__ __device__ constexpr int pair_stage_stride_bytes(int SC, int DT) {
+  return ((pair_stage_tx_bytes(SC, DT) + 1023) / 1024) * 1024;
+}
+
+// With four producer groups (small sample chunks, where the SFU binds) and with CTA pairs the split candidate rows live in shared memory
 // instead of TMEM, which frees the columns of a sixth ring slot: 128 rows in the same K-major swizzled tile format as
 // the (W | b) tile, two buffers after the stage ring; the projection MMA then takes both operands from shared memory.
 __host__ __device__ constexpr int proj_x_bytes(int DT) { return kTileM * proj_row_bytes(DT) * proj_tiles(DT); }
@@ -118,6 +125,7 @@ struct RffParams {
                              // per-slab latency, for shapes whose TMEM ring has only 3 slots
   int wstages;               // 0: the (W | b) tile of a slab travels in its Theta stage; > 0: it has its own ring of this
                              // depth, so projections + feature producers run ahead of the (few, large) Theta stages
+  int pair;                  // 1: launched as clusters of two CTAs that share every tcgen05.mma (template PAIR)
   int duel_n;                // > 0: the candidates are the ordered pairs [x_i, x_j] of duel_n base points of dimension d / 2
                              // held in X (dts.py:31-45); a tile = one i and 128 consecutive j; never materialised
   int duel_j0, duel_nj;      // this launch's shard of the second argument: j in [duel_j0, duel_j0 + duel_nj)
@@ -246,17 +254,24 @@ __device__ __forceinline__ void bf16_split3(float x, uint32_t& b1, uint32_t& b2,
   b3 = __float_as_uint(r2) >> 16;
 }
 
+// PAIR (clusters of two CTAs, cta_group::2): a work item is TWO adjacent 128-candidate tiles x one sample chunk.  Each CTA
+// keeps its own rows end to end (staging, producers, epilogue, TMEM), but every tcgen05.mma is issued once, by the leader
+// CTA, with M = 256: the B operands (Theta tiles, (W | b) tile) are fetched half by each CTA, so the L2 -> shared-memory
+// traffic and the shared-memory reads per SM halve and a stage is half as large (twice as many fit).  Cross-CTA hand-offs:
+// TMA of both CTAs completes on the leader's b_full; the peer's producer / staging / epilogue warps arrive on the leader's
+// a_full / xa_full / acc_empty through the cluster address space; the leader's commits are multicast to both CTAs'
+// p_full / b_empty / acc_full.
 template <int DT, int MODE /* 0 = argmax, 1 = store F, 2 = duel soft-Copeland sums */, int NPG /* producer warp groups: 2, 3 or 4 */,
-          bool C8 /* corrections as one e4m3 MMA (tm_lo = the e4m3 tile) instead of two fp16 MMAs */>
+          bool C8 /* corrections as one e4m3 MMA (tm_lo = the e4m3 tile) instead of two fp16 MMAs */, bool PAIR = false>
 __global__ void __launch_bounds__(kNumThreadsFor(NPG), 1)
 rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                  const __grid_constant__ CUtensorMap tm_w, const RffParams p) {
   constexpr int kPUsed = proj_k_used(DT);
   constexpr int kPCols = proj_k_alloc(DT) / 2;       // 32-bit words of one split candidate row = TMEM columns of one buffer
-  constexpr bool kXSmem = (NPG == 4);                // split candidate rows in shared memory (else in TMEM)
+  constexpr bool kXSmem = (NPG == 4) || PAIR;        // split candidate rows in shared memory (else in TMEM)
   constexpr int kXBytes = proj_x_bytes(DT);
   constexpr int kPRow = proj_row_bytes(DT);
-  constexpr int kPTile = kSlabK * kPRow;
+  constexpr int kPTile = (PAIR ? kSlabK / 2 : kSlabK) * kPRow;     // bytes of one 64-wide K block of the (W | b) rows held here
   extern __shared__ uint8_t smem_raw[];
 
   // mbarriers, addressed as bar0 + 8 * index in the hot loops
@@ -285,9 +300,14 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const int acc_bufs = p.acc_bufs, xa_bufs = p.xa_bufs;
   const int wstages = p.wstages;
   const bool split_w = wstages > 0;
-  const int sbytes = split_w ? 2 * SC * 128 : stage_stride_bytes(SC, DT);
-  const int n_items = p.n_mtiles * n_chunks;
-  const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int sbytes = PAIR ? pair_stage_stride_bytes(SC, DT) : (split_w ? 2 * SC * 128 : stage_stride_bytes(SC, DT));
+  const uint32_t cta = PAIR ? cluster_ctarank() : 0u;              // 0 = leader of the pair
+  const bool leader = (cta == 0u);
+  const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);      // item stream of this CTA / pair
+  const int n_units = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int n_items = (PAIR ? (p.n_mtiles + 1) / 2 : p.n_mtiles) * n_chunks;
+  const int my_items = (n_items - unit + n_units - 1) / n_units;
+  const int th_rows = PAIR ? SC / 2 : SC;                          // Theta rows of a stage held by this CTA
   const int total = my_items * n_slabs;              // slab iterations of this CTA
   const uint32_t bar0 = smem_u32(bars);
   // 1024-byte alignment for the 128B-swizzled tiles
@@ -296,20 +316,20 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&bars[kBFull + s], 1);
-      mbar_init(&bars[kBEmpty + s], 2);      // one commit per main MMA warp
+      mbar_init(&bars[kBEmpty + s], PAIR ? 1 : 2);      // one commit per main MMA warp
     }
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&bars[kPFull + s], 1);
-      mbar_init(&bars[kAFull + s], p.coop ? 8 : 4);   // one arrival per producer warp working on the slab
+      mbar_init(&bars[kAFull + s], (p.coop ? 8 : 4) * (PAIR ? 2 : 1));   // one arrival per producer warp working on the slab
     }
     for (int s = 0; s < kMaxWStages; ++s) {
       mbar_init(&bars[kWFull + s], 1);
       mbar_init(&bars[kWEmpty + s], 1);      // one commit by the projection warp that used it
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&bars[kAccFull + a], 2);     // one commit per main MMA warp
-      mbar_init(&bars[kAccEmpty + a], 4);    // one arrival per epilogue warp
-      mbar_init(&bars[kXaFull + a], 4);
+      mbar_init(&bars[kAccFull + a], PAIR ? 1 : 2);     // one commit per main MMA warp
+      mbar_init(&bars[kAccEmpty + a], PAIR ? 8 : 4);    // one arrival per epilogue warp (of both CTAs)
+      mbar_init(&bars[kXaFull + a], PAIR ? 8 : 4);
     }
     fence_mbar_init();
   }
@@ -317,18 +337,22 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   constexpr int kProjWarp = kTmaWarp + 1;            // kProjWarps of them
   constexpr int kProjWarps = kProjWarpsFor(NPG);
   constexpr int kMainWarp = kProjWarp + kProjWarps;  // and + 1
-  if (warp == kMainWarp) tmem_alloc(&tmem_base_smem, kTmemCols);
+  if (warp == kMainWarp) {
+    if constexpr (PAIR) tmem_alloc_pair(&tmem_base_smem, kTmemCols); else tmem_alloc(&tmem_base_smem, kTmemCols);
+  }
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tm_hi);
     tma_prefetch_desc(&tm_lo);
     tma_prefetch_desc(&tm_w);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();    // barriers initialised (cluster-wide) + TMEM allocated
   tc_fence_after();
+  // barriers of the leader as seen from either CTA (the peer arrives there); in the leader these are its own
+  const uint32_t bar0_lead = PAIR ? mapa_shared(bar0, 0u) : bar0;
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t xa_col0 = acc_bufs * SC;                         // split candidate rows follow the accumulators (TMEM form)
-  const uint32_t w_smem0 = smem0 + stages * sbytes;               // split mode: the (W | b) ring follows the Theta stages
+  const uint32_t w_smem0 = smem0 + stages * sbytes;               // split mode: the (W | b) ring follows the Theta stages (never with PAIR)
   const uint32_t xa_smem0 = w_smem0 + wstages * proj_w_bytes(DT); // candidate rows, smem form: two buffers after the rings
   const uint32_t ring_col0 = kTmemCols - ring * kSlabK;           // the ring occupies the top columns
 
@@ -346,9 +370,29 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 #pragma unroll
       for (int t = 0; t < proj_tiles(DT); ++t) tma_load_2d(dst + t * kPTile, &tm_w, full, t * 64, slab_w * kSlabK);
     };
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = unit; item < n_items; item += n_units) {
       const int chunk = item % n_chunks;
       for (int slab = 0; slab < n_slabs; ++slab, ++it) {
+        if constexpr (PAIR) {
+          // both CTAs: wait for the stage to be free here (the leader's commit is multicast), fetch this CTA's half of the
+          // Theta rows and of the (W | b) rows; every byte of the pair completes on the LEADER's b_full
+          mbar_wait(bar0 + 8 * (kBEmpty + st), ph ^ 1);
+          if (elect_one()) {
+            const uint32_t sb = smem0 + st * sbytes;
+            const uint32_t full_c = bar0_lead + 8 * (kBFull + st);
+            if (leader) mbar_arrive_expect_tx(bar0 + 8 * (kBFull + st), 2u * pair_stage_tx_bytes(SC, DT));
+            const int row0 = chunk * SC + static_cast<int>(cta) * th_rows;
+            tma_load_2d_pair(sb, &tm_hi, full_c, slab * kSlabK, row0);
+            tma_load_2d_pair(sb + th_rows * 128, &tm_lo, full_c, slab * kSlabK * (C8 ? 2 : 1), row0);
+#pragma unroll
+            for (int t = 0; t < proj_tiles(DT); ++t)
+              tma_load_2d_pair(sb + 2 * th_rows * 128 + t * kPTile, &tm_w, full_c, t * 64,
+                               slab * kSlabK + static_cast<int>(cta) * (kSlabK / 2));
+          }
+          __syncwarp();
+          if (++st == stages) { st = 0; ph ^= 1; }
+          continue;
+        }
         if (split_w) {
           while (jw < total && jw < it + wstages) {
             const uint32_t emp = bar0 + 8 * (kWEmpty + wst);
@@ -388,15 +432,15 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // slab j - ring have finished, which is b_empty of that slab's smem stage (stages >= ring, and b_full(j) seen
     // first implies every earlier phase of that barrier has completed).  The candidate rows of item i+2 (i+1 with
     // one buffer) are only staged after the epilogue of item i, i.e. after all of item i's projections were consumed.
-    const int npw = p.proj_warps < kProjWarps ? p.proj_warps : kProjWarps;
+    const int npw = PAIR ? 1 : (p.proj_warps < kProjWarps ? p.proj_warps : kProjWarps);
     const int h = warp - kProjWarp;
-    if (h < npw) {
-      constexpr uint32_t idesc_proj = idesc_bf16_f32(kTileM, kSlabK);
+    if (h < npw && leader) {
+      constexpr uint32_t idesc_proj = idesc_bf16_f32(PAIR ? 2 * kTileM : kTileM, kSlabK);
       constexpr uint32_t kWDescHi = smem_desc_hi(8 * kPRow, kPRow == 128 ? 2u : (kPRow == 64 ? 4u : 6u));
       // the (W | b) tile(s) follow Theta hi, lo inside the stage, or (split mode) sit in their own ring
       const int wn = split_w ? wstages : stages;
       const uint32_t desc_stage = static_cast<uint32_t>(split_w ? proj_w_bytes(DT) : sbytes) >> 4;
-      const uint32_t desc_w0 = smem_desc_lo(split_w ? w_smem0 : smem0 + 2 * SC * 128);
+      const uint32_t desc_w0 = smem_desc_lo(split_w ? w_smem0 : smem0 + 2 * th_rows * 128);
       const uint32_t wfull0 = bar0 + 8 * (split_w ? kWFull : kBFull);
       int slab = h % n_slabs, item = h / n_slabs;      // position of j inside this CTA's item sequence
       int st = h % wn, slot = h % ring;
@@ -408,14 +452,14 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       // apart, so a warp that owns no slab of an item (n_slabs < npw) still observes that item's phase, but never
       // the phase of an item beyond its own last slab iteration (it would not arrive).
       if (xa_bufs == 1 && h < total)
-        for (int i = 0; i < item; ++i) mbar_wait(bar0 + 8 * kXaFull, static_cast<uint32_t>(i) & 1);
+        for (int i = 0; i < item; ++i) mbar_wait_cluster(bar0 + 8 * kXaFull, static_cast<uint32_t>(i) & 1);
       for (int j = h; j < total; j += npw) {
         mbar_wait(wfull0 + 8 * st, ph);
         if (j >= ring) mbar_wait(bar0 + 8 * (kBEmpty + fst), fph);
         if (new_item) {
           const int xb = (xa_bufs == 2) ? (item & 1) : 0;
           const uint32_t use = (xa_bufs == 2) ? static_cast<uint32_t>(item >> 1) : static_cast<uint32_t>(item);
-          mbar_wait(bar0 + 8 * (kXaFull + xb), use & 1);
+          mbar_wait_cluster(bar0 + 8 * (kXaFull + xb), use & 1);
           new_item = false;
         }
         trace_event(p, kTrMmaProj, j);
@@ -430,14 +474,18 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           for (int k = 0; k < kPUsed / kUmmaK; ++k) {
             const uint32_t koff = (k % 4) * ((kUmmaK * 2) >> 4);
             const uint64_t b_desc = (static_cast<uint64_t>(kWDescHi) << 32) | (b_lo + (k / 4) * (kPTile >> 4) + koff);
-            if constexpr (kXSmem) {
+            if constexpr (PAIR) {
+              mma_f16_ss_pair(d_tmem, (static_cast<uint64_t>(kWDescHi) << 32) | (a_lo + (k / 4) * ((kTileM * kPRow) >> 4) + koff),
+                              b_desc, idesc_proj, k != 0);
+            } else if constexpr (kXSmem) {
               mma_f16_ss(d_tmem, (static_cast<uint64_t>(kWDescHi) << 32) | (a_lo + (k / 4) * ((kTileM * kPRow) >> 4) + koff),
                          b_desc, idesc_proj, k != 0);
             } else {
               mma_f16_ts(d_tmem, a_tmem + k * (kUmmaK / 2), b_desc, idesc_proj, k != 0);
             }
           }
-          tc_commit(bar0 + 8 * (kPFull + slot));
+          if constexpr (PAIR) tc_commit_pair(bar0 + 8 * (kPFull + slot), 3);
+          else tc_commit(bar0 + 8 * (kPFull + slot));
           if (split_w) tc_commit(bar0 + 8 * (kWEmpty + st));
         }
         __syncwarp();
@@ -453,7 +501,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           ++item;
           new_item = true;
           if (slab >= n_slabs && xa_bufs == 1 && j + npw < total) {   // an item without a slab of this warp
-            mbar_wait(bar0 + 8 * kXaFull, static_cast<uint32_t>(item) & 1);
+            mbar_wait_cluster(bar0 + 8 * kXaFull, static_cast<uint32_t>(item) & 1);
           }
         }
       }
@@ -466,39 +514,44 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // cycles of waits / commits / address arithmetic per burst, so when the next slab's operand is already there it
     // issues two slabs per burst; warp 0 pairs (0,1)(2,3).., warp 1 pairs (1,2)(3,4).., which keeps the two warps'
     // bookkeeping phases apart instead of idling the tensor pipe together.
+    // PAIR: one warp of the leader issues for both CTAs, full N = SC per instruction (each CTA's smem holds SC / 2 rows)
     const int h = warp - kMainWarp;
-    const int NH = SC >> 1;
-    const uint32_t idesc = idesc_f16_f32(kTileM, NH);
-    const uint32_t idesc8 = idesc_e4m3_f32(kTileM, NH);
+    const int NH = PAIR ? SC : (SC >> 1);
+    const uint32_t idesc = idesc_f16_f32(PAIR ? 2 * kTileM : kTileM, NH);
+    const uint32_t idesc8 = idesc_e4m3_f32(PAIR ? 2 * kTileM : kTileM, NH);
     // descriptor low words advance by plain adds: (addr >> 4) never carries out of its 14-bit field
-    const uint32_t desc_lo0 = smem_desc_lo(smem0 + h * NH * 128);
+    const uint32_t desc_lo0 = smem_desc_lo(smem0 + (PAIR ? 0 : h * NH * 128));
     const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
-    const uint32_t desc_lopart = static_cast<uint32_t>(SC * 128) >> 4;     // Theta-lo tile follows the hi tile
+    const uint32_t desc_lopart = static_cast<uint32_t>(th_rows * 128) >> 4;     // Theta-lo tile follows the hi tile
     const bool hi_only = (p.debug & 1) != 0;
     const bool pairing = ring >= 5 && !(p.debug & 8);  // a pair holds two ring slots while its MMAs run
+    const int total_main = (PAIR && (h != 0 || !leader)) ? 0 : total;
     int st = 0, slot = 0, ab = 0, slab = 0, nitem = 0;
     uint32_t sph = 0, aph = 0, bph = 0;
     // combined mode: a_full implies (through p_full and the projection warp's wait) that the stage's Theta tiles have
     // landed; split mode: the Theta stage has its own wait
-    for (int it = 0; it < total;) {
+    for (int it = 0; it < total_main;) {
       if (slab == 0) {
-        mbar_wait(bar0 + 8 * (kAccEmpty + ab), aph ^ 1);
+        if constexpr (PAIR) mbar_wait_cluster(bar0 + 8 * (kAccEmpty + ab), aph ^ 1);
+        else mbar_wait(bar0 + 8 * (kAccEmpty + ab), aph ^ 1);
         if (h == 0) trace_event(p, kTrMmaAccEmpty, nitem);
       }
       if (split_w) mbar_wait(bar0 + 8 * (kBFull + st), bph);
-      mbar_wait(bar0 + 8 * (kAFull + slot), sph);
+      if constexpr (PAIR) mbar_wait_cluster(bar0 + 8 * (kAFull + slot), sph);
+      else mbar_wait(bar0 + 8 * (kAFull + slot), sph);
       // second slab of the burst: same item, pair alignment of this warp, operand already produced
       int st2 = st + 1, slot2 = slot + 1;
       uint32_t sph2 = sph;
       if (st2 == stages) st2 = 0;
       if (slot2 == ring) { slot2 = 0; sph2 ^= 1; }
       const uint32_t bph2 = (st2 == 0) ? (bph ^ 1) : bph;
-      const bool two = pairing && ((it & 1) == h) && (slab + 1 < n_slabs) && mbar_test_wait(bar0 + 8 * (kAFull + slot2), sph2) &&
+      const bool two = pairing && (PAIR || ((it & 1) == h)) && (slab + 1 < n_slabs) &&
+                       (PAIR ? mbar_test_wait_cluster(bar0 + 8 * (kAFull + slot2), sph2) : mbar_test_wait(bar0 + 8 * (kAFull + slot2), sph2)) &&
                        (!split_w || mbar_test_wait(bar0 + 8 * (kBFull + st2), bph2));
       if (h == 0) trace_event(p, kTrMmaAFull, it);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d_tmem = tmem_base + ab * SC + h * NH;
+        const uint32_t d_tmem = tmem_base + ab * SC + (PAIR ? 0 : h * NH);
         auto issue_slab = [&](int st_, int slot_, int sl) {
           const uint32_t b_hi = desc_lo0 + st_ * desc_stage;
           const uint32_t b_lo = b_hi + desc_lopart;
@@ -508,19 +561,36 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             const uint32_t koff = k * ((kUmmaK * 2) >> 4);               // 32 bytes of K per step, in 16-byte units
             const uint32_t a_hi = a_st + k * kUmmaK;                     // 16 columns per K step: 8 hi words, 8 lo words
             const uint32_t a_lo = a_hi + kUmmaK / 2;
-            mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_hi + koff), idesc, (sl | k) != 0);
-            if (!hi_only) {
-              if constexpr (C8) {
-                // K = 32 e4m3: [cos (16) | u - fp16(u) (16)] . [2^12 Theta_lo (16) | Theta (16)], 32 bytes of the lo tile
-                mma_f8_ts(d_tmem, a_lo, smem_desc_from_lo(b_lo + koff), idesc8, 1);
-              } else {
-                mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_lo + koff), idesc, 1);
-                mma_f16_ts(d_tmem, a_lo, smem_desc_from_lo(b_hi + koff), idesc, 1);
+            if constexpr (PAIR) {
+              mma_f16_ts_pair(d_tmem, a_hi, smem_desc_from_lo(b_hi + koff), idesc, (sl | k) != 0);
+              if (!hi_only) {
+                if constexpr (C8) {
+                  mma_f8_ts_pair(d_tmem, a_lo, smem_desc_from_lo(b_lo + koff), idesc8, 1);
+                } else {
+                  mma_f16_ts_pair(d_tmem, a_hi, smem_desc_from_lo(b_lo + koff), idesc, 1);
+                  mma_f16_ts_pair(d_tmem, a_lo, smem_desc_from_lo(b_hi + koff), idesc, 1);
+                }
+              }
+            } else {
+              mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_hi + koff), idesc, (sl | k) != 0);
+              if (!hi_only) {
+                if constexpr (C8) {
+                  // K = 32 e4m3: [cos (16) | u - fp16(u) (16)] . [2^12 Theta_lo (16) | Theta (16)], 32 bytes of the lo tile
+                  mma_f8_ts(d_tmem, a_lo, smem_desc_from_lo(b_lo + koff), idesc8, 1);
+                } else {
+                  mma_f16_ts(d_tmem, a_hi, smem_desc_from_lo(b_lo + koff), idesc, 1);
+                  mma_f16_ts(d_tmem, a_lo, smem_desc_from_lo(b_hi + koff), idesc, 1);
+                }
               }
             }
           }
-          tc_commit(bar0 + 8 * (kBEmpty + st_));
-          if (sl == n_slabs - 1) tc_commit(bar0 + 8 * (kAccFull + ab));
+          if constexpr (PAIR) {
+            tc_commit_pair(bar0 + 8 * (kBEmpty + st_), 3);
+            if (sl == n_slabs - 1) tc_commit_pair(bar0 + 8 * (kAccFull + ab), 3);
+          } else {
+            tc_commit(bar0 + 8 * (kBEmpty + st_));
+            if (sl == n_slabs - 1) tc_commit(bar0 + 8 * (kAccFull + ab));
+          }
         };
         issue_slab(st, slot, slab);
         if (two) issue_slab(st2, slot2, slab + 1);
@@ -569,7 +639,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 8 * (kAFull + slot));
+        if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster_relaxed(bar0_lead + 8 * (kAFull + slot)); else mbar_arrive(bar0 + 8 * (kAFull + slot)); }
         if (q == 0) trace_event(p, kTrProdArrived + 2 * group, it);
         if (++slot == ring) { slot = 0; ph ^= 1; }
       }
@@ -602,7 +672,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * (kAFull + slot));
+      if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster_relaxed(bar0_lead + 8 * (kAFull + slot)); else mbar_arrive(bar0 + 8 * (kAFull + slot)); }
       if (q == 0) trace_event(p, kTrProdArrived + 2 * group, n);
       slot += NPG;
       if (slot >= ring) { slot -= ring; ph ^= 1; }
@@ -617,10 +687,12 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // j - xa_bufs, when every projection that read the buffer has long completed.  K order per input dimension i:
     // x1 x1 x2 x1 x2 x3 (against w1 w2 w1 w3 w2 w1), then three ones (against b1 b2 b3), zero padding.
     auto stage_rows = [&](int j) {
-      const int item = static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x);
+      const int item = unit + j * n_units;
       if (item >= n_items) return;
       const int xb = (xa_bufs == 2) ? (j & 1) : 0;
-      const int mtile = item / n_chunks;
+      // PAIR: this CTA's tile of the pair; an odd tile count leaves the peer's last tile empty (clamped here, skipped in
+      // the epilogue)
+      const int mtile = PAIR ? min(2 * (item / n_chunks) + static_cast<int>(cta), p.n_mtiles - 1) : item / n_chunks;
       // row of X holding input dimensions [0, dsplit) and the row holding [dsplit, d): the same row for plain
       // candidates; x_i and x_j for duels (tile = 128 consecutive i of one j)
       long long row_a, row_b;
@@ -696,7 +768,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         tc_fence_before();
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * (kXaFull + xb));
+      if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(bar0_lead + 8 * (kXaFull + xb)); else mbar_arrive(bar0 + 8 * (kXaFull + xb)); }
     };
 
     stage_rows(0);
@@ -710,8 +782,8 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // reduction + atomicMax runs only for blocks that may improve a sample -- after the first tiles that is rare
     // (a sample's maximum improves ~ln(#tiles) times).  Ties go through the slow path: the key's ~row decides.
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
-      const int mtile = item / n_chunks;
+    for (int item = unit; item < n_items; item += n_units, ++nitem) {
+      const int mtile = PAIR ? 2 * (item / n_chunks) + static_cast<int>(cta) : item / n_chunks;
       const int chunk = item % n_chunks;
       const int s_base = chunk * SC;
       // per-column constants of this item's chunk in shared memory (thr_s): the running-maximum bounds (MODE 0) or the
@@ -743,7 +815,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       const bool partial = (row0 + 32 > p.N);
       const bool row_ok = row < p.N;
       const uint32_t acc = tmem_base + lane_base + ab * SC;
-      if (row0 < p.N) {                              // else: whole warp beyond the last candidate (warp-uniform)
+      if (row0 < p.N && mtile < p.n_mtiles) {        // else: whole warp beyond the last candidate (warp-uniform)
 #pragma unroll 1
         for (int j = 0; j < SC / 32; ++j) {
           uint32_t v[32];
@@ -836,7 +908,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * (kAccEmpty + ab));
+      if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster_relaxed(bar0_lead + 8 * (kAccEmpty + ab)); else mbar_arrive(bar0 + 8 * (kAccEmpty + ab)); }
       if (q == 0) trace_event(p, kTrEpiDone, nitem);
       if (++ab == acc_bufs) { ab = 0; aph ^= 1; }
       stage_rows(nitem + xa_bufs);
@@ -845,9 +917,11 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 
   // ---------------------------------------------------------------------- teardown + final reduce
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();    // nobody signals the peer's barriers / TMEM any more
   tc_fence_after();
-  if (warp == kMainWarp) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kMainWarp) {
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
+  }
   if constexpr (MODE == 0) {
     __threadfence();
     __syncthreads();

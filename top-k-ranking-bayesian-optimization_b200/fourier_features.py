@@ -376,7 +376,10 @@ class SharedBasis:
         nat.check(nat.lib().tkbo_rff_basis_config(self._h, self._basis, int(N), cfg), "tkbo_rff_basis_config")
         keys = ["S_chunk", "n_chunks", "n_slabs", "stages", "acc_bufs", "d_template", "smem_bytes", "grid",
                 "tmem_ring", "threads", "row_bufs", "producer_groups", "proj_warps", "e4m3_corrections", "w_stages", "producers_share_slab"]
-        return dict(zip(keys, list(cfg)))
+        out = dict(zip(keys, list(cfg)))
+        out["cta_pairs"] = out["producers_share_slab"] >> 1           # cfg[15] = coop + 2 * pair
+        out["producers_share_slab"] &= 1
+        return out
 
     def _candidates(self, X):
         X = _f32(X, self.device)
