@@ -310,10 +310,18 @@ def k1_roofline(cfg, n_rows, D, S, ms, pk, form, facts_key, long_run):
     cos_rate = float(n_rows) * Dpad * cfg["n_chunks"] / (ms * 1e-3)
     cos_peak = 16.0 * 148 * pk["sm_max_mhz"] * 1e6
     facts = ncu_facts().get(facts_key, {})
+    # per-launch DRAM traffic from the committed ncu capture of the same kernel instance; the capture's launch may cover a
+    # different number of candidates (traffic is linear in N: every candidate row is read once), so it is scaled and both
+    # figures are given
+    traffic = None
+    if facts.get("dram_bytes_per_launch") and facts.get("units_per_launch"):
+        traffic = facts["dram_bytes_per_launch"] * n_rows / facts["units_per_launch"]
     sustained = pk.get("bf16_tflops_sustained") or pk["bf16_tflops"]
     peak = sustained if long_run else pk["bf16_tflops"]
     return {"bound": "tensor", "achieved": alg, "peak": peak, "unit": "TFLOP/s", "frac": alg / peak,
-            "traffic": facts.get("dram_bytes_per_launch"), "kernel": "rff_fused_kernel", "form": form,
+            "traffic": traffic, "traffic_captured": {"dram_bytes": facts.get("dram_bytes_per_launch"),
+                                                     "candidates_in_captured_launch": facts.get("units_per_launch")},
+            "kernel": "rff_fused_kernel", "form": form, "cta_pairs": bool(cfg.get("cta_pairs")),
             "flops_per_launch": 2.0 * n_rows * D * S, "launch_ms": ms,
             "peak_kind": ("sustained" if long_run else "burst") + " bf16 cuBLAS, " + pk["source"],
             "frac_of_burst_peak": alg / pk["bf16_tflops"], "executed": exe, "executed_frac": exe / peak,
@@ -447,7 +455,7 @@ def k1_block(ctx, name, args, precision, steps, warmup, with_e2e, long_run, fact
         blk = {"metric": METRIC, "value": N * S / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_step_median": ms_med,
                "steps": steps, "warmup": warmup, "config": config_of(name), "form": form, "gpu_launches": launches,
                "clocks": clocks,
-               "roofline": k1_roofline(cfg, n_rows0, D, S, ms_med, pk, form, facts_key, long_run),
+               "roofline": k1_roofline(cfg, n_rows0, D, S, ms_med, pk, form, f"k1_{name}_{form}", long_run),
                "run": {"tiling": cfg, "candidates_per_rank": n_rows0,
                        "l2": f"{n_rot} rotating candidate buffers per rank ({n_rot * shard_bytes >> 20} MiB > 2 x 126 MiB L2)",
                        "parallelism": f"candidate shards x{ctx.world} (strong scaling), merge: {merge}",
@@ -513,8 +521,8 @@ def mpes_block(ctx, args):
     # joint RFF posterior samples at the 5e5 query points and the 20 maximisers: the f-samples K2 consumes are drawn by K1
     # (store-F epilogue) exactly as the acquisition pipeline does, not i.i.d. noise
     rngq = np.random.default_rng(4)
-    Wq, bq, Tq = make_basis_arrays(1024, dq, Sm, 0.2, 0.0, 1.0, seed=4)
-    bq_basis = pkg.fourier_features.SharedBasis(Wq, bq, Tq, device=dev, precision="fp32")
+    Wq, bq, Tq, Qq = make_basis_arrays(1024, dq, Sm, 0.2, 0.0, 1.0, seed=4, return_q=True)
+    bq_basis = pkg.fourier_features.SharedBasis(Wq, bq, Tq, device=dev, precision="auto", f_scale=np.abs(Qq).max(axis=0))
     chi_h = rngq.uniform(0, 1, size=(Q * C, dq)).astype(np.float32)
     # the maximisers x* are posterior maximiser samples, as in MPES_Forr.py:295-306 (sample_maximizers, then I_batch): the
     # arg max of each of the S sampled functions over 2^16 candidates (K1), the M most frequent distinct winners
@@ -611,8 +619,8 @@ def mpes_block(ctx, args):
     torch.cuda.synchronize()
     pms = statistics.median(evs[r].elapsed_time(evs[r + 1]) for r in range(reps))
     out["pipeline"] = {"ms_per_call": pms, "value": Q / (pms * 1e-3), "unit": "acq evals/s",
-                       "what": "RFF joint f-samples at 5e5 query points + 20 maximisers (D=1024, d=6, S=1024; K1 store-F, fp32 form, "
-                               "2.05 GB written) -> K2 -> argmax; everything stays on the device",
+                       "what": f"RFF joint f-samples at 5e5 query points + 20 maximisers (D=1024, d=6, S=1024; K1 store-F, {bq_basis.precision} "
+                               "form, 2.05 GB written) -> K2 -> argmax; everything stays on the device",
                        "best_query": int(best)}
     del F_chi, fchi, chi
     torch.cuda.empty_cache()
@@ -719,7 +727,7 @@ def duel_block(ctx, steps, warmup):
            "steps": steps, "warmup": warmup, "form": basis.precision, "gpu_launches": launches, "clocks": clocks,
            "config": {"workload": "c4d: DTS batch Thompson, n=2048 base points (d_obj=2), all 2^22 duels [x_i, x_j] generated in the "
                                   "kernel, D=2048, S=4096, soft-Copeland winners", "N_total": n_tot, "d": d, "D": D, "S": S},
-           "roofline": k1_roofline(cfg, N_rank, D, S, ms_med, pk, basis.precision, "k1_c4d", True),
+           "roofline": k1_roofline(cfg, N_rank, D, S, ms_med, pk, basis.precision, f"k1_c4d_{basis.precision}", True),
            "run": {"tiling": cfg, "candidates_per_rank": N_rank,
                    "l2": "no per-step input beyond 16 KB of base points; every step rewrites the 64 MiB fixed-point sums",
                    "parallelism": f"duel shards along j x{ctx.world} (strong scaling), one int64 all_reduce(SUM) of [S, n]",

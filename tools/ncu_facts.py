@@ -6,11 +6,11 @@ import json
 import subprocess
 import sys
 
-rep, out = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-hdr, units = rows[0], rows[1]
-col = {h: i for i, h in enumerate(hdr)}
+import os
+
+out, reps = sys.argv[1], sys.argv[2:]
+facts = json.load(open(out)) if os.path.exists(out) else {}
+col, units = {}, []
 
 
 def num(r, name):
@@ -22,19 +22,46 @@ def num(r, name):
     return v * scale
 
 
-KEYS = {"rff_fused_kernel<6, 0, 2, false>": "k1_c3_fp32", "rff_fused_kernel<6, 0, 2, true>": "k1_c3_fast",
-        "rff_fused_kernel<2, 0, 4, false>": "k1_c2_fp32", "rff_fused_kernel<4, 2, 2, true>": "k1_c4d",
-        "mpes_all_perms_kernel<5, 3, true>": "k2_c5"}
-facts = {}
-for r in rows[2:]:
+import re
+
+
+def classify(name):
+    """kernel instance -> (key used by bench.py, cta_pairs); template arguments DT, MODE, NPG, C8[, PAIR]."""
+    flat = re.sub(r"\((int|bool)\)", "", name.replace(" ", ""))
+    m = re.search(r"rff_fused_kernel<(\d+),(\d+),(\d+),(\w+)(?:,(\w+))?>", flat)
+    if m:
+        dt, mode, npg = int(m.group(1)), int(m.group(2)), int(m.group(3))
+        c8 = m.group(4) in ("true", "1")
+        pair = m.group(5) in ("true", "1")
+        shape = {(6, 0): "c3", (2, 0): "c2", (4, 2): "c4d", (4, 0): "c4"}.get((dt, mode))
+        if shape is None:
+            return None, False
+        return f"k1_{shape}_{'fast' if c8 else 'fp32'}", pair
+    if re.search(r"mpes_all_perms_kernel<5,3,", flat):
+        return "k2_c5", False
+    return None, False
+
+
+rows_all = []
+for rep in reps:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    if len(rr) < 3:
+        print("no rows in", rep, file=sys.stderr)
+        continue
+    rows_all.append((rep, rr))
+for rep, rows in rows_all:
+  hdr, units = rows[0], rows[1]
+  col = {h: i for i, h in enumerate(hdr)}
+  for r in rows[2:]:
     name = r[col["Kernel Name"]]
-    key = next((v for k, v in KEYS.items() if name.replace(" ", "").startswith(("tkbo::" + k).replace(" ", "")) or
-                k.replace(" ", "") in name.replace(" ", "")), None)
+    key, pair = classify(name)
     if key is None:
         continue
     rd, wr = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum")
     facts[key] = {
-        "kernel": name, "source": f"ncu --set full --clock-control none, tools/profile_cmd.py ({rep.split('/')[-1]})",
+        "kernel": name, "cta_pairs": bool(pair) if key.startswith("k1") else None,
+        "source": f"ncu --set full --clock-control none on tools/profile_cmd.py ({rep.split('/')[-1]}), profiles/r02_*_summary.txt",
         "duration_ms": num(r, "gpu__time_duration.sum"),
         "dram_bytes_read": rd, "dram_bytes_write": wr,
         "dram_bytes_per_launch": (rd or 0.0) + (wr or 0.0),
