@@ -127,6 +127,28 @@ def test_rff_precision_modes(pbo, N, D, d, S):
     np.testing.assert_array_equal(tight.eval(X).cpu().numpy(), generous.eval(X).cpu().numpy())
 
 
+@pytest.mark.parametrize("N,D,d,S", [(70000, 512, 6, 256), (33000, 384, 4, 700), (129, 128, 2, 100), (50000, 256, 12, 160)])
+def test_cta_pairs_equal_single_ctas(pbo, N, D, d, S, monkeypatch):
+    """CTA pairs (cta_group::2: one M = 256 MMA per pair, operands fetched half by each CTA, second epilogue warp set) are
+    a different schedule of the same arithmetic: per accumulator column the same MMAs in the same order, so argmax, values
+    and stored samples are BITWISE those of the single-CTA launch - for odd tile counts (the peer's last tile is empty),
+    several sample chunks and both contraction forms."""
+    rng = np.random.default_rng(N)
+    X, W, b, Theta = _basis_inputs(rng, N, D, d, S, 0.0, 1.0, 0.3)
+    Xd = torch.from_numpy(X).cuda()
+    for form in ("fp32", "fast"):
+        res = {}
+        for pair in ("0", "1"):
+            monkeypatch.setenv("TKBO_PAIR", pair)
+            basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0", precision=form)
+            assert basis.config(N)["cta_pairs"] == int(pair)
+            res[pair] = (basis.argmax(Xd), basis.eval(Xd[:3000]))
+        (v0, i0), F0 = res["0"]
+        (v1, i1), F1 = res["1"]
+        assert torch.equal(v0, v1) and torch.equal(i0, i1) and torch.equal(F0, F1)
+    _check_argmax(v1, i1, X, W, b, Theta)
+
+
 def test_peer_merge_single_rank(pbo):
     """The peer-memory merge with one rank (its own buffer is the only peer): keys pushed by the kernel's last CTA, flags,
     epoch parity and the merge kernel give the same (value, index) as the plain call, over several epochs and shapes of

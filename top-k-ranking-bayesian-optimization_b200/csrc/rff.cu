@@ -534,7 +534,7 @@ static int launch_fused_c(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, 
       TKBO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs->smem_bytes));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
-      cfg.blockDim = dim3(kNumThreadsFor(NPG), 1, 1);
+      cfg.blockDim = dim3(kNumThreadsPair(NPG), 1, 1);
       cfg.dynamicSmemBytes = static_cast<size_t>(bs->smem_bytes);
       cfg.stream = stream;
       cudaLaunchAttribute attr[1];
@@ -944,7 +944,7 @@ int basis_config(tkbo_handle_t h, tkbo_basis_t bs, int64_t N, int32_t* cfg) {
   cfg[0] = bs->SC; cfg[1] = bs->n_chunks; cfg[2] = bs->Dpad / kSlabK; cfg[3] = bs->stages; cfg[4] = bs->acc_bufs;
   cfg[5] = bs->DT; cfg[6] = bs->smem_bytes;
   cfg[7] = fused_grid(h, bs, std::max<int64_t>(1, mt));
-  cfg[8] = bs->ring; cfg[9] = kNumThreadsFor(bs->npg); cfg[10] = bs->xa_bufs; cfg[11] = bs->npg; cfg[12] = bs->proj_warps; cfg[13] = bs->corr8; cfg[14] = bs->wstages; cfg[15] = bs->coop + 2 * bs->pair;
+  cfg[8] = bs->ring; cfg[9] = bs->pair ? kNumThreadsPair(bs->npg) : kNumThreadsFor(bs->npg); cfg[10] = bs->xa_bufs; cfg[11] = bs->npg; cfg[12] = bs->proj_warps; cfg[13] = bs->corr8; cfg[14] = bs->wstages; cfg[15] = bs->coop + 2 * bs->pair;
   return TKBO_OK;
 }
 

@@ -48,6 +48,9 @@ constexpr int kUmmaK = 16;           // K per tcgen05.mma for 16-bit inputs
 // epilogue + producers + TMA + 2 projection + 2 main MMA warps
 constexpr int kProjWarpsFor(int npg) { return 2; }
 constexpr int kNumThreadsFor(int npg) { return 32 * (4 + 4 * npg + 1 + kProjWarpsFor(npg) + 2); }
+// CTA pairs add a second set of four epilogue warps (one per TMEM lane quarter): the accumulator read-out is latency-bound
+// with one warp per quarter, and at SC = 256 it is not overlapped (single accumulator buffer)
+constexpr int kNumThreadsPair(int npg) { return kNumThreadsFor(npg) + 128; }
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 12;       // smem ring (Theta + W tiles)
 constexpr int kMaxWStages = 8;     // separate (W | b) tile ring (split mode)
@@ -263,7 +266,7 @@ __device__ __forceinline__ void bf16_split3(float x, uint32_t& b1, uint32_t& b2,
 // p_full / b_empty / acc_full.
 template <int DT, int MODE /* 0 = argmax, 1 = store F, 2 = duel soft-Copeland sums */, int NPG /* producer warp groups: 2, 3 or 4 */,
           bool C8 /* corrections as one e4m3 MMA (tm_lo = the e4m3 tile) instead of two fp16 MMAs */, bool PAIR = false>
-__global__ void __launch_bounds__(kNumThreadsFor(NPG), 1)
+__global__ void __launch_bounds__(PAIR ? kNumThreadsPair(NPG) : kNumThreadsFor(NPG), 1)
 rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                  const __grid_constant__ CUtensorMap tm_w, const RffParams p) {
   constexpr int kPUsed = proj_k_used(DT);
@@ -328,7 +331,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars[kAccFull + a], PAIR ? 1 : 2);     // one commit per main MMA warp
-      mbar_init(&bars[kAccEmpty + a], PAIR ? 8 : 4);    // one arrival per epilogue warp (of both CTAs)
+      mbar_init(&bars[kAccEmpty + a], PAIR ? 16 : 4);   // one arrival per epilogue warp (PAIR: two sets of four, both CTAs)
       mbar_init(&bars[kXaFull + a], PAIR ? 8 : 4);
     }
     fence_mbar_init();
@@ -337,6 +340,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   constexpr int kProjWarp = kTmaWarp + 1;            // kProjWarps of them
   constexpr int kProjWarps = kProjWarpsFor(NPG);
   constexpr int kMainWarp = kProjWarp + kProjWarps;  // and + 1
+  constexpr int kEpiSets = PAIR ? 2 : 1;             // PAIR: warps kMainWarp + 2 .. + 5 are a second set of epilogue warps
   if (warp == kMainWarp) {
     if constexpr (PAIR) tmem_alloc_pair(&tmem_base_smem, kTmemCols); else tmem_alloc(&tmem_base_smem, kTmemCols);
   }
@@ -506,7 +510,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         }
       }
     }
-  } else if (warp >= kMainWarp) {
+  } else if (warp >= kMainWarp && warp < kMainWarp + 2) {
     // ------------------------------------------------------------------ main MMAs: acc += Phi_slab . Theta_slab^T (3 per K step)
     // Warp h owns accumulator columns [h SC/2, (h+1) SC/2): N = SC/2 per instruction, Theta rows h SC/2 ... of the tile,
     // so every column's MMAs come from one thread in slab order (deterministic fp32 accumulation; MMAs issued by
@@ -608,7 +612,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         if (++ab == acc_bufs) { ab = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < kTmaWarp) {
     // ------------------------------------------------------------------ feature producers
     // group g owns the slab iterations it = g, g + NPG, g + 2 NPG, ... of this CTA, whatever item they belong to
     const int group = (warp - 4) >> 2;               // 0 .. NPG-1
@@ -680,7 +684,9 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------ candidate rows + epilogue
-    const int q = warp;                              // warps 0..3 <-> TMEM lanes 32q..32q+31
+    // warps 0..3 (set 0) and, with PAIR, warps kMainWarp + 2 .. + 5 (set 1); a warp reaches the TMEM lanes of its id mod 4
+    const int q = warp & 3;                          // <-> TMEM lanes 32q..32q+31
+    const int eset = (warp >= 4) ? 1 : 0;            // set 0 also stages the candidate rows; the sets alternate column blocks
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
 
     // Write the split rows of this CTA's j-th item into buffer j % xa_bufs; called after the epilogue of item
@@ -771,8 +777,10 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(bar0_lead + 8 * (kXaFull + xb)); else mbar_arrive(bar0 + 8 * (kXaFull + xb)); }
     };
 
-    stage_rows(0);
-    if (xa_bufs == 2) stage_rows(1);
+    if (eset == 0) {
+      stage_rows(0);
+      if (xa_bufs == 2) stage_rows(1);
+    }
 
     int ab = 0, nitem = 0;
     uint32_t aph = 0;
@@ -791,7 +799,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       float thr_new[2];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int c = t * 128 + q * 32 + lane;
+        const int c = (eset == 0) ? t * 128 + q * 32 + lane : SC;      // set 0 loads and publishes the per-column constants
         if constexpr (MODE == 0) {
           const unsigned long long pk = (c < SC) ? __ldcg(p.packed + s_base + c) : 0ull;
           thr_new[t] = (pk == 0ull) ? -INFINITY : f32_from_orderable(static_cast<uint32_t>(pk >> 32));
@@ -800,15 +808,15 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         }
       }
       mbar_wait(bar0 + 8 * (kAccFull + ab), aph);
-      // the four epilogue warps share thr_s: nobody still reads the previous item's values / everybody sees the new ones
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // the epilogue warps share thr_s: nobody still reads the previous item's values / everybody sees the new ones
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiSets) : "memory");
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int c = t * 128 + q * 32 + lane;
+        const int c = (eset == 0) ? t * 128 + q * 32 + lane : SC;
         if (c < SC) thr_s[c] = thr_new[t];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (q == 0) trace_event(p, kTrEpiAccFull, nitem);
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiSets) : "memory");
+      if (warp == 0) trace_event(p, kTrEpiAccFull, nitem);
       tc_fence_after();
       const long long row0 = static_cast<long long>(mtile) * kTileM + q * 32;
       const long long row = row0 + lane;
@@ -817,7 +825,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       const uint32_t acc = tmem_base + lane_base + ab * SC;
       if (row0 < p.N && mtile < p.n_mtiles) {        // else: whole warp beyond the last candidate (warp-uniform)
 #pragma unroll 1
-        for (int j = 0; j < SC / 32; ++j) {
+        for (int j = eset; j < SC / 32; j += kEpiSets) {
           uint32_t v[32];
           tmem_ld_x32(acc + j * 32, v);
           tmem_wait_ld();
@@ -909,9 +917,9 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster_relaxed(bar0_lead + 8 * (kAccEmpty + ab)); else mbar_arrive(bar0 + 8 * (kAccEmpty + ab)); }
-      if (q == 0) trace_event(p, kTrEpiDone, nitem);
+      if (warp == 0) trace_event(p, kTrEpiDone, nitem);
       if (++ab == acc_bufs) { ab = 0; aph ^= 1; }
-      stage_rows(nitem + xa_bufs);
+      if (eset == 0) stage_rows(nitem + xa_bufs);
     }
   }
 
