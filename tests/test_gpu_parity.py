@@ -961,3 +961,28 @@ def test_mpes_query_shards_equal_full(pbo):
     assert top[1] == int(torch.argmax(full)) and top[0] == float(full.max())
     mi0, best0 = dist_.sharded_mpes(fchi[:, :0, :].contiguous(), fstar, k, nat.MPES_RANK, 0)
     assert mi0.numel() == 0 and best0 == (-float("inf"), -1)
+
+
+def test_bench_gpu_arm_contract():
+    """`bench.py` (GPU arm) on the small workload: one JSON line with the contract's keys, a roofline and an e2e object
+    whose result equals the device-resident one, kernels launched through libtkbo.so, same `config` dict as the reference
+    arm prints for that workload."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "c2", "--steps", "5", "--warmup", "3",
+                        "--no-blocks", "--no-cpu"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in j, key
+    assert j["n_gpus"] == 1 and j["steps"] == 5 and j["gpu_launches"] == 5 and j["value"] > 1e10
+    assert j["config"] == {"workload": j["config"]["workload"], "N_total": 1 << 20, "d": 2, "D": 1024, "S": 64}
+    assert j["e2e"]["equals_device_resident_result"] is True and j["e2e"]["h2d_bytes_per_step"] > 8e6
+    rf = j["roofline"]
+    assert rf["bound"] == "tensor" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12 and rf["form"] == "fp32"
