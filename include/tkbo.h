@@ -165,7 +165,10 @@ int tkbo_rff_features_batched(tkbo_handle_t h, const double* X, const double* W,
                               int n, int D, int d, double* out_phi, void* stream);
 /* fourier_features.py:133-157: sign-gradient ascent (Keras RMSprop rho=0: x <- clip(x - lr g/(|g|+eps)))
  * on loss = -mean_{c,i} f_c(x[c,i]); stops when |dloss/loss| < rel_tol or after num_steps.
- * X is updated in place; *steps_run (host int, may be NULL) receives the step count. Synchronous. */
+ * X is updated in place; *steps_run (host int, may be NULL) receives the step count. Synchronous.
+ * Runs in chunks of 64 steps (TKBO_ASCENT_CHUNK) without a grid-wide barrier: the update of a start point needs only its
+ * own gradient, the global stop test is evaluated once per chunk from the recorded per-step losses, and a chunk that
+ * contains the stop is repeated for the exact number of steps (deterministic, so the iterates are the same). */
 int tkbo_rff_ascent_batched(tkbo_handle_t h, double* X, const double* W, const double* b, const double* theta,
                             int count, int n, int D, int d, double min_val, double max_val, int num_steps,
                             double lr, double eps, double rel_tol, int* steps_run, void* stream);

@@ -1,6 +1,5 @@
 // Host side of the shared-basis RFF sampler (operand preparation, tiling choice, tensor maps, launch)
 // plus the small float64 kernels for the reference-exact per-sample-basis shapes.
-#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 #include <math.h>
@@ -13,8 +12,6 @@
 
 #include "common.h"
 #include "rff_fused.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace tkbo {
 
@@ -192,112 +189,127 @@ __global__ void argmax_rows_f64_kernel(const double* __restrict__ f, int count, 
   out[c] = bi;
 }
 
-// Persistent cooperative kernel for ff.py:133-157.  One warp per start point; every step evaluates
-// f and df/dx at the current x, block-reduces the loss, grid-syncs, checks the early-stop rule on the
-// global mean loss and applies  x <- clip(x - lr g / (sqrt(g^2) + eps))  with g = dloss/dx.
-struct AscentState {
-  double* partial;     // [2][gridDim.x] per-block sum of f, by step parity
-  int* steps;          // steps actually run
-};
+// ff.py:133-157 on the device, without a grid-wide barrier.  The update of a start point only needs that point's own
+// gradient (loss = -mean over all points, so dloss/dx_p = -(1 / total) df_p/dx_p); only the early stop (ff.py:154) couples
+// the points, through the global mean loss.  So the loop runs in CHUNKS of steps: one block of 128 threads per start point
+// carries its point through the whole chunk (x in registers, the D features split over the threads, block reduction of f
+// and df/dx per step) and records its f at every step; a reduction kernel forms the global loss per step and finds the
+// first step s >= 1 with |loss_s - loss_{s-1}| / |loss_{s-1}| < rel_tol.  If there is one, the chunk is re-run from its
+// starting points for exactly s steps (everything is deterministic, so the re-run reproduces the same iterates); otherwise
+// the next chunk starts from the chunk's end points.  Against the cooperative one-barrier-per-step kernel of round 1 this
+// has 4x the warps per point and no barrier: c1 (count 20 x n_init 50, D = 1000) 43 -> 13 us per step (the float64
+// sincos of 10^6 features per step is then the bound: ~60 DFMA each on a pipe of 64 lanes per clock and SM).
+constexpr int kAscentThreads = 128;
+constexpr int kAscentMaxD = 16;
 
-__global__ void rff_ascent_batched_kernel(double* __restrict__ X, const double* __restrict__ W,
-                                          const double* __restrict__ b, const double* __restrict__ theta, int count,
-                                          int n, int D, int d, double min_val, double max_val, int num_steps,
-                                          double lr, double eps, double rel_tol, AscentState st) {
-  cg::grid_group grid = cg::this_grid();
-  extern __shared__ double sh[];                       // [warps_per_block] f partials + the grid total
-  const int warps_per_block = blockDim.x >> 5;
-  const int wib = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int total = count * n;
-  const int warps_total = gridDim.x * warps_per_block;
+__global__ void __launch_bounds__(kAscentThreads)
+rff_ascent_chunk_kernel(const double* __restrict__ Xin, double* __restrict__ Xout, const double* __restrict__ W,
+                        const double* __restrict__ b, const double* __restrict__ theta, int n, int D, int d, int total,
+                        double min_val, double max_val, int steps, double lr, double eps,
+                        double* __restrict__ f_point /* [steps + 1][total] */) {
+  __shared__ double red[kAscentThreads / 32][kAscentMaxD + 1];
+  const int pt = blockIdx.x;
+  const int c = pt / n;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const double* Wc = W + static_cast<size_t>(c) * D * d;
+  const double* bc = b + static_cast<size_t>(c) * D;
+  const double* tc = theta + static_cast<size_t>(c) * D;
   const double root = sqrt(2.0 / D);
   const double gcoef = root / static_cast<double>(total);
-  constexpr int kMaxD = 16;
-  double prev_loss = 0.0;
-  int steps_done = 0;
-  bool stop = false;
-
-  // X holds two copies of the points (ping-pong): `cur` is the accepted iterate, the tentative update of a pass goes to the
-  // other copy and becomes current only if the stop test lets the step through -- one grid-wide barrier per step.  The
-  // per-block loss partials are double-buffered by step parity for the same reason.  A point is always handled by the
-  // same warp, so the copies need no cross-block ordering.
-  const size_t half = static_cast<size_t>(total) * d;
-  int sel = 0;
-  for (int step = 0; step <= num_steps && !stop; ++step) {
-    // pass `step`: evaluate loss at the current x (step 0 = prev_loss of ff.py:148) and the gradient
-    double* cur = X + (sel ? half : 0);
-    double* nxt = X + (sel ? 0 : half);
-    double fsum = 0.0;
-    for (int pt = blockIdx.x * warps_per_block + wib; pt < total; pt += warps_total) {
-      const int c = pt / n;
-      const double* x = cur + static_cast<size_t>(pt) * d;
-      const double* Wc = W + static_cast<size_t>(c) * D * d;
-      double f = 0.0;
-      double g[kMaxD];
+  double x[kAscentMaxD];
 #pragma unroll
-      for (int k = 0; k < kMaxD; ++k) g[k] = 0.0;
-      for (int j = lane; j < D; j += 32) {
-        double t = b[static_cast<size_t>(c) * D + j];
-        for (int k = 0; k < d; ++k) t += Wc[static_cast<size_t>(j) * d + k] * x[k];
-        double sn, cs;
-        sincos(t, &sn, &cs);
-        const double th = theta[static_cast<size_t>(c) * D + j];
-        f += cs * th;
-        const double ts = th * sn;
+  for (int k = 0; k < kAscentMaxD; ++k) x[k] = (k < d) ? Xin[static_cast<size_t>(pt) * d + k] : 0.0;
+  for (int step = 0; step <= steps; ++step) {
+    // f and df/dx at the current x: this thread's share of the features
+    double f = 0.0;
+    double g[kAscentMaxD];
 #pragma unroll
-        for (int k = 0; k < kMaxD; ++k)
-          if (k < d) g[k] += ts * Wc[static_cast<size_t>(j) * d + k];
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        f += __shfl_xor_sync(0xffffffffu, f, o);
+    for (int k = 0; k < kAscentMaxD; ++k) g[k] = 0.0;
+    for (int j = threadIdx.x; j < D; j += kAscentThreads) {
+      double t = bc[j];
 #pragma unroll
-        for (int k = 0; k < kMaxD; ++k)
-          if (k < d) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
-      }
-      fsum += f * root;
-      // every lane holds all g[k]; lane k < d owns coordinate k
-      if (lane < d) {
+      for (int k = 0; k < kAscentMaxD; ++k)
+        if (k < d) t += Wc[static_cast<size_t>(j) * d + k] * x[k];
+      double sn, cs;
+      sincos(t, &sn, &cs);
+      const double th = tc[j];
+      f += cs * th;
+      const double ts = th * sn;
+#pragma unroll
+      for (int k = 0; k < kAscentMaxD; ++k)
+        if (k < d) g[k] += ts * Wc[static_cast<size_t>(j) * d + k];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      f += __shfl_xor_sync(0xffffffffu, f, o);
+#pragma unroll
+      for (int k = 0; k < kAscentMaxD; ++k)
+        if (k < d) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
+    }
+    if (lane == 0) {
+      red[wib][kAscentMaxD] = f;
+#pragma unroll
+      for (int k = 0; k < kAscentMaxD; ++k)
+        if (k < d) red[wib][k] = g[k];
+    }
+    __syncthreads();
+    // every thread sums the warps' partials in the same order: identical f, g in the whole block
+    f = 0.0;
+#pragma unroll
+    for (int w = 0; w < kAscentThreads / 32; ++w) f += red[w][kAscentMaxD];
+#pragma unroll
+    for (int k = 0; k < kAscentMaxD; ++k) {
+      if (k < d) {
         double gk = 0.0;
 #pragma unroll
-        for (int k = 0; k < kMaxD; ++k)
-          if (k == lane) gk = g[k] * gcoef;
-        const double xn = x[lane] - lr * gk / (sqrt(gk * gk) + eps);
-        nxt[static_cast<size_t>(pt) * d + lane] = fmin(fmax(xn, min_val), max_val);
+        for (int w = 0; w < kAscentThreads / 32; ++w) gk += red[w][k];
+        g[k] = gk;
       }
     }
-    if (lane == 0) sh[wib] = fsum;
-    __syncthreads();
-    double* partial = st.partial + static_cast<size_t>(step & 1) * gridDim.x;
-    if (threadIdx.x == 0) {
-      double s = 0.0;
-      for (int w = 0; w < warps_per_block; ++w) s += sh[w];
-      partial[blockIdx.x] = s;
+    __syncthreads();                                  // red is rewritten by the next step
+    if (threadIdx.x == 0) f_point[static_cast<size_t>(step) * total + pt] = f * root;
+    if (step < steps) {
+      // Keras RMSprop(rho = 0): x <- clip(x - lr g / (sqrt(g^2) + eps)), g = dloss/dx = +gcoef sum_j theta_j sin(.) w_j
+#pragma unroll
+      for (int k = 0; k < kAscentMaxD; ++k) {
+        if (k < d) {
+          const double gk = g[k] * gcoef;
+          x[k] = fmin(fmax(x[k] - lr * gk / (sqrt(gk * gk) + eps), min_val), max_val);
+        }
+      }
     }
-    grid.sync();
-    // every block sums the partials in the same order (warp 0, lane-strided + butterfly): identical `tot` everywhere
-    if (wib == 0) {
-      double t = 0.0;
-      for (int bl = lane; bl < static_cast<int>(gridDim.x); bl += 32) t += partial[bl];
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) sh[warps_per_block] = t;
-    }
-    __syncthreads();
-    const double tot = sh[warps_per_block];
-    __syncthreads();                                  // sh is rewritten by the next pass
-    const double loss = -tot / static_cast<double>(total);
-    if (step > 0) {
-      steps_done = step;
-      if (fabs((loss - prev_loss) / prev_loss) < rel_tol) stop = true;      // ff.py:154
-    }
-    prev_loss = loss;
-    if (!stop && step < num_steps) sel ^= 1;          // commit the update computed from this pass's gradient (ff.py:150)
   }
-  if (sel) {                                          // the accepted iterate goes back to the first copy
-    for (int pt = blockIdx.x * warps_per_block + wib; pt < total; pt += warps_total)
-      if (lane < d) X[static_cast<size_t>(pt) * d + lane] = X[half + static_cast<size_t>(pt) * d + lane];
+  if (static_cast<int>(threadIdx.x) < d) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < kAscentMaxD; ++k)
+      if (k == static_cast<int>(threadIdx.x)) v = x[k];
+    Xout[static_cast<size_t>(pt) * d + threadIdx.x] = v;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *st.steps = steps_done;
+}
+
+// loss[s] = -(1 / total) sum_p f_point[s][p], s = 0 .. steps: one block per step, fixed summation order.
+__global__ void __launch_bounds__(256)
+ascent_loss_kernel(const double* __restrict__ f_point, int total, double* __restrict__ loss) {
+  __shared__ double red[256];
+  const double* row = f_point + static_cast<size_t>(blockIdx.x) * total;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < total; i += 256) s += row[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (static_cast<int>(threadIdx.x) < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[blockIdx.x] = -red[0] / static_cast<double>(total);
+}
+
+// *stop = first s in 1 .. steps with |loss[s] - loss[s-1]| / |loss[s-1]| < rel_tol (ff.py:154), or -1.
+__global__ void ascent_stop_kernel(const double* __restrict__ loss, int steps, double rel_tol, int* __restrict__ stop) {
+  int found = -1;
+  for (int s = 1; s <= steps; ++s) {
+    if (fabs((loss[s] - loss[s - 1]) / loss[s - 1]) < rel_tol) { found = s; break; }
+  }
+  *stop = found;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -993,33 +1005,60 @@ int rff_ascent_batched(tkbo_handle_t h, double* X, const double* W, const double
                        int n, int D, int d, double min_val, double max_val, int num_steps, double lr, double eps,
                        double rel_tol, int* steps_run, cudaStream_t stream) {
   TKBO_REQUIRE(h && X && W && b && theta, "null pointer");
-  TKBO_REQUIRE(count >= 1 && n >= 1 && D >= 1 && d >= 1 && d <= 16, "count, n, D >= 1 and 1 <= d <= 16 required");
+  TKBO_REQUIRE(count >= 1 && n >= 1 && D >= 1 && d >= 1 && d <= kAscentMaxD, "count, n, D >= 1 and 1 <= d <= 16 required");
   TKBO_REQUIRE(num_steps >= 0, "num_steps must be >= 0");
   const int total = count * n;
-  const int block = 256, wpb = block / 32;
-  int per_sm = 0;
-  TKBO_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rff_ascent_batched_kernel, block,
-                                                                (wpb + 1) * sizeof(double)));
-  TKBO_REQUIRE(per_sm >= 1, "ascent kernel does not fit on an SM");
-  int grid = std::min(h->sm_count * per_sm, (total + wpb - 1) / wpb);
-  grid = std::max(grid, 1);
-  // X + shadow copy for the tentative update
+  int chunk = 64;       // measured at c1 with an early stop at step 856: 64 -> 13.2, 256 -> 15.3, 1024 -> 25 us per step
+  if (const char* env = getenv("TKBO_ASCENT_CHUNK")) { const int t = atoi(env); if (t >= 1 && t <= 4096) chunk = t; }
+  chunk = std::max(1, std::min(chunk, std::max(num_steps, 1)));
+  // two point buffers (ping-pong between chunks) | f_point [chunk + 1][total] | loss [chunk + 1] | stop
+  const size_t pts = static_cast<size_t>(total) * d;
+  const size_t n_doubles = 2 * pts + static_cast<size_t>(chunk + 1) * total + (chunk + 1);
   double* work = nullptr;
-  TKBO_CUDA_CHECK(cudaMallocAsync(&work, sizeof(double) * (2 * static_cast<size_t>(total) * d + 2 * grid) + sizeof(int), stream));
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(work, X, sizeof(double) * total * d, cudaMemcpyDeviceToDevice, stream));
-  AscentState st;
-  st.partial = work + 2 * static_cast<size_t>(total) * d;
-  st.steps = reinterpret_cast<int*>(st.partial + 2 * grid);
-  void* args[] = {&work, &W, &b, &theta, &count, &n, &D, &d, &min_val, &max_val, &num_steps, &lr, &eps, &rel_tol, &st};
-  TKBO_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rff_ascent_batched_kernel), dim3(grid), dim3(block),
-                                              args, (wpb + 1) * sizeof(double), stream));
-  h->launches += 1;
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(X, work, sizeof(double) * total * d, cudaMemcpyDeviceToDevice, stream));
-  int steps = 0;
-  TKBO_CUDA_CHECK(cudaMemcpyAsync(&steps, st.steps, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  TKBO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  TKBO_CUDA_CHECK(cudaMallocAsync(&work, sizeof(double) * n_doubles + sizeof(int), stream));
+  double* xa = work;
+  double* xb = work + pts;
+  double* f_point = xb + pts;
+  double* loss = f_point + static_cast<size_t>(chunk + 1) * total;
+  int* stop_dev = reinterpret_cast<int*>(loss + (chunk + 1));
+  auto fail = [&](cudaError_t e, const char* what) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    cudaFreeAsync(work, stream);
+    return TKBO_ERR_CUDA;
+  };
+  cudaError_t e = cudaMemcpyAsync(xa, X, sizeof(double) * pts, cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) return fail(e, "cudaMemcpyAsync");
+  int done = 0;
+  while (done < num_steps) {
+    const int c = std::min(chunk, num_steps - done);
+    rff_ascent_chunk_kernel<<<total, kAscentThreads, 0, stream>>>(xa, xb, W, b, theta, n, D, d, total, min_val, max_val, c, lr,
+                                                                  eps, f_point);
+    ascent_loss_kernel<<<c + 1, 256, 0, stream>>>(f_point, total, loss);
+    ascent_stop_kernel<<<1, 1, 0, stream>>>(loss, c, rel_tol, stop_dev);
+    h->launches += 3;
+    int stop = -1;
+    e = cudaMemcpyAsync(&stop, stop_dev, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return fail(e, "ascent chunk");
+    if (stop < 0) {
+      std::swap(xa, xb);                      // the chunk's end points start the next chunk
+      done += c;
+    } else {
+      // the early stop fell inside this chunk: the same start points, exactly `stop` steps
+      rff_ascent_chunk_kernel<<<total, kAscentThreads, 0, stream>>>(xa, xb, W, b, theta, n, D, d, total, min_val, max_val, stop,
+                                                                    lr, eps, f_point);
+      h->launches += 1;
+      std::swap(xa, xb);
+      done += stop;
+      break;
+    }
+  }
+  e = cudaMemcpyAsync(X, xa, sizeof(double) * pts, cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(e, "ascent");
   TKBO_CUDA_CHECK(cudaFreeAsync(work, stream));
-  if (steps_run) *steps_run = steps;
+  if (steps_run) *steps_run = done;
   return TKBO_OK;
 }
 
