@@ -413,7 +413,7 @@ def k1_parity(ctx, name, W, b, Theta, rows):
     return out
 
 
-def k1_block(ctx, name, args, precision, steps, warmup, with_e2e, long_run, facts_key, parity_rows=0):
+def k1_block(ctx, name, args, precision, steps, warmup, with_e2e, long_run, parity_rows=0):
     """Time K1 on workload `name`, candidates sharded over the ranks (strong scaling).  Returns the block dict (rank 0)."""
     torch, pkg = ctx.torch, ctx.pkg
     w = WORKLOADS[name]
@@ -555,7 +555,6 @@ def mpes_block(ctx, args):
     P = 60
     ops_per_query = Sm * (C + (1 + C + C * (C - 1) // 2) + P * k + P)      # exp + rcp + mul + add per (sample, query): SURVEY 8(d)
     facts = ncu_facts().get("k2_c5", {})
-    clk = (ctx.sampler.window(time.time() - 0.5, time.time())["sm_mhz"] if ctx.sampler else None) or pk["sm_max_mhz"]
     out = {"metric": "MPES acq evals/s", "value": Q / (mms * 1e-3), "unit": "acq evals/s", "ms_per_call": mms,
            "gpu_launches_per_call": launches / reps,
            "config": {"workload": "c5: 1e5 query sets x 1024 MC samples, k=3 of 5, M=20 maximisers", "Q": Q, "C": C, "k": k,
@@ -756,20 +755,19 @@ def run_gpu(args):
         finish(ctx)
         return
     head = k1_block(ctx, name, args, "auto", args.steps, args.warmup, with_e2e=True, long_run=(name != "c2"),
-                    facts_key=f"k1_{name}_fp32", parity_rows=(1 << 16) if ctx.world == 1 else (1 << 13))
+                    parity_rows=(1 << 16) if ctx.world == 1 else (1 << 13))
     line = headline(head, ctx, args) if ctx.rank == 0 else None
     blocks = {}
     if not args.no_blocks:
         sub_steps = max(5, min(args.steps, 10))
         # the headline shape in the fast contraction form (fp16 hi*hi + one e4m3 correction MMA): opt-in, ~1e-5 ||theta'||
-        fast = k1_block(ctx, name, args, "fast", sub_steps, 3, with_e2e=False, long_run=(name != "c2"),
-                        facts_key=f"k1_{name}_fast")
+        fast = k1_block(ctx, name, args, "fast", sub_steps, 3, with_e2e=False, long_run=(name != "c2"))
         if ctx.rank == 0:
             blocks[f"{name}_fast_form"] = fast
         if ctx.world == 8:
             for other in ("c4",):
                 if other != name:
-                    b4 = k1_block(ctx, other, args, "auto", sub_steps, 3, with_e2e=False, long_run=True, facts_key="k1_c4_fp32")
+                    b4 = k1_block(ctx, other, args, "auto", sub_steps, 3, with_e2e=False, long_run=True)
                     if ctx.rank == 0:
                         blocks[other] = b4
             bd = duel_block(ctx, sub_steps, 3)
@@ -777,7 +775,7 @@ def run_gpu(args):
                 blocks["c4d"] = bd
         if ctx.world == 1:
             if name != "c2":
-                blocks["c2"] = k1_block(ctx, "c2", args, "auto", 20, 5, with_e2e=True, long_run=False, facts_key="k1_c2_fp32",
+                blocks["c2"] = k1_block(ctx, "c2", args, "auto", 20, 5, with_e2e=True, long_run=False,
                                         parity_rows=0 if args.no_cpu else (1 << 16))
             blocks["c5_mpes"] = mpes_block(ctx, args)
             blocks["c1"] = c1_block(ctx, args)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Time the fused argmax kernel with the fp32 and the fast (e4m3 correction) contraction on a few shapes:
     python tools/precision_sweep.py
-Picks out where AUTO should switch (TKBO_PRECISION_AUTO takes fast for sample chunks >= 128)."""
+Shows where the fast form pays (sample chunks >= 128, the tensor-bound regime: SharedBasis(precision="auto", f_scale=...)
+only considers it for S > 96)."""
 import importlib
 import os
 import sys

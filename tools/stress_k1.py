@@ -43,7 +43,7 @@ def main():
         got = Fref[idx, np.arange(S)]
         gap = float(np.max((Fref.max(axis=0) - got) / scale))
         verr = float(np.max(np.abs(val.cpu().numpy() - Fref.max(axis=0)) / scale))
-        msg = f"case {case:3d} N={N:6d} D={D:4d} d={d:2d} S={S:4d} SC={cfg['S_chunk']:3d} ring={cfg['tmem_ring']} npg={cfg['producer_groups']} " \
+        msg = f"case {case:3d} N={N:6d} D={D:4d} d={d:2d} S={S:4d} SC={cfg['S_chunk']:3d} ring={cfg['tmem_ring']} npg={cfg['producer_groups']} pair={cfg['cta_pairs']} " \
               f"stages={cfg['stages']:2d}: eval {err:.1e} argmax-gap {gap:.1e} val {verr:.1e}"
         if d % 2 == 0 and N <= 5000:
             n = min(N, 150)
