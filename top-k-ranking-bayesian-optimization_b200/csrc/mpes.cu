@@ -143,19 +143,32 @@ struct PermWalk {
 // 32 queries at a time (tiles are handed out by a global counter); its warps split the SAMPLES of the tile: warp w takes
 // positions w, w + W, w + 2W, ... of the grouped sample order, whatever group they fall in, so the split is even however
 // skewed the groups are (a maximiser that wins 70 % of the samples is the normal case late in a BO run).  Each warp streams
-// its samples' rows (32*C contiguous floats per sample) through a private shared-memory ring filled by 1-D bulk copies
-// (TMA) kRing rows ahead, or by plain loads when the rows are not 16-byte aligned / the tile is ragged (STAGED = false).
+// its samples' rows (32*C contiguous floats per sample) through a private shared-memory ring filled kRing rows ahead by
+// 16-byte cp.async copies (two coalesced LDGSTS per row and warp; the 1-D TMA bulk copies of round 1 cost ~40 instructions
+// of elect / mbarrier / descriptor work per row, a sixth of the loop), or by plain loads when the rows are not 16-byte
+// aligned / the tile is ragged (STAGED = false).
 // At every group boundary the warps add their partial sums into a block-shared accumulator and the group is folded once.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRing = 4;
+constexpr int kRing = 4;            // power of two
 #ifndef TKBO_MPES_WARPS
 #define TKBO_MPES_WARPS 4           // measured on B200 at c5 (skewed groups, same box): 4 warps 1.25 ms, 8 warps 1.34 ms
 #endif
 constexpr int kMpesWarps = TKBO_MPES_WARPS;
 constexpr int kMpesBlocksPerSm = 16 / kMpesWarps;     // 16 warps of 128 registers fill the register file
 __host__ __device__ constexpr int mpes_warp_smem_bytes(int C) {
-  return ((kRing * 32 * C * 4 + kRing * 8 + 127) / 128) * 128;
+  return ((kRing * 32 * C * 4 + 127) / 128) * 128;
 }
+// one row of 32 * C floats (16-byte aligned) -> shared memory, 16 bytes per lane and instruction; one commit group per row.
+// dst_lane / src_lane already point at this lane's first 16-byte chunk; a row has 8 C <= 64 chunks.
+template <int C>
+__device__ __forceinline__ void row_copy_async(uint32_t dst_lane, const float* src_lane, int lane) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane), "l"(src_lane) : "memory");
+  if (lane + 32 < 8 * C)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane + 512u), "l"(src_lane + 128) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Accurate log(a) for the group fold.  MI is a difference of entropies of size ~log P with a result of 1e-9 .. 1e-1
 // (the eps-smoothed pes.I of a query that cannot move the maximiser is ~1e-9), so the per-group sums
@@ -231,8 +244,9 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
   __shared__ unsigned int gacc[2][P][32];                  // block-wide group sums (fixed point), double-buffered by group
   __shared__ double a_red[W][32];
   __shared__ uint64_t gbar[2];                             // "every warp has delivered its share" per gacc buffer
+  __shared__ unsigned int tot_sh[(P + W - 1) / W][W][32];  // tot_z = sum_m a_z of the orderings a warp owns (fixed point)
   __shared__ int tile_sh;
-  // dynamic shared memory, one private slice per warp: ring | mbarriers (see mpes_warp_smem_bytes)
+  // dynamic shared memory, one private slice per warp: the row ring (see mpes_warp_smem_bytes)
   extern __shared__ __align__(128) unsigned char mpes_smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -240,7 +254,9 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
   for (int i = threadIdx.x; i < 2 * P * 32; i += blockDim.x) (&gacc[0][0][0])[i] = 0u;
   unsigned char* slice = mpes_smem + static_cast<size_t>(wib) * mpes_warp_smem_bytes(C);
   float (*ring)[32 * C] = reinterpret_cast<float (*)[32 * C]>(slice);
-  uint64_t* full = reinterpret_cast<uint64_t*>(slice + kRing * 32 * C * 4);
+  const float* ring_lane = &ring[0][lane * C];             // this lane's C values of slot 0; slot s is 32 C floats further
+  const uint32_t ring_dst = smem_u32(&ring[0][4 * lane]);  // this lane's first 16-byte chunk of slot 0
+  const unsigned int rs32 = static_cast<unsigned int>(Q * C);          // floats per sample row (host checks Q C < 2^31)
   const double invS = 1.0 / static_cast<double>(S);
   const double eps = (mode == TKBO_MPES_PES) ? kPesEps : 0.0;
   const double meps = (mode == TKBO_MPES_PES) ? M * kPesEps : 0.0;
@@ -250,16 +266,11 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
   const double fix_unit = 1.0 / static_cast<double>(1ll << fix_bits);                          // 2^-F
   const long long rowstride = Q * C;
   const int i1 = group_start[M];                           // samples with a valid winner
-  if constexpr (STAGED) {
-    if (lane == 0)
-      for (int i = 0; i < kRing; ++i) mbar_init(&full[i], 1);
-  }
   if (threadIdx.x == 0) {
     mbar_init(&gbar[0], W);
     mbar_init(&gbar[1], W);
   }
   fence_mbar_init();
-  uint32_t ring_phase = 0;                                 // bit i = parity to wait for on slot i
   uint32_t g = 0;                                          // groups delivered so far by this block (runs across tiles)
 
   for (;;) {
@@ -270,23 +281,22 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
     const long long q = static_cast<long long>(tile) * 32 + lane;
     const bool valid = q < Q;
     const float* base = fchi + (valid ? q : Q - 1) * C;                          // direct path
-    const float* tile_base = fchi + static_cast<long long>(tile) * 32 * C;       // staged path
+    const float* tile_base = fchi + static_cast<long long>(tile) * 32 * C + 4 * lane;   // staged path: this lane's first chunk
     float acc[P];
 #pragma unroll
     for (int z = 0; z < P; ++z) acc[z] = 0.f;
-    unsigned int tot_own[kOwn];
 #pragma unroll
-    for (int t = 0; t < kOwn; ++t) tot_own[t] = 0u;
+    for (int t = 0; t < kOwn; ++t) tot_sh[t][wib][lane] = 0u;          // (private to this thread: no synchronisation needed)
     double A = 0.0;
 
     if constexpr (STAGED) {                                // prime the ring with this warp's first kRing rows
-      if (lane == 0) {
-        for (int r = 0; r < kRing && wib + r * W < i1; ++r) {
-          mbar_arrive_expect_tx(&full[r], 32 * C * 4);
-          bulk_load_1d(ring[r], tile_base + static_cast<long long>(order[wib + r * W]) * rowstride, 32 * C * 4, &full[r]);
-        }
+      __syncwarp();                                        // (the previous tile's last rows have been consumed by every lane)
+#pragma unroll
+      for (int r = 0; r < kRing; ++r) {                    // one commit group per slot, empty past the end
+        if (wib + r * W < i1)
+          row_copy_async<C>(ring_dst + r * (32 * C * 4), tile_base + static_cast<size_t>(static_cast<unsigned int>(order[wib + r * W])) * rs32, lane);
+        cp_async_commit();
       }
-      __syncwarp();
     }
     float fnext[C];
     if constexpr (!STAGED) {
@@ -298,7 +308,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
     }
 
     int i = wib;                                           // position in the grouped sample order
-    int n = 0;                                             // samples this warp has consumed (ring slot = n % kRing)
+    unsigned int n = 0;                                    // samples this warp has consumed (ring slot = n % kRing)
     // Software pipeline over the groups: a warp delivers its share of group m and goes straight on to the samples of the
     // next group; it folds group m only after those (by then the other warps have delivered too, so the wait on gbar is
     // normally already satisfied).  Order per warp: samples(m), [wait + fold(previous)], deliver(m), arrive.  Buffer reuse:
@@ -307,7 +317,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
     int prev = -1;                                         // group delivered but not folded yet
     for (int m = 0; m <= M; ++m) {
       const bool tail = (m == M);                          // one extra pass to fold the last group
-      int n_before = n;
+      const unsigned int n_before = n;
       if (!tail) {
         const int hi = group_start[m + 1];
         if (hi == group_start[m] && mode == TKBO_MPES_RANK) continue;   // rank_pes.py:86-93 drops empty groups (block-uniform)
@@ -315,10 +325,10 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
           float f[C];
           if constexpr (STAGED) {
             const int slot = n % kRing;
-            mbar_wait(&full[slot], (ring_phase >> slot) & 1u);
-            ring_phase ^= 1u << slot;
+            cp_async_wait<kRing - 1>();                    // this lane's copies of row n have landed ...
+            __syncwarp();                                  // ... and so have the other lanes'
 #pragma unroll
-            for (int c = 0; c < C; ++c) f[c] = ring[slot][lane * C + c];
+            for (int c = 0; c < C; ++c) f[c] = ring_lane[slot * (32 * C) + c];
           } else {
 #pragma unroll
             for (int c = 0; c < C; ++c) f[c] = fnext[c];
@@ -339,11 +349,10 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
           for (int c = 0; c < C; ++c) e[c] = fmaxf(fast_ex2(fmaf(f[c], kLog2e, -mxs)), 1.17549435e-38f);
           if constexpr (STAGED) {
             __syncwarp();                                  // every lane has consumed its slot values
-            if (lane == 0 && i + kRing * W < i1) {
-              const int slot = n % kRing;
-              mbar_arrive_expect_tx(&full[slot], 32 * C * 4);
-              bulk_load_1d(ring[slot], tile_base + static_cast<long long>(order[i + kRing * W]) * rowstride, 32 * C * 4, &full[slot]);
-            }
+            if (i + kRing * W < i1)
+              row_copy_async<C>(ring_dst + (n % kRing) * (32 * C * 4),
+                                tile_base + static_cast<size_t>(static_cast<unsigned int>(order[i + kRing * W])) * rs32, lane);
+            cp_async_commit();                             // (an empty group past the end keeps the group count in step)
           }
           float rs[1 << C];
           subset_reciprocals<C, K>(e, rs);
@@ -369,7 +378,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
               gacc[buf][z][lane] = 0u;                     // free for the group after next
               if (fx != 0u) s1 = fma(static_cast<double>(fx), table_log_uint(logtab, fx), s1);
               isum += fx;                                  // <= S 2^F <= 2^31 over ALL orderings
-              tot_own[t] += fx;
+              tot_sh[t][wib][lane] += fx;
             }
           }
           s0 = static_cast<double>(isum) * fix_unit;
@@ -391,7 +400,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
                 s1 += ad * la;
                 s0 += ad;
               }
-              tot_own[t] += fx;
+              tot_sh[t][wib][lane] += fx;
             }
           }
         }
@@ -421,9 +430,10 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
       unsigned int isum = 0u;
 #pragma unroll
       for (int t = 0; t < kOwn; ++t) {
-        if (wib + t * W < P && tot_own[t] != 0u) {
-          acc_t = fma(static_cast<double>(tot_own[t]), table_log_uint(logtab, tot_own[t]), acc_t);
-          isum += tot_own[t];
+        const unsigned int tz = tot_sh[t][wib][lane];
+        if (wib + t * W < P && tz != 0u) {
+          acc_t = fma(static_cast<double>(tz), table_log_uint(logtab, tz), acc_t);
+          isum += tz;
         }
       }
       A -= (acc_t - shift * static_cast<double>(isum)) * fix_unit * invS;
@@ -431,7 +441,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
 #pragma unroll
       for (int t = 0; t < kOwn; ++t) {
         if (wib + t * W < P) {
-          const double pz = (static_cast<double>(tot_own[t]) * fix_unit + meps) * invS;
+          const double pz = (static_cast<double>(tot_sh[t][wib][lane]) * fix_unit + meps) * invS;
           if (pz > 0.0) A -= pz * log(pz);
         }
       }
@@ -716,6 +726,7 @@ int mpes_topk(tkbo_handle_t h, const float* fchi, const int32_t* fstar_argmax, i
   TKBO_REQUIRE(h && fchi && fstar_argmax && out_mi, "null pointer");
   TKBO_REQUIRE(S >= 1 && Q >= 1 && Q < (int64_t(1) << 31) && M >= 1, "S, Q, M must be >= 1 and Q < 2^31");
   TKBO_REQUIRE(C >= 1 && C <= kGenMaxC && k >= 1 && k <= C, "need 1 <= k <= C <= 8");
+  TKBO_REQUIRE(Q * C < (int64_t(1) << 31), "Q * C must stay below 2^31");
   TKBO_REQUIRE(mode == TKBO_MPES_RANK || mode == TKBO_MPES_PES, "unknown mode");
   if (mode == TKBO_MPES_PES) TKBO_REQUIRE(k == 1 && perms == nullptr, "PES mode is top-1 with the implicit table");
   const bool fast = perms == nullptr && has_all_perms_kernel(C, k);
