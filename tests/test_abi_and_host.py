@@ -34,7 +34,7 @@ def test_library_is_sm100a_with_tcgen05_and_tma(pbo):
         pytest.skip("cuobjdump unavailable")
     sass = out.stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "CREDUX", "UBLKCP"):
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTCQMMA", "UTMALDG", "UTCBAR.2CTA.MULTICAST", "LDTM", "STTM", "CREDUX", "LDGSTS"):
         assert mnemonic in sass, mnemonic
 
 

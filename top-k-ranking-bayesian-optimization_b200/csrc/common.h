@@ -1,6 +1,7 @@
 // Host-side state shared by the translation units of libtkbo.so.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

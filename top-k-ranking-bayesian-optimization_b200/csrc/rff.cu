@@ -12,6 +12,7 @@
 
 #include "common.h"
 #include "rff_fused.cuh"
+#include "rff_launch.cuh"
 
 namespace tkbo {
 
@@ -537,60 +538,17 @@ int basis_set(tkbo_handle_t h, tkbo_basis_t bs, const double* W, const double* b
   return TKBO_OK;
 }
 
-template <int DT, int MODE, int NPG, bool C8>
-static int launch_fused_c(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
-  if constexpr (NPG != 4) {
-    if (bs->pair) {
-      // clusters of two CTAs (one TPC): an even grid, one item stream per pair
-      auto kern = rff_fused_kernel<DT, MODE, NPG, C8, true>;
-      TKBO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs->smem_bytes));
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
-      cfg.blockDim = dim3(kNumThreadsPair(NPG), 1, 1);
-      cfg.dynamicSmemBytes = static_cast<size_t>(bs->smem_bytes);
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      TKBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, bs->tm_hi, bs->tm_lo, bs->tm_w, p));
-      h->launches += 1;
-      return TKBO_OK;
-    }
-  }
-  auto kern = rff_fused_kernel<DT, MODE, NPG, C8>;
-  TKBO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bs->smem_bytes));
-  kern<<<grid, kNumThreadsFor(NPG), bs->smem_bytes, stream>>>(bs->tm_hi, bs->tm_lo, bs->tm_w, p);
-  h->launches += 1;
-  TKBO_CUDA_CHECK(cudaGetLastError());
-  return TKBO_OK;
-}
-
-template <int DT, int MODE, int NPG>
-static int launch_fused_n(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
-  return bs->corr8 ? launch_fused_c<DT, MODE, NPG, true>(h, bs, p, grid, stream)
-                   : launch_fused_c<DT, MODE, NPG, false>(h, bs, p, grid, stream);
-}
-
-template <int DT, int MODE>
-static int launch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
-  return bs->npg == 4 ? launch_fused_n<DT, MODE, 4>(h, bs, p, grid, stream)
-         : bs->npg == 3 ? launch_fused_n<DT, MODE, 3>(h, bs, p, grid, stream)
-                        : launch_fused_n<DT, MODE, 2>(h, bs, p, grid, stream);
-}
-
 template <int MODE>
 static int dispatch_fused(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
   switch (bs->DT) {
-    case 1: if constexpr (MODE != 2) return launch_fused<1, MODE>(h, bs, p, grid, stream); else break;
-    case 2: return launch_fused<2, MODE>(h, bs, p, grid, stream);
-    case 3: if constexpr (MODE != 2) return launch_fused<3, MODE>(h, bs, p, grid, stream); else break;
-    case 4: return launch_fused<4, MODE>(h, bs, p, grid, stream);
-    case 6: return launch_fused<6, MODE>(h, bs, p, grid, stream);
-    case 8: return launch_fused<8, MODE>(h, bs, p, grid, stream);
-    case 12: return launch_fused<12, MODE>(h, bs, p, grid, stream);
-    case 16: return launch_fused<16, MODE>(h, bs, p, grid, stream);
+    case 1: return fused_launch_dt<1>(MODE, h, bs, p, grid, stream);
+    case 2: return fused_launch_dt<2>(MODE, h, bs, p, grid, stream);
+    case 3: return fused_launch_dt<3>(MODE, h, bs, p, grid, stream);
+    case 4: return fused_launch_dt<4>(MODE, h, bs, p, grid, stream);
+    case 6: return fused_launch_dt<6>(MODE, h, bs, p, grid, stream);
+    case 8: return fused_launch_dt<8>(MODE, h, bs, p, grid, stream);
+    case 12: return fused_launch_dt<12>(MODE, h, bs, p, grid, stream);
+    case 16: return fused_launch_dt<16>(MODE, h, bs, p, grid, stream);
   }
   set_error("internal: unsupported DT");
   return TKBO_ERR_UNSUPPORTED;
