@@ -467,6 +467,7 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
   // operands.  Needs the split candidate rows in TMEM (not the four-group form) and an even SM count; a stage is half as
   // large, so the combined ring is deep enough without the separate (W | b) ring.  TKBO_PAIR=0/1 overrides the default.
   bs->pair = 0;
+  bs->halves = 0;
   {
     const char* env = getenv("TKBO_PAIR");
     const bool want = env != nullptr ? atoi(env) != 0 : kPairDefault;
@@ -486,6 +487,9 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
         if (const char* e2 = getenv("TKBO_NPG")) { const int t = atoi(e2); if (t == 2 || t == 3) bs->npg = t; }
         if (const char* e3 = getenv("TKBO_COOP")) bs->coop = (bs->npg == 2 && atoi(e3) != 0) ? 1 : 0;
         bs->smem_bytes = st * stride_p + 2 * proj_x_bytes(DT) + 1024;
+        // single accumulator buffer: retire it in two column halves (rff_fused.cuh, RffParams::halves)
+        const char* eh = getenv("TKBO_HALVES");
+        bs->halves = (bs->acc_bufs == 1 && bs->SC % 64 == 0 && !(eh != nullptr && atoi(eh) == 0)) ? 1 : 0;
       }
     }
   }
@@ -507,7 +511,7 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
     free_basis(bs);
     return TKBO_ERR_NOMEM;
   }
-  const int th_rows = bs->pair ? bs->SC / 2 : bs->SC;
+  const int th_rows = bs->pair ? (bs->halves ? bs->SC / 4 : bs->SC / 2) : bs->SC;      // Theta rows per TMA box
   int rc = make_theta_map(h, &bs->tm_hi, bs->theta_hi, bs->Salloc, bs->Dpad, th_rows);
   if (rc == TKBO_OK) rc = make_theta_map(h, &bs->tm_lo, bs->theta_lo, bs->Salloc, bs->Dpad, th_rows, bs->corr8 != 0);
   if (rc == TKBO_OK) rc = make_wproj_map(h, &bs->tm_w, bs->Wproj, bs->Dpad, DT, bs->pair ? kSlabK / 2 : kSlabK);
@@ -581,7 +585,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->debug = 0;
   if (const char* env = getenv("TKBO_DEBUG")) p->debug = atoi(env);
   p->trace = h->trace; p->trace_cap = h->trace_cap;
-  p->pair = bs->pair;
+  p->pair = bs->pair; p->halves = bs->halves;
   *grid = fused_grid(h, bs, mt);
   return TKBO_OK;
 }
@@ -878,7 +882,7 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   p.score_fix = reinterpret_cast<unsigned long long*>(fix);
   p.debug = 0;
   p.trace = nullptr; p.trace_cap = 0;
-  p.pair = bs->pair;
+  p.pair = bs->pair; p.halves = bs->halves;
   const int grid = fused_grid(h, bs, mt);
   return dispatch_fused<2>(h, bs, p, grid, stream);
 }

@@ -129,6 +129,8 @@ struct RffParams {
   int wstages;               // 0: the (W | b) tile of a slab travels in its Theta stage; > 0: it has its own ring of this
                              // depth, so projections + feature producers run ahead of the (few, large) Theta stages
   int pair;                  // 1: launched as clusters of two CTAs that share every tcgen05.mma (template PAIR)
+  int halves;                // 1 (pairs, one accumulator buffer, SC % 64 == 0): the accumulator is retired in two column halves,
+                             // so the next item's first MMAs overlap the read-out of the second half
   int duel_n;                // > 0: the candidates are the ordered pairs [x_i, x_j] of duel_n base points of dimension d / 2
                              // held in X (dts.py:31-45); a tile = one i and 128 consecutive j; never materialised
   int duel_j0, duel_nj;      // this launch's shard of the second argument: j in [duel_j0, duel_j0 + duel_nj)
@@ -385,9 +387,21 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             const uint32_t sb = smem0 + st * sbytes;
             const uint32_t full_c = bar0_lead + 8 * (kBFull + st);
             if (leader) mbar_arrive_expect_tx(bar0 + 8 * (kBFull + st), 2u * pair_stage_tx_bytes(SC, DT));
-            const int row0 = chunk * SC + static_cast<int>(cta) * th_rows;
-            tma_load_2d_pair(sb, &tm_hi, full_c, slab * kSlabK, row0);
-            tma_load_2d_pair(sb + th_rows * 128, &tm_lo, full_c, slab * kSlabK * (C8 ? 2 : 1), row0);
+            if (p.halves) {
+              // column half h of the accumulator = samples [h SC/2, (h+1) SC/2) of the chunk; an MMA of N = SC / 2 takes
+              // SC / 4 of its B rows from each CTA, so this CTA keeps rows [h SC/2 + cta SC/4, + SC/4) at offset h SC/4
+              const int qr = SC / 4;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int row0 = chunk * SC + hh * (SC / 2) + static_cast<int>(cta) * qr;
+                tma_load_2d_pair(sb + hh * qr * 128, &tm_hi, full_c, slab * kSlabK, row0);
+                tma_load_2d_pair(sb + th_rows * 128 + hh * qr * 128, &tm_lo, full_c, slab * kSlabK * (C8 ? 2 : 1), row0);
+              }
+            } else {
+              const int row0 = chunk * SC + static_cast<int>(cta) * th_rows;
+              tma_load_2d_pair(sb, &tm_hi, full_c, slab * kSlabK, row0);
+              tma_load_2d_pair(sb + th_rows * 128, &tm_lo, full_c, slab * kSlabK * (C8 ? 2 : 1), row0);
+            }
 #pragma unroll
             for (int t = 0; t < proj_tiles(DT); ++t)
               tma_load_2d_pair(sb + 2 * th_rows * 128 + t * kPTile, &tm_w, full_c, t * 64,
@@ -529,7 +543,79 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t desc_lopart = static_cast<uint32_t>(th_rows * 128) >> 4;     // Theta-lo tile follows the hi tile
     const bool hi_only = (p.debug & 1) != 0;
     const bool pairing = ring >= 5 && !(p.debug & 8);  // a pair holds two ring slots while its MMAs run
-    const int total_main = (PAIR && (h != 0 || !leader)) ? 0 : total;
+    const bool halves = PAIR && p.halves;
+    const int total_main = (PAIR && (h != 0 || !leader || halves)) ? 0 : total;
+    if constexpr (PAIR) {
+      if (halves && h == 0 && leader) {
+        // One accumulator buffer retired in two column halves.  Per item: the half-0 MMAs of the first `lead` slabs go out
+        // as soon as the epilogue has drained half 0 of the previous item, i.e. while it is still reading half 1; then,
+        // once half 1 is free, their half-1 MMAs and the stage releases; the remaining slabs issue both halves in turn.
+        // Every column still sees its MMAs in slab order (deterministic accumulation).
+        const int NQ = SC >> 1;
+        const uint32_t idh = idesc_f16_f32(2 * kTileM, NQ);
+        const uint32_t idh8 = idesc_e4m3_f32(2 * kTileM, NQ);
+        const uint32_t b_half = static_cast<uint32_t>((SC / 4) * 128) >> 4;     // rows of half 1 inside a Theta tile
+        auto issue_half = [&](int st_, int slot_, int sl, int hh) {
+          const uint32_t d_tmem = tmem_base + hh * NQ;
+          const uint32_t b_hi = desc_lo0 + st_ * desc_stage + hh * b_half;
+          const uint32_t b_lo = b_hi + desc_lopart;
+          const uint32_t a_st = tmem_base + ring_col0 + slot_ * kSlabK;
+#pragma unroll
+          for (int k = 0; k < kSlabK / kUmmaK; ++k) {
+            const uint32_t koff = k * ((kUmmaK * 2) >> 4);
+            const uint32_t a_hi = a_st + k * kUmmaK;
+            const uint32_t a_lo = a_hi + kUmmaK / 2;
+            mma_f16_ts_pair(d_tmem, a_hi, smem_desc_from_lo(b_hi + koff), idh, (sl | k) != 0);
+            if (!hi_only) {
+              if constexpr (C8) {
+                mma_f8_ts_pair(d_tmem, a_lo, smem_desc_from_lo(b_lo + koff), idh8, 1);
+              } else {
+                mma_f16_ts_pair(d_tmem, a_hi, smem_desc_from_lo(b_lo + koff), idh, 1);
+                mma_f16_ts_pair(d_tmem, a_lo, smem_desc_from_lo(b_hi + koff), idh, 1);
+              }
+            }
+          }
+        };
+        int st = 0, slot = 0;
+        uint32_t sph = 0, eph = 0;
+        const int lead = ring < n_slabs ? ring : n_slabs;
+        for (int item = 0; item < my_items; ++item) {
+          // phase A: half 0 of the first `lead` slabs (their ring slots and stages stay held)
+          mbar_wait_cluster(bar0 + 8 * (kAccEmpty + 0), eph ^ 1);
+          {
+            int st_a = st, slot_a = slot;
+            uint32_t sph_a = sph;
+            for (int t = 0; t < lead; ++t) {
+              mbar_wait_cluster(bar0 + 8 * (kAFull + slot_a), sph_a);
+              tc_fence_after();
+              if (elect_one()) issue_half(st_a, slot_a, t, 0);
+              __syncwarp();
+              if (++st_a == stages) st_a = 0;
+              if (++slot_a == ring) { slot_a = 0; sph_a ^= 1; }
+            }
+          }
+          // phase B: their half-1 MMAs, then the stages / slots are released
+          mbar_wait_cluster(bar0 + 8 * (kAccEmpty + 1), eph ^ 1);
+          tc_fence_after();
+          for (int t = 0; t < n_slabs; ++t) {
+            if (t >= lead) {
+              mbar_wait_cluster(bar0 + 8 * (kAFull + slot), sph);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              if (t >= lead) issue_half(st, slot, t, 0);
+              issue_half(st, slot, t, 1);
+              tc_commit_pair(bar0 + 8 * (kBEmpty + st), 3);
+              if (t == n_slabs - 1) tc_commit_pair(bar0 + 8 * (kAccFull + 0), 3);
+            }
+            __syncwarp();
+            if (++st == stages) st = 0;
+            if (++slot == ring) { slot = 0; sph ^= 1; }
+          }
+          eph ^= 1;
+        }
+      }
+    }
     int st = 0, slot = 0, ab = 0, slab = 0, nitem = 0;
     uint32_t sph = 0, aph = 0, bph = 0;
     // combined mode: a_full implies (through p_full and the projection warp's wait) that the stage's Theta tiles have
@@ -823,9 +909,16 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       const bool partial = (row0 + 32 > p.N);
       const bool row_ok = row < p.N;
       const uint32_t acc = tmem_base + lane_base + ab * SC;
+      const bool halves = PAIR && p.halves;
+      const int half_blocks = SC / 64;                 // 32-column blocks per accumulator half (halves mode)
+      // halves mode: blocks [0, half_blocks) first, then acc_empty[0] is released while the second half is read
+#pragma unroll 1
+      for (int part = 0; part < (halves ? 2 : 1); ++part) {
+      const int j_begin = halves ? part * half_blocks + eset : eset;
+      const int j_end = halves ? (part + 1) * half_blocks : SC / 32;
       if (row0 < p.N && mtile < p.n_mtiles) {        // else: whole warp beyond the last candidate (warp-uniform)
 #pragma unroll 1
-        for (int j = eset; j < SC / 32; j += kEpiSets) {
+        for (int j = j_begin; j < j_end; j += kEpiSets) {
           uint32_t v[32];
           tmem_ld_x32(acc + j * 32, v);
           tmem_wait_ld();
@@ -916,7 +1009,11 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster_relaxed(bar0_lead + 8 * (kAccEmpty + ab)); else mbar_arrive(bar0 + 8 * (kAccEmpty + ab)); }
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster_relaxed(bar0_lead + 8 * (kAccEmpty + (halves ? part : ab)));
+        else mbar_arrive(bar0 + 8 * (kAccEmpty + ab));
+      }
+      }   // part
       if (warp == 0) trace_event(p, kTrEpiDone, nitem);
       if (++ab == acc_bufs) { ab = 0; aph ^= 1; }
       if (eset == 0) stage_rows(nitem + xa_bufs);
