@@ -42,6 +42,12 @@ def classify(name):
     return None, False
 
 
+# what one captured launch of tools/profile_cmd.py processes (bench.py scales the measured DRAM bytes by its own units / these)
+UNITS = {"k1_c3_fp32": {"units_per_launch": 1 << 21, "unit": "candidates"},
+         "k1_c3_fast": {"units_per_launch": 1 << 21, "unit": "candidates"},
+         "k1_c2_fp32": {"units_per_launch": 1 << 20, "unit": "candidates"},
+         "k1_c4d_fast": {"units_per_launch": 2048 * 256, "unit": "candidates"},
+         "k2_c5": {"units_per_launch": 100000, "unit": "query sets"}}
 rows_all = []
 for rep in reps:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -74,6 +80,7 @@ for rep, rows in rows_all:
         "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
         "registers_per_thread": num(r, "launch__registers_per_thread"),
         "sm_cycles": num(r, "sm__cycles_elapsed.avg")}
+    facts[key].update(UNITS.get(key, {}))
 with open(out, "w") as fh:
     json.dump(facts, fh, indent=1)
 print(json.dumps(facts, indent=1))

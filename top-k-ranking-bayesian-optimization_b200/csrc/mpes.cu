@@ -99,20 +99,25 @@ __device__ __forceinline__ float fast_rcp(float x) {      // raw MUFU.RCP, ~1 ul
 // 1 / (sum of e over the choices NOT in mask) for every mask with fewer than K members: the Plackett-Luce
 // denominators depend on the *set* of already-ranked choices only, so C=5, K=3 needs 1 + 5 + 10 reciprocals for
 // its 60 orderings.  Sums are taken directly over the remaining entries (no T - e_a cancellation).
+// The sum over a set is the sum over the set without its lowest member plus that member, so every set costs one addition
+// (26 for C = 5; the compiler drops the sets nothing needs).
+__host__ __device__ constexpr int lowest_bit_c(unsigned m) {
+  int c = 0;
+  for (; !((m >> c) & 1u); ++c) {}
+  return c;
+}
 template <int C, int K>
 __device__ __forceinline__ void subset_reciprocals(const float (&e)[C], float (&rs)[1 << C]) {
+  float ss[1 << C];                                        // ss[set] = sum of e over the set
+#pragma unroll
+  for (unsigned set = 1; set < (1u << C); ++set) {
+    const unsigned rest = set & (set - 1u);
+    ss[set] = (rest == 0u) ? e[lowest_bit_c(set)] : ss[rest] + e[lowest_bit_c(set)];
+  }
 #pragma unroll
   for (unsigned m = 0; m < (1u << C); ++m) {
     if (popcount_c(m) >= K || popcount_c(m) >= C - 1) continue;       // a lone remaining choice has probability 1
-    float s = 0.f;
-    bool first = true;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      if ((m >> c) & 1u) continue;
-      s = first ? e[c] : s + e[c];
-      first = false;
-    }
-    rs[m] = fast_rcp(s);                                  // s > 0: the callers keep every e[c] >= 2^-126
+    rs[m] = fast_rcp(ss[((1u << C) - 1u) & ~m]);          // > 0: the callers keep every e[c] >= 2^-126
   }
 }
 
@@ -133,6 +138,44 @@ struct PermWalk {
       } else {
         const float child = (remaining > 1) ? pr * e[c] : pr;
         PermWalk<C, K, DEPTH + 1>::run(e, rs, used | (1u << c), child, acc, leaf);
+      }
+    }
+  }
+};
+
+// Packed walk (K >= 2): sm_100's two-wide fp32 instructions (FMUL2 / FFMA2, one issue slot for two results) with the two
+// halves working on mirror images of each other.  Relabelling the choices c -> C-1-c maps orderings onto orderings without
+// fixed points, so the walk visits only the prefixes that are lexicographically <= their mirror image, carries
+// (prob(prefix), prob(mirror prefix)) and multiplies by (e_c, e_{C-1-c}) and (rs[used], rs[mirror(used)]): half the
+// multiply / accumulate instructions of PermWalk for the same P results.  acc[j] = (ordering j, its mirror image).
+__host__ __device__ constexpr unsigned mask_mirror(unsigned m, int C) {
+  unsigned r = 0;
+  for (int c = 0; c < C; ++c)
+    if ((m >> c) & 1u) r |= 1u << (C - 1 - c);
+  return r;
+}
+template <int C, int K, int DEPTH>
+struct PermWalk2 {
+  // tied: the prefix so far equals its own mirror image (empty, or the middle choice of an odd C)
+  template <int P2>
+  static __device__ __forceinline__ void run(const float2 (&e2)[C], const float (&rs)[1 << C], unsigned used, bool tied,
+                                             float2 prob, float2 (&acc)[P2], int& leaf) {
+    constexpr int remaining = C - DEPTH;
+    float2 pr = prob;
+    if constexpr (remaining > 1) {
+      const float2 r2 = make_float2(rs[used], rs[mask_mirror(used, C)]);
+      pr = (DEPTH == 0) ? r2 : __fmul2_rn(prob, r2);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if ((used >> c) & 1u) continue;
+      if (tied && c > C - 1 - c) continue;                 // its mirror image is the one that is walked
+      if constexpr (DEPTH + 1 == K) {
+        acc[leaf] = (remaining > 1) ? __ffma2_rn(pr, e2[c], acc[leaf]) : __fadd2_rn(acc[leaf], pr);
+        ++leaf;
+      } else {
+        const float2 child = (remaining > 1) ? __fmul2_rn(pr, e2[c]) : pr;
+        PermWalk2<C, K, DEPTH + 1>::run(e2, rs, used | (1u << c), tied && (c == C - 1 - c), child, acc, leaf);
       }
     }
   }
@@ -194,13 +237,18 @@ __device__ __forceinline__ void log_table_fill(LogTable& tab, int tid) {
 }
 // log(n) for an integer n >= 1, all in float64 (about 1e-15): n = 2^E v 2^-31 with v in [2^31, 2^32), k = the 7 bits below
 // v's leading one, x = v rd[k] - 1 exactly (32 x 9 bits), log1p(x) = x (1 - x/2 + x^2/3 - x^3/4) up to x^5/5 < 2e-12.
+// exact uint32 -> float64 on the float64 pipe (2^52 + n, minus 2^52): the I2F.F64 conversions run on the 16-lane XU
+// pipe, which the sample loop already saturates
+__device__ __forceinline__ double u32_to_double(unsigned int n) {
+  return __hiloint2double(0x43300000, static_cast<int>(n)) - 4503599627370496.0;
+}
 __device__ __forceinline__ double table_log_uint(const LogTable& tab, unsigned int n) {
   const int lz = __clz(static_cast<int>(n));
   const unsigned int v = n << lz;
   const unsigned int k = (v >> 24) & 127u;
-  const double x = fma(static_cast<double>(v), tab.rd[k], -1.0);
+  const double x = fma(u32_to_double(v), tab.rd[k], -1.0);
   const double p = fma(x, fma(x, fma(x, -0.25, 0.3333333333333333), -0.5), 1.0);
-  return fma(static_cast<double>(31 - lz), 0.6931471805599453, fma(x, p, tab.t[k]));
+  return fma(u32_to_double(static_cast<unsigned int>(31 - lz)), 0.6931471805599453, fma(x, p, tab.t[k]));
 }
 // log(a) for a normal positive float a
 __device__ __forceinline__ double table_log(const LogTable& tab, float a) {
@@ -235,6 +283,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
   constexpr int P = perm_count(C, K);
   constexpr int W = kMpesWarps;
   constexpr int kOwn = (P + W - 1) / W;                    // orderings folded by one warp
+  constexpr bool kPacked = (K >= 2);                       // PermWalk2 (P is even then)
   constexpr float kLog2e = 1.4426950408889634f;
   // exponent offset: e_c = 2^((f_c - max) log2e + 120), so that choices up to 246 binades (170 nats) below the best one stay
   // normal floats (the sums stay below 2^127, every stage factor e * rs is scale free); rank_pes.py:166 renormalises per
@@ -282,9 +331,12 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
     const bool valid = q < Q;
     const float* base = fchi + (valid ? q : Q - 1) * C;                          // direct path
     const float* tile_base = fchi + static_cast<long long>(tile) * 32 * C + 4 * lane;   // staged path: this lane's first chunk
-    float acc[P];
+    float acc[kPacked ? 1 : P];                            // K = 1: one accumulator per ordering
+    float2 acc2[kPacked ? P / 2 : 1];                      // K >= 2: (ordering j, its mirror image = ordering j + P/2)
 #pragma unroll
-    for (int z = 0; z < P; ++z) acc[z] = 0.f;
+    for (int z = 0; z < (kPacked ? 1 : P); ++z) acc[z] = 0.f;
+#pragma unroll
+    for (int z = 0; z < (kPacked ? P / 2 : 1); ++z) acc2[z] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < kOwn; ++t) tot_sh[t][wib][lane] = 0u;          // (private to this thread: no synchronisation needed)
     double A = 0.0;
@@ -357,7 +409,14 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
           float rs[1 << C];
           subset_reciprocals<C, K>(e, rs);
           int leaf = 0;
-          PermWalk<C, K, 0>::run(e, rs, 0u, 1.f, acc, leaf);
+          if constexpr (kPacked) {
+            float2 e2[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) e2[c] = make_float2(e[c], e[C - 1 - c]);
+            PermWalk2<C, K, 0>::run(e2, rs, 0u, true, make_float2(1.f, 1.f), acc2, leaf);
+          } else {
+            PermWalk<C, K, 0>::run(e, rs, 0u, 1.f, acc, leaf);
+          }
         }
       }
       if (prev >= 0) {
@@ -376,7 +435,8 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
             if (z < P) {
               const unsigned int fx = gacc[buf][z][lane];
               gacc[buf][z][lane] = 0u;                     // free for the group after next
-              if (fx != 0u) s1 = fma(static_cast<double>(fx), table_log_uint(logtab, fx), s1);
+              // branch-free (0 log 1 = 0): the P / W logarithms of a fold are independent chains the compiler can interleave
+              s1 = fma(u32_to_double(fx), table_log_uint(logtab, fx | static_cast<unsigned int>(fx == 0u)), s1);
               isum += fx;                                  // <= S 2^F <= 2^31 over ALL orderings
               tot_sh[t][wib][lane] += fx;
             }
@@ -393,13 +453,14 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
               // a = grid sum + eps in float64 (eps = 1e-7 is below float32 resolution of a sum of ~S/M probabilities, and
               // pes.I of an uninformative query consists of nothing but these eps terms):
               // log a = log(fl32(a)) + (a - fl32(a)) / fl32(a)
-              const double ad = static_cast<double>(fx) * fix_unit + eps;
-              const float af = static_cast<float>(ad);
-              if (af >= 1e-30f) {                          // below: a log a < 7e-29, and no denormal handling needed
-                const double la = table_log(logtab, af) + (ad - static_cast<double>(af)) * static_cast<double>(fast_rcp(af));
-                s1 += ad * la;
-                s0 += ad;
-              }
+              const double ad = u32_to_double(fx) * fix_unit + eps;
+              const float af0 = static_cast<float>(ad);
+              const bool tiny = !(af0 >= 1e-30f);          // a log a < 7e-29: dropped (and no denormal handling needed)
+              const float af = tiny ? 1.f : af0;           // branch-free: independent chains
+              const double adk = tiny ? 0.0 : ad;
+              const double la = table_log(logtab, af) + (adk - static_cast<double>(af)) * static_cast<double>(fast_rcp(af));
+              s1 = fma(adk, tiny ? 0.0 : la, s1);
+              s0 += adk;
               tot_sh[t][wib][lane] += fx;
             }
           }
@@ -412,10 +473,19 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
       // that saw no sample of the group (groups smaller than the block) only arrives
       const int buf = static_cast<int>(g & 1u);
       if (n != n_before) {
+        if constexpr (kPacked) {
 #pragma unroll
-        for (int z = 0; z < P; ++z) {
-          atomicAdd(&gacc[buf][z][lane], __float2uint_rn(acc[z] * fix_scale));
-          acc[z] = 0.f;
+          for (int z = 0; z < P / 2; ++z) {
+            atomicAdd(&gacc[buf][z][lane], __float2uint_rn(acc2[z].x * fix_scale));
+            atomicAdd(&gacc[buf][z + P / 2][lane], __float2uint_rn(acc2[z].y * fix_scale));
+            acc2[z] = make_float2(0.f, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int z = 0; z < P; ++z) {
+            atomicAdd(&gacc[buf][z][lane], __float2uint_rn(acc[z] * fix_scale));
+            acc[z] = 0.f;
+          }
         }
       }
       __syncwarp();
@@ -430,11 +500,9 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
       unsigned int isum = 0u;
 #pragma unroll
       for (int t = 0; t < kOwn; ++t) {
-        const unsigned int tz = tot_sh[t][wib][lane];
-        if (wib + t * W < P && tz != 0u) {
-          acc_t = fma(static_cast<double>(tz), table_log_uint(logtab, tz), acc_t);
-          isum += tz;
-        }
+        const unsigned int tz = (wib + t * W < P) ? tot_sh[t][wib][lane] : 0u;
+        acc_t = fma(u32_to_double(tz), table_log_uint(logtab, tz | static_cast<unsigned int>(tz == 0u)), acc_t);
+        isum += tz;
       }
       A -= (acc_t - shift * static_cast<double>(isum)) * fix_unit * invS;
     } else {

@@ -16,6 +16,7 @@
 
 namespace tkbo {
 
+constexpr int kHalvesDefault = 2;       // 1: the start of an item overlaps the read-out of half 1; 2: also mirror it at the end
 constexpr bool kPairDefault = true;     // CTA pairs (cta_group::2) wherever they apply: 4-18 % faster on B200; TKBO_PAIR=0 switches them off
 
 // ------------------------------------------------------------------------------------------------
@@ -489,7 +490,7 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
         bs->smem_bytes = st * stride_p + 2 * proj_x_bytes(DT) + 1024;
         // single accumulator buffer: retire it in two column halves (rff_fused.cuh, RffParams::halves)
         const char* eh = getenv("TKBO_HALVES");
-        bs->halves = (bs->acc_bufs == 1 && bs->SC % 64 == 0 && !(eh != nullptr && atoi(eh) == 0)) ? 1 : 0;
+        bs->halves = (bs->acc_bufs == 1 && bs->SC % 64 == 0) ? (eh != nullptr ? atoi(eh) : kHalvesDefault) : 0;   // 0 / 1 / 2
       }
     }
   }

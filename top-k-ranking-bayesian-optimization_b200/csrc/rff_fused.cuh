@@ -594,10 +594,13 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
               if (++slot_a == ring) { slot_a = 0; sph_a ^= 1; }
             }
           }
-          // phase B: their half-1 MMAs, then the stages / slots are released
+          // phase B: their half-1 MMAs, then the stages / slots are released; the middle slabs issue both halves in turn
           mbar_wait_cluster(bar0 + 8 * (kAccEmpty + 1), eph ^ 1);
           tc_fence_after();
-          for (int t = 0; t < n_slabs; ++t) {
+          // the last `tail` slabs mirror the start: all their half-0 MMAs first (half 0 is then complete and the epilogue
+          // starts on it), then their half-1 MMAs, which run while half 0 is read
+          const int tail = (p.halves >= 2 && n_slabs >= 2 * lead) ? lead : 0;
+          for (int t = 0; t < n_slabs - tail; ++t) {
             if (t >= lead) {
               mbar_wait_cluster(bar0 + 8 * (kAFull + slot), sph);
               tc_fence_after();
@@ -606,11 +609,39 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
               if (t >= lead) issue_half(st, slot, t, 0);
               issue_half(st, slot, t, 1);
               tc_commit_pair(bar0 + 8 * (kBEmpty + st), 3);
-              if (t == n_slabs - 1) tc_commit_pair(bar0 + 8 * (kAccFull + 0), 3);
+              if (t == n_slabs - 1) {
+                tc_commit_pair(bar0 + 8 * (kAccFull + 0), 3);
+                tc_commit_pair(bar0 + 8 * (kAccFull + 1), 3);
+              }
             }
             __syncwarp();
             if (++st == stages) st = 0;
             if (++slot == ring) { slot = 0; sph ^= 1; }
+          }
+          if (tail > 0) {
+            int st_c = st, slot_c = slot;
+            uint32_t sph_c = sph;
+            for (int t = n_slabs - tail; t < n_slabs; ++t) {
+              mbar_wait_cluster(bar0 + 8 * (kAFull + slot_c), sph_c);
+              tc_fence_after();
+              if (elect_one()) {
+                issue_half(st_c, slot_c, t, 0);
+                if (t == n_slabs - 1) tc_commit_pair(bar0 + 8 * (kAccFull + 0), 3);
+              }
+              __syncwarp();
+              if (++st_c == stages) st_c = 0;
+              if (++slot_c == ring) { slot_c = 0; sph_c ^= 1; }
+            }
+            for (int t = n_slabs - tail; t < n_slabs; ++t) {
+              if (elect_one()) {
+                issue_half(st, slot, t, 1);
+                tc_commit_pair(bar0 + 8 * (kBEmpty + st), 3);
+                if (t == n_slabs - 1) tc_commit_pair(bar0 + 8 * (kAccFull + 1), 3);
+              }
+              __syncwarp();
+              if (++st == stages) st = 0;
+              if (++slot == ring) { slot = 0; sph ^= 1; }
+            }
           }
           eph ^= 1;
         }
@@ -914,6 +945,10 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       // halves mode: blocks [0, half_blocks) first, then acc_empty[0] is released while the second half is read
 #pragma unroll 1
       for (int part = 0; part < (halves ? 2 : 1); ++part) {
+      if (part == 1) {                                 // half 1 has its own completion (it may trail half 0)
+        mbar_wait(bar0 + 8 * (kAccFull + 1), aph);
+        tc_fence_after();
+      }
       const int j_begin = halves ? part * half_blocks + eset : eset;
       const int j_end = halves ? (part + 1) * half_blocks : SC / 32;
       if (row0 < p.N && mtile < p.n_mtiles) {        // else: whole warp beyond the last candidate (warp-uniform)
