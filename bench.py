@@ -571,8 +571,13 @@ def mpes_block(ctx, args):
                                        "frac": ops_per_query * Q / (mms * 1e-3) / (148 * 128 * pk["sm_max_mhz"] * 1e6),
                                        "issue_active_pct_ncu": facts.get("issue_active_pct"),
                                        "note": "SURVEY 8(d)'s second bound: S*(C exp + 16 rcp + P*k mul + P add) lane-operations "
-                                               "per query against 148 SMs x 128 lanes x max SM clock; the kernel executes ~230 "
-                                               "warp-instructions per (sample, 32 queries), so the issue slots, not HBM, bind it"}},
+                                               "per query against 148 SMs x 128 lanes x max SM clock; the kernel executes 162 "
+                                               "warp-instructions per (sample, 32 queries), 56 of them two-wide (FMUL2 / FFMA2), and "
+                                               "21 MUFU (16 lanes/clk/SM = 168 cycles): MUFU, issue and FMA pipe are within 20 % of "
+                                               "each other and bind it, not HBM"},
+                        "mufu": {"per_sample_query": 21, "achieved_per_s": 21.0 * Sm * Q / (mms * 1e-3),
+                                 "peak_per_s": 148 * 16 * pk["sm_max_mhz"] * 1e6,
+                                 "frac": 21.0 * Sm * Q / (mms * 1e-3) / (148 * 16 * pk["sm_max_mhz"] * 1e6)}},
            "checksum": float(mi.sum())}
     if not args.no_cpu:
         # CPU leg: the NumPy restatement of rank_pes.I_batch (pinned to golden vectors of the unmodified rank_pes.py) on the

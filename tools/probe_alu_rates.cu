@@ -23,6 +23,13 @@ __global__ void __launch_bounds__(1024) k(float* out, long long* cyc, int iters,
       if (OP == 6) { unsigned u; asm volatile("cvt.rni.u32.f32 %0, %1;" : "=r"(u) : "f"(v[j])); v[j] = __uint_as_float(u | 0x3f800000u); }
       if (OP == 7) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(v[j]));
       if (OP == 8) asm volatile("cos.approx.ftz.f32 %0, %0;" : "+f"(v[j]));
+      if (OP == 9) { unsigned u; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(v[j]), "f"(w[j].x)); v[j] = __uint_as_float((u & 0x007fffffu) | 0x3f800000u); }
+      if (OP == 10) { unsigned short h; asm volatile("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h) : "f"(v[j]), "f"(w[j].x)); v[j] = __uint_as_float(h | 0x3f800000u); }
+      if (OP == 11) { asm volatile("{.reg .b16 a, m; mov.b32 {a, m}, %1; fma.rn.f32.f16 %0, a, m, %0;}" : "+f"(v[j]) : "r"(0x3c003c00u)); }
+      if (OP == 13) { unsigned u; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(v[j]), "f"(w[j].x)); v[j] = __uint_as_float(u); }
+      if (OP == 14) { unsigned u; asm volatile("cos.approx.ftz.f32 %0, %0;" : "+f"(v[j])); asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(w[j].y), "f"(w[j].x)); w[j].x = __uint_as_float(u); }
+      if (OP == 15) { asm volatile("cos.approx.ftz.f32 %0, %0;" : "+f"(v[j])); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(w[j].x) : "f"(m2.x), "f"(a2.x)); }
+      if (OP == 12) { asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(v[j])); v[j] += 1.0f; }
     }
   }
   const long long t1 = clock64();
@@ -46,6 +53,6 @@ void run(const char* name) {
   cudaFree(out); cudaFree(cyc);
 }
 int main() {
-  run<0>("MUFU.RCP"); run<1>("MUFU.EX2"); run<7>("MUFU.LG2"); run<8>("MUFU.COS"); run<2>("FFMA"); run<3>("FFMA2"); run<4>("FMUL2"); run<5>("FADD"); run<6>("F2I");
+  run<0>("MUFU.RCP"); run<1>("MUFU.EX2"); run<7>("MUFU.LG2"); run<8>("MUFU.COS"); run<2>("FFMA"); run<3>("FFMA2"); run<4>("FMUL2"); run<5>("FADD"); run<6>("F2I"); run<9>("F2FP.F16x2"); run<10>("F2FP.E4M3x2"); run<11>("FMA.f32.f16"); run<12>("RCP+FADD"); run<13>("F2FP only"); run<14>("COS+F2FP"); run<15>("COS+FFMA");
   return 0;
 }

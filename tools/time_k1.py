@@ -37,9 +37,23 @@ for i in range(reps):
     evs[i + 1].record()
 torch.cuda.synchronize()
 ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(reps)]
+clk = ""
+try:                                                     # SM clock while the same loop keeps the GPU busy for ~0.3 s
+    import pynvml
+    pynvml.nvmlInit()
+    hnd = pynvml.nvmlDeviceGetHandleByIndex(0)
+    seen = []
+    for _ in range(6):
+        for i in range(max(1, int(50.0 / max(statistics.median(ms), 1e-3)))):
+            basis.argmax(bufs[i % n_rot])
+        seen.append(pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM))
+        torch.cuda.synchronize()
+    clk = f"  sm_mhz {statistics.median(seen)}"
+except Exception as exc:                                 # noqa: BLE001
+    clk = f"  (no clock sample: {exc})"
 Xs = bench.candidates_host(name, 0, 8192)
 F = basis.eval(torch.from_numpy(Xs).to(dev)).cpu().numpy().T.astype(np.float64)
 Fref = rff_oracle.rff_values_shared(Xs.astype(np.float64), W, b, Theta)
 err = float((np.abs(F - Fref) / np.abs(Fref).max(axis=0)).max())
 print(f"{os.environ.get('TKBO_LIB', 'libtkbo.so').split('/')[-1]:18s} {name} {form} rows={rows}: median {statistics.median(ms):.4f} ms "
-      f"min {min(ms):.4f}  max|dv|/max|f| {err:.2e}  cfg {basis.config(rows)['producer_groups']}pg", flush=True)
+      f"min {min(ms):.4f}  max|dv|/max|f| {err:.2e}  cfg {basis.config(rows)['producer_groups']}pg{clk}", flush=True)

@@ -444,7 +444,7 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
   // took ~9 instructions per feature; with 4-6 the fixed per-slab cost per warp outweighs it (c3 shard 6.8 vs 6.3 ms), so
   // the mode is off unless asked for.
   bs->coop = 0;
-  if (const char* env = getenv("TKBO_COOP")) bs->coop = (bs->npg == 2 && atoi(env) != 0) ? 1 : 0;
+  if (const char* env = getenv("TKBO_COOP")) bs->coop = ((bs->npg == 2 || bs->npg == 4) && atoi(env) != 0) ? 1 : 0;
   // The widest sample chunks (SC > 192) leave room for only 3 combined stages, and a stage is then held from its TMA issue
   // through the projection and the feature producers until its main MMAs retire (~4500 cycles for ~1000 cycles of use).
   // Split mode gives the small (W | b) tiles their own ring: the Theta stages are held for TMA latency + main MMAs only,
@@ -469,6 +469,9 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
   // large, so the combined ring is deep enough without the separate (W | b) ring.  TKBO_PAIR=0/1 overrides the default.
   bs->pair = 0;
   bs->halves = 0;
+  // sample chunks of <= 128 columns are issued whole by one main MMA warp (RffParams::nsplit)
+  bs->nsplit = bs->SC > 128 ? 1 : 0;
+  if (const char* env = getenv("TKBO_NSPLIT")) bs->nsplit = atoi(env) != 0 ? 1 : 0;
   {
     const char* env = getenv("TKBO_PAIR");
     const bool want = env != nullptr ? atoi(env) != 0 : kPairDefault;
@@ -586,7 +589,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->debug = 0;
   if (const char* env = getenv("TKBO_DEBUG")) p->debug = atoi(env);
   p->trace = h->trace; p->trace_cap = h->trace_cap;
-  p->pair = bs->pair; p->halves = bs->halves;
+  p->pair = bs->pair; p->halves = bs->halves; p->nsplit = bs->nsplit;
   *grid = fused_grid(h, bs, mt);
   return TKBO_OK;
 }
@@ -883,7 +886,7 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   p.score_fix = reinterpret_cast<unsigned long long*>(fix);
   p.debug = 0;
   p.trace = nullptr; p.trace_cap = 0;
-  p.pair = bs->pair; p.halves = bs->halves;
+  p.pair = bs->pair; p.halves = bs->halves; p.nsplit = bs->nsplit;
   const int grid = fused_grid(h, bs, mt);
   return dispatch_fused<2>(h, bs, p, grid, stream);
 }

@@ -131,6 +131,10 @@ struct RffParams {
   int pair;                  // 1: launched as clusters of two CTAs that share every tcgen05.mma (template PAIR)
   int halves;                // 1 (pairs, one accumulator buffer, SC % 64 == 0): the accumulator is retired in two column halves,
                              // so the next item's first MMAs overlap the read-out of the second half
+  int nsplit;                // single CTAs: 1 = the two main MMA warps each issue half of the sample columns (N = SC / 2) of
+                             // every slab; 0 = one warp issues N = SC.  An MMA with A in TMEM costs >= ~32 cycles
+                             // whatever its N (tools/trace_k1.py: 12 MMAs of N = 32 take ~480 cycles to issue), so
+                             // chunks of <= 128 samples must not be split: the MMA count per slab would bind
   int duel_n;                // > 0: the candidates are the ordered pairs [x_i, x_j] of duel_n base points of dimension d / 2
                              // held in X (dts.py:31-45); a tile = one i and 128 consecutive j; never materialised
   int duel_j0, duel_nj;      // this launch's shard of the second argument: j in [duel_j0, duel_j0 + duel_nj)
@@ -197,6 +201,9 @@ __device__ __forceinline__ float poly_cos(float x) {
   return fmaf(u, p, 1.f);
 }
 
+// (Tried: the residual as a truncated bf16 -- one PRMT instead of an F2FP -- multiplied against the fp16 Theta tile.  A
+// kind::f16 MMA with A = bf16 and B = fp16 is an illegal instruction on sm_100a; and F2FP does not compete with MUFU
+// anyway: tools/probe_alu_rates.cu measures COS + F2FP at the rate of COS alone.)
 // 16 projection values (fp32 bits) -> 8 packed fp16x2 hi words followed by 8 lo words: five instructions per feature
 // (FMUL.RZ + MUFU.COS, half an F2FP for hi, one FHFMA for the residual, half an F2FP for lo).  POLY: the features in
 // kPolyMask evaluate their cos on the FMA pipe instead.
@@ -321,7 +328,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&bars[kBFull + s], 1);
-      mbar_init(&bars[kBEmpty + s], PAIR ? 1 : 2);      // one commit per main MMA warp
+      mbar_init(&bars[kBEmpty + s], (PAIR || !p.nsplit) ? 1 : 2);      // one commit per issuing main MMA warp
     }
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&bars[kPFull + s], 1);
@@ -332,7 +339,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       mbar_init(&bars[kWEmpty + s], 1);      // one commit by the projection warp that used it
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&bars[kAccFull + a], PAIR ? 1 : 2);     // one commit per main MMA warp
+      mbar_init(&bars[kAccFull + a], (PAIR || !p.nsplit) ? 1 : 2);     // one commit per issuing main MMA warp
       mbar_init(&bars[kAccEmpty + a], PAIR ? 16 : 4);   // one arrival per epilogue warp (PAIR: two sets of four, both CTAs)
       mbar_init(&bars[kXaFull + a], PAIR ? 8 : 4);
     }
@@ -534,17 +541,18 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // bookkeeping phases apart instead of idling the tensor pipe together.
     // PAIR: one warp of the leader issues for both CTAs, full N = SC per instruction (each CTA's smem holds SC / 2 rows)
     const int h = warp - kMainWarp;
-    const int NH = PAIR ? SC : (SC >> 1);
+    const bool whole = PAIR || !p.nsplit;            // this warp issues all SC columns (and the other main warp none)
+    const int NH = whole ? SC : (SC >> 1);
     const uint32_t idesc = idesc_f16_f32(PAIR ? 2 * kTileM : kTileM, NH);
     const uint32_t idesc8 = idesc_e4m3_f32(PAIR ? 2 * kTileM : kTileM, NH);
     // descriptor low words advance by plain adds: (addr >> 4) never carries out of its 14-bit field
-    const uint32_t desc_lo0 = smem_desc_lo(smem0 + (PAIR ? 0 : h * NH * 128));
+    const uint32_t desc_lo0 = smem_desc_lo(smem0 + (whole ? 0 : h * NH * 128));
     const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
     const uint32_t desc_lopart = static_cast<uint32_t>(th_rows * 128) >> 4;     // Theta-lo tile follows the hi tile
     const bool hi_only = (p.debug & 1) != 0;
     const bool pairing = ring >= 5 && !(p.debug & 8);  // a pair holds two ring slots while its MMAs run
     const bool halves = PAIR && p.halves;
-    const int total_main = (PAIR && (h != 0 || !leader || halves)) ? 0 : total;
+    const int total_main = ((PAIR && (h != 0 || !leader || halves)) || (!PAIR && whole && h != 0)) ? 0 : total;
     if constexpr (PAIR) {
       if (halves && h == 0 && leader) {
         // One accumulator buffer retired in two column halves.  Per item: the half-0 MMAs of the first `lead` slabs go out
@@ -666,13 +674,13 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       if (st2 == stages) st2 = 0;
       if (slot2 == ring) { slot2 = 0; sph2 ^= 1; }
       const uint32_t bph2 = (st2 == 0) ? (bph ^ 1) : bph;
-      const bool two = pairing && (PAIR || ((it & 1) == h)) && (slab + 1 < n_slabs) &&
+      const bool two = pairing && (whole || ((it & 1) == h)) && (slab + 1 < n_slabs) &&
                        (PAIR ? mbar_test_wait_cluster(bar0 + 8 * (kAFull + slot2), sph2) : mbar_test_wait(bar0 + 8 * (kAFull + slot2), sph2)) &&
                        (!split_w || mbar_test_wait(bar0 + 8 * (kBFull + st2), bph2));
       if (h == 0) trace_event(p, kTrMmaAFull, it);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d_tmem = tmem_base + ab * SC + (PAIR ? 0 : h * NH);
+        const uint32_t d_tmem = tmem_base + ab * SC + (whole ? 0 : h * NH);
         auto issue_slab = [&](int st_, int slot_, int sl) {
           const uint32_t b_hi = desc_lo0 + st_ * desc_stage;
           const uint32_t b_lo = b_hi + desc_lopart;
@@ -740,15 +748,19 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       // four producer groups = the shapes bound by the feature map (XU pipe): part of the cos goes to the FMA pipe
       if constexpr (C8) cos_split16_c8(a, o, sk); else cos_split16<NPG == 4>(a, o, sk);
     };
-    if (NPG == 2 && p.coop) {
-      // latency form: every slab is converted by both groups, group g taking columns [32 g, 32 g + 32)
-      int slot = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < total; ++it) {
+    if ((NPG == 2 || NPG == 4) && p.coop) {
+      // latency form: every slab is converted by two groups, each taking 32 of its 64 columns.  Two groups: both work on
+      // every slab; four groups: the pair (0, 1) takes the even slab iterations, (2, 3) the odd ones -- a slab is then held
+      // by its producers for half as long, which is what the TMEM ring (six slots of 64 columns) is short of at S <= 64
+      constexpr int kStep = NPG / 2;                 // slab iterations between two slabs of this warp
+      const int first_it = (NPG == 4) ? (group >> 1) : 0;
+      int slot = first_it % ring;
+      uint32_t ph = (first_it / ring) & 1;
+      for (int it = first_it; it < total; it += kStep) {
         mbar_wait(bar0 + 8 * (kPFull + slot), ph);
         if (q == 0) trace_event(p, kTrProdPFull + 2 * group, it);
         tc_fence_after();
-        const uint32_t col = tmem_base + lane_base + ring_col0 + slot * kSlabK + group * 32;
+        const uint32_t col = tmem_base + lane_base + ring_col0 + slot * kSlabK + (group & 1) * 32;
         uint32_t r0[16], r1[16], out[16];
         tmem_ld_x16(col, r0);
         tmem_ld_x16(col + 16, r1);
@@ -762,7 +774,8 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         __syncwarp();
         if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster_relaxed(bar0_lead + 8 * (kAFull + slot)); else mbar_arrive(bar0 + 8 * (kAFull + slot)); }
         if (q == 0) trace_event(p, kTrProdArrived + 2 * group, it);
-        if (++slot == ring) { slot = 0; ph ^= 1; }
+        slot += kStep;
+        if (slot >= ring) { slot -= ring; ph ^= 1; }
       }
     } else {
     int slot = group % ring;
