@@ -594,6 +594,23 @@ def test_mpes_skewed_groups_large_batch(pbo):
     np.testing.assert_allclose(mi[sl].cpu().numpy(), ref, rtol=1e-4, atol=1e-9)
 
 
+@pytest.mark.parametrize("C,k", [(2, 1), (2, 2), (3, 1), (3, 2), (3, 3), (4, 1), (4, 2), (4, 3), (4, 4), (5, 1), (5, 2), (5, 3),
+                                 (6, 1), (6, 2)])
+def test_mpes_every_register_resident_shape_matches_oracle(pbo, C, k):
+    """Every (C, k) that has an all-orderings instantiation (k >= 2 takes the two-wide mirror-image walk, k = 1 the scalar
+    one) against the oracle port of rank_pes.I_batch on smooth samples (small MI), including a ragged last tile."""
+    rng = np.random.default_rng(100 * C + k)
+    S, Q, M = 256, 77, 7
+    basis = rng.standard_normal((Q * C + M, 4)).astype(np.float32)
+    f_all = (rng.standard_normal((S, 4)).astype(np.float32) @ basis.T * 0.6).astype(np.float32)
+    fchi_h, fstar_h = f_all[:, :Q * C].reshape(S, Q, C).copy(), f_all[:, Q * C:].copy()
+    common = pbo.acquisitions._common
+    mi = common.mpes_from_device_samples(torch.from_numpy(fchi_h).cuda(), torch.from_numpy(fstar_h).cuda(), k,
+                                         pbo._native.MPES_RANK)
+    ref = mpes_oracle.rank_mpes_from_samples(fchi_h.astype(np.float64), fstar_h.astype(np.float64), topk=k)
+    np.testing.assert_allclose(mi.cpu().numpy(), ref, rtol=1e-4, atol=1e-9)
+
+
 def test_rank_pes_log_likelihood_matches_reference_golden(pbo, golden):
     """rank_pes.get_log_likelihood / get_log_likelihood_given_order (rank_pes.py:111-177) against the (P, Q) table the
     unmodified reference functions produced."""
