@@ -964,12 +964,25 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       }
       const int j_begin = halves ? part * half_blocks + eset : eset;
       const int j_end = halves ? (part + 1) * half_blocks : SC / 32;
+      // this warp's share of the accumulator (half) is released as soon as its last block sits in registers, i.e. before
+      // that block's arithmetic (sigmoids + reductions in duel mode, the stores of store-F)
+      bool released = false;
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster_relaxed(bar0_lead + 8 * (kAccEmpty + (halves ? part : ab)));
+          else mbar_arrive(bar0 + 8 * (kAccEmpty + ab));
+        }
+        released = true;
+      };
       if (row0 < p.N && mtile < p.n_mtiles) {        // else: whole warp beyond the last candidate (warp-uniform)
 #pragma unroll 1
         for (int j = j_begin; j < j_end; j += kEpiSets) {
           uint32_t v[32];
           tmem_ld_x32(acc + j * 32, v);
           tmem_wait_ld();
+          if (j + kEpiSets >= j_end) release_acc();
           if constexpr (MODE == 0) {
             if (partial) {
 #pragma unroll
@@ -1055,12 +1068,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_cluster_relaxed(bar0_lead + 8 * (kAccEmpty + (halves ? part : ab)));
-        else mbar_arrive(bar0 + 8 * (kAccEmpty + ab));
-      }
+      if (!released) release_acc();
       }   // part
       if (warp == 0) trace_event(p, kTrEpiDone, nitem);
       if (++ab == acc_bufs) { ab = 0; aph ^= 1; }
