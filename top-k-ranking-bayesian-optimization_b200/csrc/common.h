@@ -84,6 +84,7 @@ struct tkbo_basis_s {
   int npg = 2;       // producer warp groups (2, 3 or 4)
   int pair = 0;      // 1: clusters of two CTAs share every tcgen05.mma (cta_group::2), each fetching half of the B operands
   int nsplit = 1;    // single CTAs: the two main MMA warps split the sample columns of a slab (0: one warp issues them all)
+  int lead = 0;      // halves mode: slabs issued ahead per item (0 = ring depth); TKBO_LEAD
   int halves = 0;    // 1 (pairs, one accumulator buffer): the accumulator is retired in two column halves
   int corr8 = 0;     // 1: correction terms as one e4m3 MMA (fp16 hi*hi + fp8 [hi*lo | lo*hi]); 0: three fp16 MMAs
   int smem_bytes = 0;

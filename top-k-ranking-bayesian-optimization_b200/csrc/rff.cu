@@ -469,6 +469,10 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
   // large, so the combined ring is deep enough without the separate (W | b) ring.  TKBO_PAIR=0/1 overrides the default.
   bs->pair = 0;
   bs->halves = 0;
+  // two slabs ahead measured best (c3 shard, unthrottled launches: 5.80 / 5.76 / 5.72 / 5.72 ms for 4 / 1 / 2 / 3): the slabs
+  // issued ahead pin their ring slots until their half-1 MMAs retire, and the producers need the other slots to keep going
+  bs->lead = 2;
+  if (const char* env = getenv("TKBO_LEAD")) bs->lead = std::max(0, atoi(env));
   // sample chunks of <= 128 columns are issued whole by one main MMA warp (RffParams::nsplit)
   bs->nsplit = bs->SC > 128 ? 1 : 0;
   if (const char* env = getenv("TKBO_NSPLIT")) bs->nsplit = atoi(env) != 0 ? 1 : 0;
@@ -589,7 +593,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->debug = 0;
   if (const char* env = getenv("TKBO_DEBUG")) p->debug = atoi(env);
   p->trace = h->trace; p->trace_cap = h->trace_cap;
-  p->pair = bs->pair; p->halves = bs->halves; p->nsplit = bs->nsplit;
+  p->pair = bs->pair; p->halves = bs->halves; p->nsplit = bs->nsplit; p->lead = bs->lead;
   *grid = fused_grid(h, bs, mt);
   return TKBO_OK;
 }
@@ -886,7 +890,7 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   p.score_fix = reinterpret_cast<unsigned long long*>(fix);
   p.debug = 0;
   p.trace = nullptr; p.trace_cap = 0;
-  p.pair = bs->pair; p.halves = bs->halves; p.nsplit = bs->nsplit;
+  p.pair = bs->pair; p.halves = bs->halves; p.nsplit = bs->nsplit; p.lead = bs->lead;
   const int grid = fused_grid(h, bs, mt);
   return dispatch_fused<2>(h, bs, p, grid, stream);
 }

@@ -131,6 +131,7 @@ struct RffParams {
   int pair;                  // 1: launched as clusters of two CTAs that share every tcgen05.mma (template PAIR)
   int halves;                // 1 (pairs, one accumulator buffer, SC % 64 == 0): the accumulator is retired in two column halves,
                              // so the next item's first MMAs overlap the read-out of the second half
+  int lead;                  // halves mode: slabs whose half-0 MMAs are issued ahead at the start of an item (0 = the ring depth)
   int nsplit;                // single CTAs: 1 = the two main MMA warps each issue half of the sample columns (N = SC / 2) of
                              // every slab; 0 = one warp issues N = SC.  An MMA with A in TMEM costs >= ~32 cycles
                              // whatever its N (tools/trace_k1.py: 12 MMAs of N = 32 take ~480 cycles to issue), so
@@ -586,7 +587,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         };
         int st = 0, slot = 0;
         uint32_t sph = 0, eph = 0;
-        const int lead = ring < n_slabs ? ring : n_slabs;
+        const int lead = min(min(ring, n_slabs), p.lead > 0 ? p.lead : ring);
         for (int item = 0; item < my_items; ++item) {
           // phase A: half 0 of the first `lead` slabs (their ring slots and stages stay held)
           mbar_wait_cluster(bar0 + 8 * (kAccEmpty + 0), eph ^ 1);
@@ -607,7 +608,9 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           tc_fence_after();
           // the last `tail` slabs mirror the start: all their half-0 MMAs first (half 0 is then complete and the epilogue
           // starts on it), then their half-1 MMAs, which run while half 0 is read
-          const int tail = (p.halves >= 2 && n_slabs >= 2 * lead) ? lead : 0;
+          // (it pins every ring slot once more per item, which only pays when the item is long: D = 1024, 16 slabs, loses
+          // 2.7 % with it, D = 4096 gains 1 %)
+          const int tail = (p.halves >= 2 && n_slabs >= 12 * lead) ? lead : 0;
           for (int t = 0; t < n_slabs - tail; ++t) {
             if (t >= lead) {
               mbar_wait_cluster(bar0 + 8 * (kAFull + slot), sph);
@@ -1018,10 +1021,27 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             }
           } else if constexpr (MODE == 1) {
             if (row_ok) {
+              // column c of the block -> row s0 + c of out_F: 32 lanes write 128 contiguous bytes.  Whole blocks (the usual
+              // case: S is a multiple of 32) take a branch-free path - unscale factors as float4, one pointer bumped by ldf -
+              // so that the 32 multiplies and stores pipeline; with a test per column the read-out took ~3400 cycles per
+              // block and the store-F kernel spent a third of its time waiting for the accumulator (ncu: tensor pipe 66 %)
+              const int s0 = s_base + j * 32;
+              float* dst = p.out_F + static_cast<long long>(s0) * p.ldf + row;
+              if (s0 + 32 <= p.S) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const int s = s_base + j * 32 + c;
-                if (s < p.S) p.out_F[static_cast<long long>(s) * p.ldf + row] = __uint_as_float(v[c]) * thr_s[j * 32 + c];
+                for (int c4 = 0; c4 < 8; ++c4) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(&thr_s[j * 32 + c4 * 4]);
+                  dst[0] = __uint_as_float(v[4 * c4 + 0]) * t4.x;
+                  dst[p.ldf] = __uint_as_float(v[4 * c4 + 1]) * t4.y;
+                  dst[2 * p.ldf] = __uint_as_float(v[4 * c4 + 2]) * t4.z;
+                  dst[3 * p.ldf] = __uint_as_float(v[4 * c4 + 3]) * t4.w;
+                  dst += 4 * p.ldf;
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  if (s0 + c < p.S) dst[static_cast<long long>(c) * p.ldf] = __uint_as_float(v[c]) * thr_s[j * 32 + c];
+                }
               }
             }
           } else {
