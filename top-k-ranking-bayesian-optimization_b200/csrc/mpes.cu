@@ -197,7 +197,12 @@ constexpr int kRing = 4;            // power of two
 #define TKBO_MPES_WARPS 4           // measured on B200 at c5 (skewed groups, same box): 4 warps 1.25 ms, 8 warps 1.34 ms
 #endif
 constexpr int kMpesWarps = TKBO_MPES_WARPS;
-constexpr int kMpesBlocksPerSm = 16 / kMpesWarps;     // 16 warps of 128 registers fill the register file
+// blocks per SM: 16 warps of <= 128 registers fill the register file.  Five blocks of four warps (96 registers, 32 bytes of
+// spills) measured slower at c5: 1.072 against 1.040 ms
+#ifndef TKBO_MPES_BLOCKS
+#define TKBO_MPES_BLOCKS (16 / TKBO_MPES_WARPS)
+#endif
+constexpr int kMpesBlocksPerSm = TKBO_MPES_BLOCKS;    // 16 warps of 128 registers fill the register file
 __host__ __device__ constexpr int mpes_warp_smem_bytes(int C) {
   return ((kRing * 32 * C * 4 + 127) / 128) * 128;
 }
