@@ -671,7 +671,10 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       if (split_w) mbar_wait(bar0 + 8 * (kBFull + st), bph);
       if constexpr (PAIR) mbar_wait_cluster(bar0 + 8 * (kAFull + slot), sph);
       else mbar_wait(bar0 + 8 * (kAFull + slot), sph);
-      // second slab of the burst: same item, pair alignment of this warp, operand already produced
+      // second slab of the burst: same item, pair alignment of this warp, operand already produced.  (A burst pays the
+      // warp's fixed cost per iteration once: at c2 single slabs cost 0.410 ms, bursts of two 0.367 ms.  Longer bursts were
+      // tried in round 2 - as a run-time loop and as four predicated copies - and lost 0.04-0.05 ms: this hand-written
+      // pair, whose second copy ptxas predicates and interleaves with the first, is the fastest form found.)
       int st2 = st + 1, slot2 = slot + 1;
       uint32_t sph2 = sph;
       if (st2 == stages) st2 = 0;
