@@ -611,6 +611,27 @@ def test_mpes_every_register_resident_shape_matches_oracle(pbo, C, k):
     np.testing.assert_allclose(mi.cpu().numpy(), ref, rtol=1e-4, atol=1e-9)
 
 
+@pytest.mark.parametrize("C,k", [(2, 1), (3, 2)])
+def test_mpes_short_rows_do_not_touch_their_neighbours(pbo, C, k):
+    """Rows of fewer than 32 16-byte chunks (C < 4): the staged copy must neither read past the tile's row segment nor write
+    into the next ring slot.  Everything outside the queries' own columns is NaN here, so any stray byte poisons the result;
+    the slice is compared with the same queries evaluated on their own."""
+    rng = np.random.default_rng(31 + C)
+    S, Q, M, pad = 300, 96, 9, 64
+    basis = rng.standard_normal((Q * C + M, 3)).astype(np.float32)
+    f_all = (rng.standard_normal((S, 3)).astype(np.float32) @ basis.T * 0.7).astype(np.float32)
+    fchi_h, fstar_h = f_all[:, :Q * C].reshape(S, Q, C).copy(), f_all[:, Q * C:].copy()
+    common = pbo.acquisitions._common
+    wide = torch.full((S, Q + pad, C), float("nan"), device="cuda")
+    wide[:, :Q] = torch.from_numpy(fchi_h).cuda()
+    fstar = torch.from_numpy(fstar_h).cuda()
+    ref = mpes_oracle.rank_mpes_from_samples(fchi_h.astype(np.float64), fstar_h.astype(np.float64), topk=k)
+    alone = common.mpes_from_device_samples(torch.from_numpy(fchi_h).cuda(), fstar, k, pbo._native.MPES_RANK).cpu().numpy()
+    np.testing.assert_allclose(alone, ref, rtol=1e-4, atol=1e-9)
+    padded = common.mpes_from_device_samples(wide, fstar, k, pbo._native.MPES_RANK).cpu().numpy()
+    assert np.array_equal(padded[:Q], alone)               # (the NaN queries themselves are not specified)
+
+
 def test_rank_pes_log_likelihood_matches_reference_golden(pbo, golden):
     """rank_pes.get_log_likelihood / get_log_likelihood_given_order (rank_pes.py:111-177) against the (P, Q) table the
     unmodified reference functions produced."""

@@ -192,7 +192,10 @@ struct PermWalk2 {
 // aligned / the tile is ragged (STAGED = false).
 // At every group boundary the warps add their partial sums into a block-shared accumulator and the group is folded once.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRing = 4;            // power of two
+// Rows in flight per warp (power of two).  Few choices = short rows (C = 2: 256 bytes per row and warp): with 4 rows ahead
+// 16 warps hold 16 KB in flight per SM and the pairwise shape - the reference's default - stopped at 2.3 TB/s, bound by
+// bytes in flight, not by arithmetic; ~4 KB per warp are needed.  C = 5 is bound by its arithmetic and keeps 4.
+__host__ __device__ constexpr int ring_rows(int C) { return C <= 2 ? 16 : (C <= 4 ? 8 : 4); }
 #ifndef TKBO_MPES_WARPS
 #define TKBO_MPES_WARPS 4           // measured on B200 at c5 (skewed groups, same box): 4 warps 1.25 ms, 8 warps 1.34 ms
 #endif
@@ -204,13 +207,14 @@ constexpr int kMpesWarps = TKBO_MPES_WARPS;
 #endif
 constexpr int kMpesBlocksPerSm = TKBO_MPES_BLOCKS;    // 16 warps of 128 registers fill the register file
 __host__ __device__ constexpr int mpes_warp_smem_bytes(int C) {
-  return ((kRing * 32 * C * 4 + 127) / 128) * 128;
+  return ((ring_rows(C) * 32 * C * 4 + 127) / 128) * 128;
 }
 // one row of 32 * C floats (16-byte aligned) -> shared memory, 16 bytes per lane and instruction; one commit group per row.
 // dst_lane / src_lane already point at this lane's first 16-byte chunk; a row has 8 C <= 64 chunks.
 template <int C>
 __device__ __forceinline__ void row_copy_async(uint32_t dst_lane, const float* src_lane, int lane) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane), "l"(src_lane) : "memory");
+  if (8 * C >= 32 || lane < 8 * C)                         // C < 4: a row is shorter than 32 chunks
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane), "l"(src_lane) : "memory");
   if (lane + 32 < 8 * C)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane + 512u), "l"(src_lane + 128) : "memory");
 }
@@ -288,6 +292,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
   constexpr int P = perm_count(C, K);
   constexpr int W = kMpesWarps;
   constexpr int kOwn = (P + W - 1) / W;                    // orderings folded by one warp
+  constexpr int kRing = ring_rows(C);
   constexpr bool kPacked = (K >= 2);                       // PermWalk2 (P is even then)
   constexpr float kLog2e = 1.4426950408889634f;
   // exponent offset: e_c = 2^((f_c - max) log2e + 120), so that choices up to 246 binades (170 nats) below the best one stay
@@ -355,6 +360,10 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
         cp_async_commit();
       }
     }
+    // sample index of the row the NEXT refill fetches, loaded one iteration early: the refill's address would otherwise wait
+    // for this load in every iteration (the top stall of the short-row shapes)
+    unsigned int ord_ahead = 0u;
+    if constexpr (STAGED) ord_ahead = static_cast<unsigned int>(order[min(wib + kRing * W, i1 > 0 ? i1 - 1 : 0)]);
     float fnext[C];
     if constexpr (!STAGED) {
       if (wib < i1) {
@@ -407,9 +416,9 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
           if constexpr (STAGED) {
             __syncwarp();                                  // every lane has consumed its slot values
             if (i + kRing * W < i1)
-              row_copy_async<C>(ring_dst + (n % kRing) * (32 * C * 4),
-                                tile_base + static_cast<size_t>(static_cast<unsigned int>(order[i + kRing * W])) * rs32, lane);
+              row_copy_async<C>(ring_dst + (n % kRing) * (32 * C * 4), tile_base + static_cast<size_t>(ord_ahead) * rs32, lane);
             cp_async_commit();                             // (an empty group past the end keeps the group count in step)
+            ord_ahead = static_cast<unsigned int>(order[min(i + (kRing + 1) * W, i1 - 1)]);
           }
           float rs[1 << C];
           subset_reciprocals<C, K>(e, rs);
