@@ -27,11 +27,16 @@
 //               (wstages > 0: the (W | b) tiles have their own, deeper ring and run ahead of the Theta stages)
 //   2 warps     projection MMAs, alternating slabs (1 warp when the smem ring depth is odd): they run ahead of the
 //               main MMAs as far as free TMEM ring slots and landed tiles allow
-//   2 warps     main MMAs, each owning one half of the accumulator columns (N = SC / 2 per instruction), two slabs
-//               per burst when the operands are ready, the two warps' bursts offset by one slab.
+//   2 warps     main MMAs, two slabs per burst when the operands are ready.  Sample chunks > 128 (single CTAs): each warp
+//               owns one half of the accumulator columns (N = SC / 2 per instruction), the two warps' bursts offset by
+//               one slab; chunks <= 128 and CTA pairs: one warp issues N = SC and the other idles (RffParams::nsplit).
 //   A lone warp needs ~300 cycles for the waits, commits and address arithmetic of one slab while the tensor
-//   pipe queues only ~4 instructions, so a single issuing warp starves the pipe (tools/probe_mma_chain.cu);
-//   splitting the issue work by columns keeps every accumulator column's MMAs in one program order.
+//   pipe queues only ~4 instructions (tools/probe_mma_chain.cu); splitting the issue work by columns keeps every
+//   accumulator column's MMAs in one program order, but halving N does not halve an MMA's cost, so it pays only for
+//   wide chunks.
+//
+// CTA pairs (template PAIR, clusters of two, cta_group::2 MMAs with M = 256 issued by the leader; a second set of four
+// epilogue warps; the single accumulator retired in two column halves): see the comment above the kernel.
 //
 // Around the launch: the last CTA unpacks the running keys and, for the multi-GPU merge, stores them into every rank's
 // peer-mapped buffer and releases a flag (RffParams::peer_buf); with host candidates the row-staging warps acquire a
@@ -54,9 +59,9 @@ constexpr int kNumThreadsPair(int npg) { return kNumThreadsFor(npg) + 128; }
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 12;       // smem ring (Theta + W tiles)
 constexpr int kMaxWStages = 8;     // separate (W | b) tile ring (split mode)
-constexpr int kMaxRing = 6;
+constexpr int kMaxRing = 6;          // TMEM ring (projection result -> Phi hi/lo), 64 columns per slot
 constexpr int kCopelandFixBits = 23;                     // soft-Copeland sums: sigmoid in 2^-23 fixed point
-constexpr float kCopelandFixScale = 8388608.f;           // 2^23, also the magic number that rounds s 2^23 to an integer          // TMEM ring (projection result -> Phi hi/lo), 64 columns per slot
+constexpr float kCopelandFixScale = 8388608.f;           // 2^23, also the magic number that rounds s 2^23 to an integer
 
 // Projection K extent for a template input dimension: 6 split products per dimension + 3 bias terms.
 __host__ __device__ constexpr int proj_k_used(int DT) { return ((6 * DT + 3 + 15) / 16) * 16; }     // K multiplied
