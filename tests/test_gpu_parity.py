@@ -596,11 +596,14 @@ def test_mpes_skewed_groups_large_batch(pbo):
 
 @pytest.mark.parametrize("C,k", [(2, 1), (2, 2), (3, 1), (3, 2), (3, 3), (4, 1), (4, 2), (4, 3), (4, 4), (5, 1), (5, 2), (5, 3),
                                  (6, 1), (6, 2)])
-def test_mpes_every_register_resident_shape_matches_oracle(pbo, C, k):
+@pytest.mark.parametrize("Q", [77, 84])
+def test_mpes_every_register_resident_shape_matches_oracle(pbo, C, k, Q):
     """Every (C, k) that has an all-orderings instantiation (k >= 2 takes the two-wide mirror-image walk, k = 1 the scalar
-    one) against the oracle port of rank_pes.I_batch on smooth samples (small MI), including a ragged last tile."""
+    one) against the oracle port of rank_pes.I_batch on smooth samples (small MI).  Q = 77: rows that are not multiples of
+    16 bytes for most C (direct loads); Q = 84: 16-byte rows with a ragged last tile of 20 queries (staged copies that stop
+    at the end of the row)."""
     rng = np.random.default_rng(100 * C + k)
-    S, Q, M = 256, 77, 7
+    S, M = 256, 7
     basis = rng.standard_normal((Q * C + M, 4)).astype(np.float32)
     f_all = (rng.standard_normal((S, 4)).astype(np.float32) @ basis.T * 0.6).astype(np.float32)
     fchi_h, fstar_h = f_all[:, :Q * C].reshape(S, Q, C).copy(), f_all[:, Q * C:].copy()

@@ -211,11 +211,13 @@ __host__ __device__ constexpr int mpes_warp_smem_bytes(int C) {
 }
 // one row of 32 * C floats (16-byte aligned) -> shared memory, 16 bytes per lane and instruction; one commit group per row.
 // dst_lane / src_lane already point at this lane's first 16-byte chunk; a row has 8 C <= 64 chunks.
+// `chunks` = 16-byte chunks of the row that belong to this tile: 8 C, fewer for the ragged last tile (whose missing queries
+// are never written out) and never more than the row holds, so nothing is read past the row or written past the slot.
 template <int C>
-__device__ __forceinline__ void row_copy_async(uint32_t dst_lane, const float* src_lane, int lane) {
-  if (8 * C >= 32 || lane < 8 * C)                         // C < 4: a row is shorter than 32 chunks
+__device__ __forceinline__ void row_copy_async(uint32_t dst_lane, const float* src_lane, int lane, int chunks) {
+  if (lane < chunks)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane), "l"(src_lane) : "memory");
-  if (lane + 32 < 8 * C)
+  if (lane + 32 < chunks)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane + 512u), "l"(src_lane + 128) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -341,6 +343,8 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
     const bool valid = q < Q;
     const float* base = fchi + (valid ? q : Q - 1) * C;                          // direct path
     const float* tile_base = fchi + static_cast<long long>(tile) * 32 * C + 4 * lane;   // staged path: this lane's first chunk
+    // chunks of a row segment that lie inside the row (rows are multiples of 16 bytes here): all 8 C except in a ragged last tile
+    const int chunks = static_cast<int>(min(static_cast<long long>(8 * C), (Q * C - static_cast<long long>(tile) * 32 * C) / 4));
     float acc[kPacked ? 1 : P];                            // K = 1: one accumulator per ordering
     float2 acc2[kPacked ? P / 2 : 1];                      // K >= 2: (ordering j, its mirror image = ordering j + P/2)
 #pragma unroll
@@ -356,7 +360,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
 #pragma unroll
       for (int r = 0; r < kRing; ++r) {                    // one commit group per slot, empty past the end
         if (wib + r * W < i1)
-          row_copy_async<C>(ring_dst + r * (32 * C * 4), tile_base + static_cast<size_t>(static_cast<unsigned int>(order[wib + r * W])) * rs32, lane);
+          row_copy_async<C>(ring_dst + r * (32 * C * 4), tile_base + static_cast<size_t>(static_cast<unsigned int>(order[wib + r * W])) * rs32, lane, chunks);
         cp_async_commit();
       }
     }
@@ -416,7 +420,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
           if constexpr (STAGED) {
             __syncwarp();                                  // every lane has consumed its slot values
             if (i + kRing * W < i1)
-              row_copy_async<C>(ring_dst + (n % kRing) * (32 * C * 4), tile_base + static_cast<size_t>(ord_ahead) * rs32, lane);
+              row_copy_async<C>(ring_dst + (n % kRing) * (32 * C * 4), tile_base + static_cast<size_t>(ord_ahead) * rs32, lane, chunks);
             cp_async_commit();                             // (an empty group past the end keeps the group count in step)
             ord_ahead = static_cast<unsigned int>(order[min(i + (kRing + 1) * W, i1 - 1)]);
           }
@@ -737,9 +741,10 @@ template <int C, int K>
 static void launch_all_perms(const float* fchi, const int* order, const int* gs, const double* gconst, int S, int64_t Q, int M,
                              int mode, int sm_count, unsigned int* counters, double* out, cudaStream_t stream) {
   const int64_t tiles = (Q + 31) / 32;
-  // the bulk-copy path needs 16-byte aligned rows (Q*C % 4 == 0, base aligned) and full 32-query tiles
+  // the staged path needs 16-byte aligned rows (Q*C % 4 == 0, base aligned); a ragged last tile copies only the chunks its
+  // row segment has (a separate direct-load launch for that one tile took 0.14 ms at S = 1000: one block, serial loads)
   const bool aligned = ((Q * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(fchi) & 15) == 0);
-  const int64_t staged_tiles = aligned ? Q / 32 : 0;
+  const int64_t staged_tiles = aligned ? tiles : 0;
   const int threads = 32 * kMpesWarps;
   const int smem = kMpesWarps * mpes_warp_smem_bytes(C);
   cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
