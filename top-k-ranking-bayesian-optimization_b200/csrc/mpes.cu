@@ -187,9 +187,10 @@ struct PermWalk2 {
 // positions w, w + W, w + 2W, ... of the grouped sample order, whatever group they fall in, so the split is even however
 // skewed the groups are (a maximiser that wins 70 % of the samples is the normal case late in a BO run).  Each warp streams
 // its samples' rows (32*C contiguous floats per sample) through a private shared-memory ring filled kRing rows ahead by
-// 16-byte cp.async copies (two coalesced LDGSTS per row and warp; the 1-D TMA bulk copies of round 1 cost ~40 instructions
-// of elect / mbarrier / descriptor work per row, a sixth of the loop), or by plain loads when the rows are not 16-byte
-// aligned / the tile is ragged (STAGED = false).
+// cp.async copies: 16 bytes per lane and instruction (two coalesced LDGSTS per row and warp; the 1-D TMA bulk copies of
+// round 1 cost ~40 instructions of elect / mbarrier / descriptor work per row, a sixth of the loop), or 4 bytes (C
+// instructions per row) when the rows are not multiples of 16 bytes (template CPB).  A ragged last tile copies only the
+// part of its row segment that exists.
 // At every group boundary the warps add their partial sums into a block-shared accumulator and the group is folded once.
 // ------------------------------------------------------------------------------------------------
 // Rows in flight per warp (power of two).  Few choices = short rows (C = 2: 256 bytes per row and warp): with 4 rows ahead
@@ -211,14 +212,24 @@ __host__ __device__ constexpr int mpes_warp_smem_bytes(int C) {
 }
 // one row of 32 * C floats (16-byte aligned) -> shared memory, 16 bytes per lane and instruction; one commit group per row.
 // dst_lane / src_lane already point at this lane's first 16-byte chunk; a row has 8 C <= 64 chunks.
-// `chunks` = 16-byte chunks of the row that belong to this tile: 8 C, fewer for the ragged last tile (whose missing queries
-// are never written out) and never more than the row holds, so nothing is read past the row or written past the slot.
-template <int C>
-__device__ __forceinline__ void row_copy_async(uint32_t dst_lane, const float* src_lane, int lane, int chunks) {
-  if (lane < chunks)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane), "l"(src_lane) : "memory");
-  if (lane + 32 < chunks)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane + 512u), "l"(src_lane + 128) : "memory");
+// One row segment of a tile (32 C floats, fewer in a ragged last tile) -> shared memory; one commit group per row.
+// CPB = 16: rows that are multiples of 16 bytes from a 16-byte aligned base, one or two coalesced 16-byte copies per lane;
+// CPB = 4: any other row length, C coalesced 4-byte copies per lane.  `units` = CPB-sized pieces of the segment that lie
+// inside the row, so nothing is read past the row or written past the ring slot; dst_lane / src_lane point at this lane's
+// first piece.
+template <int C, int CPB>
+__device__ __forceinline__ void row_copy_async(uint32_t dst_lane, const float* src_lane, int lane, int units) {
+  if constexpr (CPB == 16) {
+    if (lane < units)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane), "l"(src_lane) : "memory");
+    if (lane + 32 < units)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_lane + 512u), "l"(src_lane + 128) : "memory");
+  } else {
+#pragma unroll
+    for (int t = 0; t < C; ++t)
+      if (lane + 32 * t < units)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_lane + 128u * t), "l"(src_lane + 32 * t) : "memory");
+  }
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -286,7 +297,7 @@ __device__ __forceinline__ double table_log(const LogTable& tab, float a) {
 // only if p_z is EXACTLY sum_m J_zm; a float32 running sum of the group values breaks that at the 1e-7 level, which is
 // 1e-4 of a typical MI.  The grid value is what the fold uses AND what is summed into tot_z.
 // At the end of the tile  MI = sum_w A_w  with  A_w = sum_m (fold terms of w's orderings) - sum_{z of w} p_z log p_z.
-template <int C, int K, bool STAGED>
+template <int C, int K, int CPB /* bytes per staged copy: 16 or 4 */>
 __global__ void __launch_bounds__(32 * kMpesWarps, kMpesBlocksPerSm)
 mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ order, const int* __restrict__ group_start,
                       const double* __restrict__ group_const, int S, long long Q, int M, int mode, int tile_begin,
@@ -316,7 +327,7 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
   unsigned char* slice = mpes_smem + static_cast<size_t>(wib) * mpes_warp_smem_bytes(C);
   float (*ring)[32 * C] = reinterpret_cast<float (*)[32 * C]>(slice);
   const float* ring_lane = &ring[0][lane * C];             // this lane's C values of slot 0; slot s is 32 C floats further
-  const uint32_t ring_dst = smem_u32(&ring[0][4 * lane]);  // this lane's first 16-byte chunk of slot 0
+  const uint32_t ring_dst = smem_u32(&ring[0][(CPB / 4) * lane]);  // this lane's first piece of slot 0
   const unsigned int rs32 = static_cast<unsigned int>(Q * C);          // floats per sample row (host checks Q C < 2^31)
   const double invS = 1.0 / static_cast<double>(S);
   const double eps = (mode == TKBO_MPES_PES) ? kPesEps : 0.0;
@@ -325,7 +336,6 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
   while (fix_bits > 0 && (static_cast<long long>(S) << fix_bits) > (1ll << 31)) --fix_bits;   // S 2^F <= 2^31
   const float fix_scale = __int_as_float((127 + fix_bits) << 23);                              // 2^F
   const double fix_unit = 1.0 / static_cast<double>(1ll << fix_bits);                          // 2^-F
-  const long long rowstride = Q * C;
   const int i1 = group_start[M];                           // samples with a valid winner
   if (threadIdx.x == 0) {
     mbar_init(&gbar[0], W);
@@ -341,10 +351,10 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
     if (tile >= tile_end) break;
     const long long q = static_cast<long long>(tile) * 32 + lane;
     const bool valid = q < Q;
-    const float* base = fchi + (valid ? q : Q - 1) * C;                          // direct path
-    const float* tile_base = fchi + static_cast<long long>(tile) * 32 * C + 4 * lane;   // staged path: this lane's first chunk
-    // chunks of a row segment that lie inside the row (rows are multiples of 16 bytes here): all 8 C except in a ragged last tile
-    const int chunks = static_cast<int>(min(static_cast<long long>(8 * C), (Q * C - static_cast<long long>(tile) * 32 * C) / 4));
+    const float* tile_base = fchi + static_cast<long long>(tile) * 32 * C + (CPB / 4) * lane;   // this lane's first piece
+    // pieces of a row segment that lie inside the row: all of them except in a ragged last tile
+    const int chunks = static_cast<int>(min(static_cast<long long>(32 * C * 4 / CPB),
+                                            (Q * C - static_cast<long long>(tile) * 32 * C) / (CPB / 4)));
     float acc[kPacked ? 1 : P];                            // K = 1: one accumulator per ordering
     float2 acc2[kPacked ? P / 2 : 1];                      // K >= 2: (ordering j, its mirror image = ordering j + P/2)
 #pragma unroll
@@ -355,27 +365,18 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
     for (int t = 0; t < kOwn; ++t) tot_sh[t][wib][lane] = 0u;          // (private to this thread: no synchronisation needed)
     double A = 0.0;
 
-    if constexpr (STAGED) {                                // prime the ring with this warp's first kRing rows
+    {                                                      // prime the ring with this warp's first kRing rows
       __syncwarp();                                        // (the previous tile's last rows have been consumed by every lane)
 #pragma unroll
       for (int r = 0; r < kRing; ++r) {                    // one commit group per slot, empty past the end
         if (wib + r * W < i1)
-          row_copy_async<C>(ring_dst + r * (32 * C * 4), tile_base + static_cast<size_t>(static_cast<unsigned int>(order[wib + r * W])) * rs32, lane, chunks);
+          row_copy_async<C, CPB>(ring_dst + r * (32 * C * 4), tile_base + static_cast<size_t>(static_cast<unsigned int>(order[wib + r * W])) * rs32, lane, chunks);
         cp_async_commit();
       }
     }
     // sample index of the row the NEXT refill fetches, loaded one iteration early: the refill's address would otherwise wait
     // for this load in every iteration (the top stall of the short-row shapes)
-    unsigned int ord_ahead = 0u;
-    if constexpr (STAGED) ord_ahead = static_cast<unsigned int>(order[min(wib + kRing * W, i1 > 0 ? i1 - 1 : 0)]);
-    float fnext[C];
-    if constexpr (!STAGED) {
-      if (wib < i1) {
-        const float* r = base + static_cast<long long>(order[wib]) * rowstride;
-#pragma unroll
-        for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
-      }
-    }
+    unsigned int ord_ahead = static_cast<unsigned int>(order[min(wib + kRing * W, i1 > 0 ? i1 - 1 : 0)]);
 
     int i = wib;                                           // position in the grouped sample order
     unsigned int n = 0;                                    // samples this warp has consumed (ring slot = n % kRing)
@@ -393,20 +394,12 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
         if (hi == group_start[m] && mode == TKBO_MPES_RANK) continue;   // rank_pes.py:86-93 drops empty groups (block-uniform)
         for (; i < hi; i += W, ++n) {
           float f[C];
-          if constexpr (STAGED) {
+          {
             const int slot = n % kRing;
             cp_async_wait<kRing - 1>();                    // this lane's copies of row n have landed ...
             __syncwarp();                                  // ... and so have the other lanes'
 #pragma unroll
             for (int c = 0; c < C; ++c) f[c] = ring_lane[slot * (32 * C) + c];
-          } else {
-#pragma unroll
-            for (int c = 0; c < C; ++c) f[c] = fnext[c];
-            if (i + W < i1) {
-              const float* r = base + static_cast<long long>(order[i + W]) * rowstride;
-#pragma unroll
-              for (int c = 0; c < C; ++c) fnext[c] = __ldg(r + c);
-            }
           }
           float mx = f[0];
 #pragma unroll
@@ -417,10 +410,10 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
           // floor at the smallest normal: a set of remaining choices that has underflowed entirely (> 170 nats below the
           // best) then shares its (negligible) mass evenly instead of producing 0 * inf
           for (int c = 0; c < C; ++c) e[c] = fmaxf(fast_ex2(fmaf(f[c], kLog2e, -mxs)), 1.17549435e-38f);
-          if constexpr (STAGED) {
+          {
             __syncwarp();                                  // every lane has consumed its slot values
             if (i + kRing * W < i1)
-              row_copy_async<C>(ring_dst + (n % kRing) * (32 * C * 4), tile_base + static_cast<size_t>(ord_ahead) * rs32, lane, chunks);
+              row_copy_async<C, CPB>(ring_dst + (n % kRing) * (32 * C * 4), tile_base + static_cast<size_t>(ord_ahead) * rs32, lane, chunks);
             cp_async_commit();                             // (an empty group past the end keeps the group count in step)
             ord_ahead = static_cast<unsigned int>(order[min(i + (kRing + 1) * W, i1 - 1)]);
           }
@@ -741,24 +734,20 @@ template <int C, int K>
 static void launch_all_perms(const float* fchi, const int* order, const int* gs, const double* gconst, int S, int64_t Q, int M,
                              int mode, int sm_count, unsigned int* counters, double* out, cudaStream_t stream) {
   const int64_t tiles = (Q + 31) / 32;
-  // the staged path needs 16-byte aligned rows (Q*C % 4 == 0, base aligned); a ragged last tile copies only the chunks its
-  // row segment has (a separate direct-load launch for that one tile took 0.14 ms at S = 1000: one block, serial loads)
+  // 16-byte copies need rows that are multiples of 16 bytes from an aligned base; anything else takes 4-byte copies (same
+  // kernel otherwise: at c5, Q = 100001 instead of 100000, the former direct-load path took 1.36 ms against 1.04)
   const bool aligned = ((Q * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(fchi) & 15) == 0);
-  const int64_t staged_tiles = aligned ? tiles : 0;
   const int threads = 32 * kMpesWarps;
   const int smem = kMpesWarps * mpes_warp_smem_bytes(C);
-  cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (staged_tiles > 0) {
-    const int grid = static_cast<int>(std::min<int64_t>(kMpesBlocksPerSm * sm_count, staged_tiles));
-    mpes_all_perms_kernel<C, K, true><<<grid, threads, smem, stream>>>(fchi, order, gs, gconst, S, Q, M, mode, 0,
-                                                                   static_cast<int>(staged_tiles), counters, out);
-  }
-  if (staged_tiles < tiles) {
-    const int grid = static_cast<int>(std::min<int64_t>(kMpesBlocksPerSm * sm_count, tiles - staged_tiles));
-    mpes_all_perms_kernel<C, K, false><<<grid, threads, smem, stream>>>(fchi, order, gs, gconst, S, Q, M, mode,
-                                                                    static_cast<int>(staged_tiles), static_cast<int>(tiles),
-                                                                    counters + 1, out);
+  const int grid = static_cast<int>(std::min<int64_t>(kMpesBlocksPerSm * sm_count, tiles));
+  if (aligned) {
+    cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    mpes_all_perms_kernel<C, K, 16><<<grid, threads, smem, stream>>>(fchi, order, gs, gconst, S, Q, M, mode, 0,
+                                                                 static_cast<int>(tiles), counters, out);
+  } else {
+    cudaFuncSetAttribute(mpes_all_perms_kernel<C, K, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    mpes_all_perms_kernel<C, K, 4><<<grid, threads, smem, stream>>>(fchi, order, gs, gconst, S, Q, M, mode, 0,
+                                                                static_cast<int>(tiles), counters, out);
   }
 }
 
