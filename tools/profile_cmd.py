@@ -3,7 +3,7 @@ inputs resident on the device (no host path: ncu serialises kernels against copi
     python tools/profile_cmd.py                      (plain run; prints CUDA-event times)
     ncu --set full ... -k regex:'rff_fused_kernel|mpes_all_perms' python tools/profile_cmd.py
 Kernel instances: rff_fused_kernel<6,0,2,false> = c3 shard (2^21 of the 2^24 candidates) fp32 form, <6,0,2,true> = fast form,
-<2,0,4,false> = c2, <4,2,2,*> = c4 duel shard; mpes_all_perms_kernel<5,3,true> = c5."""
+<2,0,4,false> = c2, <4,2,2,*> = c4 duel shard; mpes_all_perms_kernel<5,3,16> = c5 (16-byte staged copies)."""
 import importlib
 import os
 import sys
