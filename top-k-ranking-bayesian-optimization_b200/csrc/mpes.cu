@@ -411,6 +411,9 @@ mpes_all_perms_kernel(const float* __restrict__ fchi, const int* __restrict__ or
       if (!tail) {
         const int hi = group_start[m + 1];
         if (hi == group_start[m] && mode == TKBO_MPES_RANK) continue;   // rank_pes.py:86-93 drops empty groups (block-uniform)
+        // (Tried in round 2: the loads / max / exponentials of sample n + 1 issued inside the iteration of sample n - a
+        // software pipeline by hand.  128 registers with spills, 1.112 against 1.034 ms at c5: the four warps of a
+        // sub-partition already interleave these phases.)
         for (; i < hi; i += W, ++n) {
           float f[C];
           {
