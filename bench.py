@@ -301,15 +301,20 @@ def tensor_equivalents(cfg):
     return (2 if cfg.get("e4m3_corrections") else 3), proj_k
 
 
-def k1_roofline(cfg, n_rows, D, S, ms, pk, form, facts_key, long_run):
+def k1_roofline(cfg, n_rows, D, S, ms, pk, form, facts_key, long_run, two_pass=None):
     mma_eq, proj_k = tensor_equivalents(cfg)
     Dpad = cfg["n_slabs"] * 64
     alg = 2.0 * n_rows * D * S / (ms * 1e-3) / 1e12
-    exe = (mma_eq * 2.0 * n_rows * Dpad * cfg["S_chunk"] * cfg["n_chunks"] + 2.0 * n_rows * Dpad * proj_k * cfg["n_chunks"]) \
-        / (ms * 1e-3) / 1e12
+    one_pass = 2.0 * n_rows * Dpad * cfg["S_chunk"] * cfg["n_chunks"]            # flops of one MMA equivalent over everything
+    proj = 2.0 * n_rows * Dpad * proj_k * cfg["n_chunks"]
+    if two_pass:       # pass 1: hi*hi only (1 equivalent) + projection over everything; pass 2: the full form over the listed share
+        share = two_pass[0] / max(two_pass[1], 1)
+        exe = ((1.0 + share * mma_eq) * one_pass + (1.0 + share) * proj) / (ms * 1e-3) / 1e12
+    else:
+        exe = (mma_eq * one_pass + proj) / (ms * 1e-3) / 1e12
     cos_rate = float(n_rows) * Dpad * cfg["n_chunks"] / (ms * 1e-3)
     cos_peak = 16.0 * 148 * pk["sm_max_mhz"] * 1e6
-    facts = ncu_facts().get(facts_key, {})
+    facts = ncu_facts().get(facts_key + ("_pass1" if two_pass else ""), {}) or ncu_facts().get(facts_key, {})
     # per-launch DRAM traffic from the committed ncu capture of the same kernel instance; the capture's launch may cover a
     # different number of candidates (traffic is linear in N: every candidate row is read once), so it is scaled and both
     # figures are given
@@ -326,6 +331,10 @@ def k1_roofline(cfg, n_rows, D, S, ms, pk, form, facts_key, long_run):
             "peak_kind": ("sustained" if long_run else "burst") + " bf16 cuBLAS, " + pk["source"],
             "frac_of_burst_peak": alg / pk["bf16_tflops"], "executed": exe, "executed_frac": exe / peak,
             "executed_frac_of_burst_peak": exe / pk["bf16_tflops"],
+            "two_pass": ({"items_in_full_precision_pass": two_pass[0], "items": two_pass[1],
+                          "what": "pass 1 = hi*hi MMAs only over every item (1 MMA equivalent per product), pass 2 = the full "
+                                  "contraction over the items that can hold a maximum; same result bits as a single pass"}
+                         if two_pass else None),
             "tensor_pipe_active_pct_ncu": facts.get("tensor_pipe_active_pct"), "ncu_source": facts.get("source"),
             "algorithmic_bytes_per_launch": 4.0 * n_rows * cfg["d_template"],
             "mufu": {"cos_per_s": cos_rate, "peak_cos_per_s": cos_peak, "frac": cos_rate / cos_peak},
@@ -447,6 +456,7 @@ def k1_block(ctx, name, args, precision, steps, warmup, with_e2e, long_run, pari
     clocks = ctx.sampler.window(t0, t1) if ctx.sampler else None
     if peer is not None:
         peer.check()
+    two_pass = basis.two_pass_items()                  # of the last timed step on this rank (None: single pass)
     blk = None
     if ctx.rank == 0:
         pk = peaks()
@@ -455,7 +465,7 @@ def k1_block(ctx, name, args, precision, steps, warmup, with_e2e, long_run, pari
         blk = {"metric": METRIC, "value": N * S / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_step_median": ms_med,
                "steps": steps, "warmup": warmup, "config": config_of(name), "form": form, "gpu_launches": launches,
                "clocks": clocks,
-               "roofline": k1_roofline(cfg, n_rows0, D, S, ms_med, pk, form, f"k1_{name}_{form}", long_run),
+               "roofline": k1_roofline(cfg, n_rows0, D, S, ms_med, pk, form, f"k1_{name}_{form}", long_run, two_pass),
                "run": {"tiling": cfg, "candidates_per_rank": n_rows0,
                        "l2": f"{n_rot} rotating candidate buffers per rank ({n_rot * shard_bytes >> 20} MiB > 2 x 126 MiB L2)",
                        "parallelism": f"candidate shards x{ctx.world} (strong scaling), merge: {merge}",

@@ -122,6 +122,10 @@ int tkbo_rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t basis, const float* X, in
 /* 0, or the epoch of a merge on this handle that gave up waiting for a peer (index -2 in its outputs); reading clears it.
  * The word lives in host-mapped memory, so it is meaningful once the stream that ran the merge has been synchronised. */
 int64_t tkbo_peer_status(tkbo_handle_t h);
+/* Diagnostics of the two-pass argmax (every tkbo_rff_argmax* entry point, large problems): after the stream of the last call
+ * has been synchronised, *listed = work items the full-precision pass covered, *total = work items in all; both -1 if that
+ * call ran as a single pass.  The results do not depend on the pass structure. */
+int tkbo_two_pass_items(tkbo_handle_t h, int* listed, int* total);
 /* Delivers ready-made keys [S] for this epoch instead of running the fused kernel; keys == NULL delivers "no candidate"
  * (INT64_MIN) -- what a rank whose shard is empty calls so that its peers' merges do not wait for it. */
 int tkbo_peer_push_keys(tkbo_handle_t h, const int64_t* keys, int S, void* const* peer_bufs, int world, int rank,

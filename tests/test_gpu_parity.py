@@ -542,6 +542,37 @@ def test_singular_regression_retries_then_fails(pbo):
     assert out.getvalue().count("Resampling phi, W, b, theta") == 100 and "Retry limit exceeded" in out.getvalue()
 
 
+@pytest.mark.parametrize("N,d,D,S,form", [(40000, 3, 192, 256, "fp32"), (40000, 3, 192, 256, "fast"), (30001, 6, 320, 300, "fast"),
+                                          (9000, 4, 128, 64, "fp32")])
+def test_two_pass_argmax_equals_single_pass(pbo, monkeypatch, N, d, D, S, form):
+    """Large argmax calls run a hi*hi-only pass over everything and the full contraction only over the items that can hold a
+    maximum (csrc/rff.cu: launch_argmax).  Forced on here (TKBO_PRUNE=2) against the single pass (TKBO_PRUNE=0): the same
+    bits, with exact ties across tiles (lowest index wins), a NaN row and a ragged last tile in the input."""
+    rng = np.random.default_rng(N + D + S)
+    W = rng.standard_normal((D, d)) / 0.3
+    b = rng.uniform(0, 2 * np.pi, D)
+    Theta = rng.standard_normal((D, S)) * rng.uniform(0.5, 2.0, size=(1, S))
+    X = rng.uniform(0.0, 1.0, size=(N, d)).astype(np.float32)
+    ref = rff_oracle.rff_values_shared(X.astype(np.float64), W, b, Theta)          # (N, S)
+    top = int(np.argmax(ref[:, 0]))
+    X[N - 7] = X[top]                                   # an exact tie in another tile: the lower index has to win
+    X[min(top + 1, N - 8)] = X[top] if top + 1 < N - 8 else X[min(top + 1, N - 8)]
+    X[123] = np.nan
+    Xd = torch.from_numpy(X).cuda()
+    out = {}
+    for prune in ("0", "2"):
+        monkeypatch.setenv("TKBO_PRUNE", prune)
+        basis = pbo.fourier_features.SharedBasis(W, b, Theta, device="cuda:0", precision=form)
+        val, idx = basis.argmax(Xd)
+        tp = basis.two_pass_items()
+        assert (tp is None) == (prune == "0")
+        if tp is not None:
+            assert 1 <= tp[0] <= tp[1]
+        out[prune] = (val.clone(), idx.clone())
+    assert torch.equal(out["0"][0], out["2"][0]) and torch.equal(out["0"][1], out["2"][1])
+    assert int(out["2"][1][0]) == min(top, N - 7)
+
+
 # ------------------------------------------------------------------------------------------- MPES / PES / DTS
 @pytest.mark.parametrize("tag", ["c5k3", "c4k4", "c3k1", "c5k2_sparse", "gp_small", "gp_tiny", "gp_c4k2", "spread"])
 def test_rank_pes_matches_reference_golden(pbo, golden, tag, capsys):
@@ -1022,7 +1053,7 @@ def test_bench_gpu_arm_contract():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert key in j, key
-    assert j["n_gpus"] == 1 and j["steps"] == 5 and j["gpu_launches"] == 5 and j["value"] > 1e10
+    assert j["n_gpus"] == 1 and j["steps"] == 5 and j["gpu_launches"] in (5, 15) and j["value"] > 1e10
     assert j["config"] == {"workload": j["config"]["workload"], "N_total": 1 << 20, "d": 2, "D": 1024, "S": 64}
     assert j["e2e"]["equals_device_resident_result"] is True and j["e2e"]["h2d_bytes_per_step"] > 8e6
     rf = j["roofline"]

@@ -45,6 +45,8 @@ def classify(name):
 # what one captured launch of tools/profile_cmd.py processes (bench.py scales the measured DRAM bytes by its own units / these)
 UNITS = {"k1_c3_fp32": {"units_per_launch": 1 << 21, "unit": "candidates"},
          "k1_c3_fast": {"units_per_launch": 1 << 21, "unit": "candidates"},
+         "k1_c3_fp32_pass1": {"units_per_launch": 1 << 21, "unit": "candidates"},
+         "k1_c3_fast_pass1": {"units_per_launch": 1 << 21, "unit": "candidates"},
          "k1_c2_fp32": {"units_per_launch": 1 << 20, "unit": "candidates"},
          "k1_c4d_fast": {"units_per_launch": 2048 * 256, "unit": "candidates"},
          "k2_c5": {"units_per_launch": 100000, "unit": "query sets"}}
@@ -64,6 +66,8 @@ for rep, rows in rows_all:
     key, pair = classify(name)
     if key is None:
         continue
+    if "pass1" in rep:                 # the hi*hi-only pass of the two-pass argmax: same kernel instance, other facts
+        key += "_pass1"
     rd, wr = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum")
     facts[key] = {
         "kernel": name, "cta_pairs": bool(pair) if key.startswith("k1") else None,

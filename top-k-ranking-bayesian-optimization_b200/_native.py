@@ -44,6 +44,7 @@ _SIGNATURES = {
     "tkbo_peer_buffer_bytes": (c_i64, [c_i, c_i]),
     "tkbo_rff_argmax_peer": (c_i, [c_p, c_p, c_p, c_i64, c_i64, ctypes.POINTER(c_p), c_i, c_i, ctypes.c_uint64, c_p, c_p, c_p]),
     "tkbo_peer_status": (c_i64, [c_p]),
+    "tkbo_two_pass_items": (c_i, [c_p, c_p, c_p]),
     "tkbo_rff_argmax_host_peer": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i64, c_i, c_i64, ctypes.POINTER(c_p), c_i, c_i,
                                         ctypes.c_uint64, c_p, c_p]),
     "tkbo_merge_peer_keys": (c_i, [c_p, c_p, c_i, c_i, ctypes.c_uint64, c_p, c_p, c_p]),

@@ -153,6 +153,11 @@ int tkbo_create(tkbo_handle_t* out, int device) {
     set_error(std::string("cudaMalloc (handle): ") + cudaGetErrorString(e));
     return TKBO_ERR_NOMEM;
   }
+  if (cudaHostAlloc(&h->two_pass_host, 2 * sizeof(int), cudaHostAllocDefault) == cudaSuccess) {
+    h->two_pass_host[0] = -1; h->two_pass_host[1] = -1;
+  } else {
+    h->two_pass_host = nullptr;
+  }
   if (cudaHostAlloc(&h->peer_status_host, sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
     *h->peer_status_host = 0u;
     if (cudaHostGetDevicePointer(&h->peer_status_dev, h->peer_status_host, 0) != cudaSuccess) h->peer_status_dev = nullptr;
@@ -175,6 +180,7 @@ int tkbo_destroy(tkbo_handle_t h) {
     host_path_release(h);
     cudaFree(h->done_counter);
     if (h->peer_status_host) cudaFreeHost(h->peer_status_host);
+    if (h->two_pass_host) cudaFreeHost(h->two_pass_host);
   }
   delete h;
   return TKBO_OK;
@@ -260,6 +266,13 @@ int tkbo_rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t basis, const float* X, in
   TKBO_ENTER(h);
   return rff_argmax_peer(h, basis, X, N, idx_offset, peer_bufs, world, rank, epoch, out_val, out_idx, as_stream(stream));
 }
+int tkbo_two_pass_items(tkbo_handle_t h, int* listed, int* total) {
+  TKBO_REQUIRE(h && listed && total, "null pointer");
+  *listed = h->two_pass_host ? h->two_pass_host[0] : -1;
+  *total = h->two_pass_host ? h->two_pass_host[1] : -1;
+  return TKBO_OK;
+}
+
 int64_t tkbo_peer_status(tkbo_handle_t h) {
   if (!h) return TKBO_ERR_INVALID;
   if (!h->peer_status_host) return 0;

@@ -44,6 +44,7 @@ struct tkbo_handle_s {
   // merge over peer memory: one host-mapped word that a merge (kernel tail or tkbo_merge_peer_keys) sets to the epoch it
   // gave up on; tkbo_peer_status() reads and clears it
   unsigned int* peer_status_host = nullptr;
+  int* two_pass_host = nullptr;              // pinned [2]: items listed for pass 2 of the last two-pass argmax, items in all (-1: single pass)
   unsigned int* peer_status_dev = nullptr;
   // persistent state of the host-buffer entry point (tkbo_rff_argmax_host): basis + device staging, reused across calls
   struct HostPath {
@@ -84,6 +85,7 @@ struct tkbo_basis_s {
   int npg = 2;       // producer warp groups (2, 3 or 4)
   int pair = 0;      // 1: clusters of two CTAs share every tcgen05.mma (cta_group::2), each fetching half of the B operands
   int nsplit = 1;    // single CTAs: the two main MMA warps split the sample columns of a slab (0: one warp issues them all)
+  int prune = 0;     // 1: MODE 0 launches run in two passes (RffParams::approx); TKBO_PRUNE
   int lead = 0;      // halves mode: slabs issued ahead per item (0 = ring depth); TKBO_LEAD
   int halves = 0;    // 1 (pairs, one accumulator buffer): the accumulator is retired in two column halves
   int corr8 = 0;     // 1: correction terms as one e4m3 MMA (fp16 hi*hi + fp8 [hi*lo | lo*hi]); 0: three fp16 MMAs

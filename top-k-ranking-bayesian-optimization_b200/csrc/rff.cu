@@ -105,10 +105,12 @@ prep_basis_kernel(const double* __restrict__ Theta, int transposed, const double
   }
   __syncthreads();
   const double sc = scale_sh;
+  double l1 = 0.0;                                         // sum_j |hi operand| of this sample (two-pass argmax bound)
   for (int j = threadIdx.x; j < Dpad; j += blockDim.x) {
     double v = 0.0;
     if (s < S && j < D) v = theta_at(Theta, transposed, D, S, j, s) * root * sc;
     const __half h = __double2half(v);
+    l1 += fabs(static_cast<double>(__half2float(h)));
     const size_t i = static_cast<size_t>(s) * Dpad + j;
     hi[i] = h;
     if (corr8) {
@@ -119,6 +121,23 @@ prep_basis_kernel(const double* __restrict__ Theta, int transposed, const double
     } else {
       lo[i] = __double2half(v - static_cast<double>(__half2float(h)));
     }
+  }
+  // eps2[s] (stored behind the Salloc unscale factors) = 2 eps_s in accumulator units, eps_s >= |full - hi*hi-only value|:
+  // the two correction terms are at most (2^-11 + 2^-12) amp sum|v| (fp16 half-ulps of both operands, |Phi operand| <= amp
+  // = 4096 in the fast form, 1 otherwise; the e4m3 corrections of the fast form approximate the same two terms), rounded
+  // up to 1.25 x 2^-10 (the fast form's e4m3-rounded corrections reach 2^-10.3); every accumulator update truncates by < 2^-23 of a partial sum that is <= amp sum|v|, and the two passes
+  // make Dpad / 16 and at most 3 Dpad / 16 updates.
+  __syncthreads();
+  red[threadIdx.x] = l1;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double amp = corr8 ? 4096.0 : 1.0;
+    const double eps = amp * red[0] * (1.25 * ldexp(1.0, -10) + (Dpad / 4.0) * ldexp(1.0, -23));
+    unscale[Salloc + s] = static_cast<float>(2.02 * eps);
   }
 }
 
@@ -469,6 +488,8 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
   // large, so the combined ring is deep enough without the separate (W | b) ring.  TKBO_PAIR=0/1 overrides the default.
   bs->pair = 0;
   bs->halves = 0;
+  bs->prune = 1;                         // 0: single pass, 1: two passes when there are >= 8 items per CTA, 2: always
+  if (const char* env = getenv("TKBO_PRUNE")) bs->prune = std::max(0, std::min(2, atoi(env)));
   // two slabs ahead measured best (c3 shard, unthrottled launches: 5.80 / 5.76 / 5.72 / 5.72 ms for 4 / 1 / 2 / 3): the slabs
   // issued ahead pin their ring slots until their half-1 MMAs retire, and the producers need the other slots to keep going
   bs->lead = 2;
@@ -509,7 +530,7 @@ int basis_create(tkbo_handle_t h, tkbo_basis_t* out, int D, int d, int S, int pr
   e = e ? e : cudaMalloc(&bs->Wproj, static_cast<size_t>(bs->Dpad) * proj_k_alloc(DT) * sizeof(uint16_t));
   e = e ? e : cudaMalloc(&bs->theta_hi, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
   e = e ? e : cudaMalloc(&bs->theta_lo, static_cast<size_t>(bs->Salloc) * bs->Dpad * sizeof(__half));
-  e = e ? e : cudaMalloc(&bs->unscale, static_cast<size_t>(bs->Salloc) * sizeof(float));
+  e = e ? e : cudaMalloc(&bs->unscale, static_cast<size_t>(2 * bs->Salloc) * sizeof(float));   // + eps2 (two-pass argmax)
   // + one word behind the keys: the last-CTA counter of this basis' launches (launches on different bases may
   // overlap on different streams; launches on the same basis must be stream-ordered)
   e = e ? e : cudaMalloc(&bs->packed, static_cast<size_t>(bs->Salloc + 1) * sizeof(unsigned long long));
@@ -582,6 +603,7 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   p->duel_n = 0; p->duel_j0 = 0; p->duel_nj = 0; p->score_fix = nullptr;
   p->peer_world = 0; p->peer_rank = 0; p->peer_epoch = 0; p->ready_flag = nullptr; p->rows_per_chunk = 0;
   p->peer_merge = 0; p->peer_status = nullptr;
+  p->approx = 0; p->eps2 = bs->unscale + bs->Salloc; p->rg_max = nullptr; p->lb_out = nullptr; p->item_list = nullptr; p->list_count = nullptr;
   for (int r = 0; r < 8; ++r) p->peer_buf[r] = nullptr;
   p->N = N; p->d = bs->d; p->S = bs->S; p->SC = bs->SC; p->n_chunks = bs->n_chunks;
   p->n_slabs = bs->Dpad / kSlabK;
@@ -598,9 +620,85 @@ static int fill_params(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t
   return TKBO_OK;
 }
 
+// MODE 0 launch, in two passes when the problem is large enough to pay for a second launch (RffParams::approx): pass 1 over
+// every item with the hi*hi MMAs only, pass 2 in full precision over the items pass 1 could not exclude.  Results are the
+// same bits as the single pass (every recorded key comes from the full-precision pass; excluded items are provably below
+// the maximum).  TKBO_PRUNE=0 switches it off.
+// Item list of pass 2 of the two-pass argmax (RffParams::approx): item (tile or tile pair, sample chunk) is kept if one of
+// its row groups has an approximate maximum that reaches the sample's final lower bound.  One block per item, thread = column.
+__global__ void __launch_bounds__(256)
+mark_items_kernel(const float* __restrict__ rg_max, const float* __restrict__ lb, long long N, int S, int SC, int n_chunks,
+                  int pair, int n_items, int* __restrict__ item_list, int* __restrict__ list_count) {
+  const int item = blockIdx.x;
+  if (item >= n_items) return;
+  const int chunk = item % n_chunks;
+  const long long first_tile = static_cast<long long>(item / n_chunks) * (pair ? 2 : 1);
+  const long long n_groups = (N + 31) / 32;
+  const long long ld = static_cast<long long>(SC) * n_chunks;
+  bool keep = false;
+  for (int c = threadIdx.x; c < SC && chunk * SC + c < S; c += blockDim.x) {       // (padded samples have no bound)
+    const float bound = lb[chunk * SC + c];
+    for (int g = 0; g < (pair ? 8 : 4); ++g) {
+      const long long grp = first_tile * 4 + g;
+      if (grp >= n_groups) break;
+      keep |= !(rg_max[grp * ld + chunk * SC + c] < bound);          // (NaN: cannot be excluded)
+    }
+  }
+  if (__syncthreads_or(keep) && threadIdx.x == 0) item_list[atomicAdd(list_count, 1)] = item;
+}
+
+
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+static int launch_argmax(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, int grid, cudaStream_t stream) {
+  const int64_t mt = p.n_mtiles;
+  const int64_t n_items = (bs->pair ? (mt + 1) / 2 : mt) * bs->n_chunks;
+  // automatic: only the tensor-bound forms (sample chunks >= 128) with enough items per CTA to pay for the extra launches;
+  // at c2 (chunk 64, bound by the feature map, which pass 1 evaluates in full) two passes cost 0.43 against 0.37 ms
+  if (bs->prune == 0 || (bs->prune == 1 && (n_items < 8ll * grid || bs->SC < 128))) {
+    if (h->two_pass_host) { h->two_pass_host[0] = -1; h->two_pass_host[1] = -1; }
+    return dispatch_fused<0>(h, bs, p, grid, stream);
+  }
+  const size_t n_groups = static_cast<size_t>((p.N + 31) / 32);
+  const size_t o_lb = align256(sizeof(float) * n_groups * bs->Salloc);                    // after rg_max
+  const size_t o_list = o_lb + align256(sizeof(float) * bs->Salloc);
+  const size_t o_cnt = o_list + align256(sizeof(int) * static_cast<size_t>(n_items));
+  unsigned char* scratch = nullptr;
+  TKBO_CUDA_CHECK(cudaMallocAsync(&scratch, o_cnt + 256, stream));
+  cudaError_t e = cudaMemsetAsync(scratch + o_cnt, 0, 256, stream);
+  int rc = TKBO_OK;
+  if (e != cudaSuccess) { set_error(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); rc = TKBO_ERR_CUDA; }
+  RffParams a = p;
+  a.approx = 1;
+  a.rg_max = reinterpret_cast<float*>(scratch);
+  a.lb_out = reinterpret_cast<float*>(scratch + o_lb);
+  a.peer_world = 0; a.peer_merge = 0; a.out_key = nullptr;            // pass 1 reports nothing
+  if (rc == TKBO_OK) rc = dispatch_fused<0>(h, bs, a, grid, stream);
+  int* list = reinterpret_cast<int*>(scratch + o_list);
+  int* count = reinterpret_cast<int*>(scratch + o_cnt);
+  if (rc == TKBO_OK) {
+    mark_items_kernel<<<static_cast<unsigned>(n_items), 256, 0, stream>>>(a.rg_max, a.lb_out, p.N, bs->S, bs->SC, bs->n_chunks,
+                                                                       bs->pair, static_cast<int>(n_items), list, count);
+    h->launches += 1;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(std::string("mark_items_kernel: ") + cudaGetErrorString(e)); rc = TKBO_ERR_CUDA; }
+  }
+  if (rc == TKBO_OK && h->two_pass_host) {
+    h->two_pass_host[1] = static_cast<int>(n_items);
+    cudaMemcpyAsync(h->two_pass_host, count, sizeof(int), cudaMemcpyDeviceToHost, stream);      // diagnostics only
+  }
+  RffParams c = p;
+  c.item_list = list;
+  c.list_count = count;
+  c.ready_flag = nullptr;                                               // every chunk has landed: pass 1 has read them all
+  if (rc == TKBO_OK) rc = dispatch_fused<0>(h, bs, c, grid, stream);
+  e = cudaFreeAsync(scratch, stream);
+  if (e != cudaSuccess && rc == TKBO_OK) { set_error(std::string("cudaFreeAsync: ") + cudaGetErrorString(e)); rc = TKBO_ERR_CUDA; }
+  return rc;
+}
+
 int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, float* out_val,
                int64_t* out_idx, cudaStream_t stream) {
-  RffParams p;
+  RffParams p{};
   int grid = 0;
   int rc = fill_params(h, bs, X, N, &p, &grid);
   if (rc != TKBO_OK) return rc;
@@ -608,7 +706,7 @@ int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int6
   p.out_val = out_val;
   p.out_idx = reinterpret_cast<long long*>(out_idx);
   p.idx_offset = idx_offset;
-  return dispatch_fused<0>(h, bs, p, grid, stream);
+  return launch_argmax(h, bs, p, grid, stream);
 }
 
 // X is being filled by H2D copies on another stream, `rows_per_chunk` (multiple of 128) rows at a time; ready_flag[0]
@@ -617,7 +715,7 @@ int rff_argmax(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int6
 int rff_argmax_streamed(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, int64_t rows_per_chunk,
                         unsigned int* ready_flag, void* const* peer_bufs, int world, int rank, uint64_t epoch,
                         float* out_val, int64_t* out_idx, cudaStream_t stream) {
-  RffParams p;
+  RffParams p{};
   int grid = 0;
   int rc = fill_params(h, bs, X, N, &p, &grid);
   if (rc != TKBO_OK) return rc;
@@ -639,12 +737,12 @@ int rff_argmax_streamed(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_
     p.peer_world = world; p.peer_rank = rank; p.peer_epoch = epoch;
     p.peer_merge = 1; p.peer_status = h->peer_status_dev;
   }
-  return dispatch_fused<0>(h, bs, p, grid, stream);
+  return launch_argmax(h, bs, p, grid, stream);
 }
 
 int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, int64_t* out_key,
                    cudaStream_t stream) {
-  RffParams p;
+  RffParams p{};
   int grid = 0;
   int rc = fill_params(h, bs, X, N, &p, &grid);
   if (rc != TKBO_OK) return rc;
@@ -652,7 +750,7 @@ int rff_argmax_key(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, 
   TKBO_REQUIRE(idx_offset >= 0 && idx_offset + N <= (int64_t(1) << 32) - 1, "global index must stay below 2^32 - 1 for the key form");
   p.out_key = reinterpret_cast<long long*>(out_key);
   p.idx_offset = idx_offset;
-  return dispatch_fused<0>(h, bs, p, grid, stream);
+  return launch_argmax(h, bs, p, grid, stream);
 }
 
 // ---- merge over peer memory ---------------------------------------------------------------------------------------
@@ -671,7 +769,7 @@ struct RffPeer {
 
 int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, int64_t idx_offset, void* const* peer_bufs,
                     int world, int rank, uint64_t epoch, float* out_val, int64_t* out_idx, cudaStream_t stream) {
-  RffParams p;
+  RffParams p{};
   int grid = 0;
   int rc = fill_params(h, bs, X, N, &p, &grid);
   if (rc != TKBO_OK) return rc;
@@ -690,7 +788,7 @@ int rff_argmax_peer(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N,
     p.peer_merge = 1;
     p.peer_status = h->peer_status_dev;
   }
-  return dispatch_fused<0>(h, bs, p, grid, stream);
+  return launch_argmax(h, bs, p, grid, stream);
 }
 
 // Delivery of ready-made keys (or, keys == nullptr, of "nothing seen": a rank whose shard is empty still has to release
@@ -822,7 +920,7 @@ int unpack_argmax_key(tkbo_handle_t h, const int64_t* key, int S, float* out_val
 
 int rff_eval(tkbo_handle_t h, tkbo_basis_t bs, const float* X, int64_t N, float* out_F, int64_t ldf,
              cudaStream_t stream) {
-  RffParams p;
+  RffParams p{};
   int grid = 0;
   int rc = fill_params(h, bs, X, N, &p, &grid);
   if (rc != TKBO_OK) return rc;
@@ -872,7 +970,7 @@ int rff_duel_copeland_partial(tkbo_handle_t h, tkbo_basis_t bs, const float* Xba
   TKBO_REQUIRE(n >= 1 && n <= (1 << 20), "n must be in [1, 2^20]");
   TKBO_REQUIRE(0 <= j_begin && j_begin <= j_end && j_end <= n, "need 0 <= j_begin <= j_end <= n");
   if (j_begin == j_end) return TKBO_OK;
-  RffParams p;
+  RffParams p{};
   const int64_t tpi = (j_end - j_begin + kTileM - 1) / kTileM;       // tiles per i: 128 consecutive j each
   const int64_t mt = static_cast<int64_t>(n) * tpi;
   TKBO_REQUIRE(mt * bs->n_chunks < (int64_t(1) << 31), "too many work items");

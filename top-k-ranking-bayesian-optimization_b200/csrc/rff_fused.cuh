@@ -136,6 +136,18 @@ struct RffParams {
   int pair;                  // 1: launched as clusters of two CTAs that share every tcgen05.mma (template PAIR)
   int halves;                // 1 (pairs, one accumulator buffer, SC % 64 == 0): the accumulator is retired in two column halves,
                              // so the next item's first MMAs overlap the read-out of the second half
+  // Two-pass argmax (MODE 0).  Pass 1 (approx = 1) runs the hi*hi MMAs only - half (fast form) or a third (fp32 form) of the
+  // tensor work.  Per sample it keeps (largest approximate value seen) - 2 eps_s in the running keys (eps2[s] = 2 eps_s,
+  // eps_s >= |full - approximate| in accumulator units) and stores the approximate maximum of every group of 32 rows in
+  // rg_max; its last CTA hands the final bounds out as lb_out.  mark_items_kernel then lists the items in which some row
+  // group comes within 2 eps of the largest approximate value - everything else provably cannot hold (or tie) the
+  // maximum - and pass 2 is the ordinary launch restricted to that list (item_list != nullptr).
+  int approx;
+  const float* eps2;         // [Salloc]
+  float* rg_max;             // pass 1: [ceil(N / 32)][Salloc] approximate maxima per row group (accumulator units)
+  float* lb_out;             // pass 1: [Salloc] final lower bounds
+  const int* item_list;      // pass 2
+  const int* list_count;     // pass 2
   int lead;                  // halves mode: slabs whose half-0 MMAs are issued ahead at the start of an item (0 = the ring depth)
   int nsplit;                // single CTAs: 1 = the two main MMA warps each issue half of the sample columns (N = SC / 2) of
                              // every slab; 0 = one warp issues N = SC.  An MMA with A in TMEM costs >= ~32 cycles
@@ -261,6 +273,20 @@ __device__ __forceinline__ void cos_split16_c8(const uint32_t* __restrict__ arg,
   }
 }
 
+// Pass 1 of the two-pass argmax: only the hi operand is read, so the residual / e4m3 words are left as zeros (three to
+// three and a half instructions per feature).
+template <bool C8v>
+__device__ __forceinline__ void cos_hi16(const uint32_t* __restrict__ arg, uint32_t (&out)[16], bool skip) {
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    float c0 = feature_cos(arg[2 * jj], skip), c1 = feature_cos(arg[2 * jj + 1], skip);
+    if constexpr (C8v) { c0 *= 4096.f; c1 *= 4096.f; }
+    const __half2 h = __floats2half2_rn(c0, c1);
+    out[jj] = *reinterpret_cast<const uint32_t*>(&h);
+    out[8 + jj] = 0u;
+  }
+}
+
 // x = x1 + x2 + x3 exactly, each term a bf16 (truncating the fp32 bits keeps every step exact).
 __device__ __forceinline__ void bf16_split3(float x, uint32_t& b1, uint32_t& b2, uint32_t& b3) {
   const uint32_t u = __float_as_uint(x);
@@ -323,7 +349,10 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const bool leader = (cta == 0u);
   const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);      // item stream of this CTA / pair
   const int n_units = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int n_items = (PAIR ? (p.n_mtiles + 1) / 2 : p.n_mtiles) * n_chunks;
+  const int n_items_all = (PAIR ? (p.n_mtiles + 1) / 2 : p.n_mtiles) * n_chunks;
+  const bool listed = (p.item_list != nullptr) && !p.approx;          // pass 2 of the two-pass argmax: items come from the list
+  const int n_items = listed ? __ldcg(p.list_count) : n_items_all;
+  auto item_of = [&](int i) { return listed ? __ldcg(p.item_list + i) : i; };
   const int my_items = (n_items - unit + n_units - 1) / n_units;
   const int th_rows = PAIR ? SC / 2 : SC;                          // Theta rows of a stage held by this CTA
   const int total = my_items * n_slabs;              // slab iterations of this CTA
@@ -389,7 +418,8 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 #pragma unroll
       for (int t = 0; t < proj_tiles(DT); ++t) tma_load_2d(dst + t * kPTile, &tm_w, full, t * 64, slab_w * kSlabK);
     };
-    for (int item = unit; item < n_items; item += n_units) {
+    for (int it_i = unit; it_i < n_items; it_i += n_units) {
+      const int item = item_of(it_i);
       const int chunk = item % n_chunks;
       for (int slab = 0; slab < n_slabs; ++slab, ++it) {
         if constexpr (PAIR) {
@@ -555,7 +585,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t desc_lo0 = smem_desc_lo(smem0 + (whole ? 0 : h * NH * 128));
     const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
     const uint32_t desc_lopart = static_cast<uint32_t>(th_rows * 128) >> 4;     // Theta-lo tile follows the hi tile
-    const bool hi_only = (p.debug & 1) != 0;
+    const bool hi_only = (p.debug & 1) != 0 || p.approx != 0;
     const bool pairing = ring >= 5 && !(p.debug & 8);  // a pair holds two ring slots while its MMAs run
     const bool halves = PAIR && p.halves;
     const int total_main = ((PAIR && (h != 0 || !leader || halves)) || (!PAIR && whole && h != 0)) ? 0 : total;
@@ -755,9 +785,12 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int q = warp & 3;                          // TMEM lane quarter of this warp
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const bool skip = (p.debug & 2) != 0;
-    auto split16 = [](const uint32_t* a, uint32_t (&o)[16], bool sk) {
+    const bool approx = p.approx != 0;               // pass 1 of the two-pass argmax reads the hi operand only
+    auto split16 = [approx](const uint32_t* a, uint32_t (&o)[16], bool sk) {
       // four producer groups = the shapes bound by the feature map (XU pipe): part of the cos goes to the FMA pipe
-      if constexpr (C8) cos_split16_c8(a, o, sk); else cos_split16<NPG == 4>(a, o, sk);
+      if (approx) cos_hi16<C8>(a, o, sk);
+      else if constexpr (C8) cos_split16_c8(a, o, sk);
+      else cos_split16<NPG == 4>(a, o, sk);
     };
     if ((NPG == 2 || NPG == 4) && p.coop) {
       // latency form: every slab is converted by two groups, each taking 32 of its 64 columns.  Two groups: both work on
@@ -834,8 +867,8 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // j - xa_bufs, when every projection that read the buffer has long completed.  K order per input dimension i:
     // x1 x1 x2 x1 x2 x3 (against w1 w2 w1 w3 w2 w1), then three ones (against b1 b2 b3), zero padding.
     auto stage_rows = [&](int j) {
-      const int item = unit + j * n_units;
-      if (item >= n_items) return;
+      if (unit + j * n_units >= n_items) return;
+      const int item = item_of(unit + j * n_units);
       const int xb = (xa_bufs == 2) ? (j & 1) : 0;
       // PAIR: this CTA's tile of the pair; an odd tile count leaves the peer's last tile empty (clamped here, skipped in
       // the epilogue)
@@ -931,7 +964,8 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // reduction + atomicMax runs only for blocks that may improve a sample -- after the first tiles that is rare
     // (a sample's maximum improves ~ln(#tiles) times).  Ties go through the slow path: the key's ~row decides.
 
-    for (int item = unit; item < n_items; item += n_units, ++nitem) {
+    for (int it_i = unit; it_i < n_items; it_i += n_units, ++nitem) {
+      const int item = item_of(it_i);
       const int mtile = PAIR ? 2 * (item / n_chunks) + static_cast<int>(cta) : item / n_chunks;
       const int chunk = item % n_chunks;
       const int s_base = chunk * SC;
@@ -999,6 +1033,17 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 #pragma unroll
               for (int c = 0; c < 32; ++c) v[c] = row_ok ? v[c] : 0xFF800000u;     // -inf
             }
+            if (p.approx) {
+              // approximate maximum of this warp's 32 rows in each of the block's 32 columns (NaN rows drop out of the
+              // max; an all-NaN group yields NaN, which the marking kernel treats as "cannot be excluded")
+              float gm = -INFINITY;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const float m = warp_max_f32(__uint_as_float(v[c]));
+                if (lane == c) gm = m;
+              }
+              p.rg_max[(static_cast<long long>(mtile) * 4 + q) * (static_cast<long long>(SC) * n_chunks) + s_base + j * 32 + lane] = gm;
+            }
             bool reach = false;                        // !(val < bound): also true for NaN, which the slow path skips
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
@@ -1021,9 +1066,17 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
               // lane c holds (max, rows attaining it) of column c; record it if it may beat (or tie) the bound
               const int cs = j * 32 + lane;
               if (minehit != 0u && mine > -INFINITY && !(mine < thr_s[cs]) && s_base + cs < p.S) {
-                atomicMax(p.packed + s_base + cs,
-                          pack_val_row(mine + 0.0f, static_cast<uint32_t>(row0) + (__ffs(minehit) - 1)));
-                thr_s[cs] = mine;                      // racing warps may leave the lower of two finds: still a lower bound
+                if (p.approx) {
+                  // pass 1: the recorded bound is 2 eps below the largest approximate value: a value that reaches it may,
+                  // in full precision, reach the largest value seen
+                  const float lb = mine - __ldg(p.eps2 + s_base + cs);
+                  atomicMax(p.packed + s_base + cs, pack_val_row(lb + 0.0f, static_cast<uint32_t>(row0) + (__ffs(minehit) - 1)));
+                  if (!(lb < thr_s[cs])) thr_s[cs] = lb;
+                } else {
+                  atomicMax(p.packed + s_base + cs,
+                            pack_val_row(mine + 0.0f, static_cast<uint32_t>(row0) + (__ffs(minehit) - 1)));
+                  thr_s[cs] = mine;                    // racing warps may leave the lower of two finds: still a lower bound
+                }
               }
               __syncwarp();
             }
@@ -1120,7 +1173,17 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       peer_timed_out = 0;
     }
     __syncthreads();
-    if (is_last_cta) {
+    if (is_last_cta && p.approx) {
+      // pass 1: nothing to report yet.  Hand the final bounds to the marking kernel and clear the keys (pass 2 starts from
+      // scratch with exact values)
+      __threadfence();
+      for (int s = threadIdx.x; s < p.SC * n_chunks; s += blockDim.x) {
+        const unsigned long long pk = __ldcg(p.packed + s);
+        p.lb_out[s] = (pk == 0ull) ? -INFINITY : f32_from_orderable(static_cast<uint32_t>(pk >> 32));
+        p.packed[s] = 0ull;
+      }
+      if (threadIdx.x == 0) *p.done_counter = 0u;
+    } else if (is_last_cta) {
       __threadfence();
       for (int s = threadIdx.x; s < p.S; s += blockDim.x) {
         const unsigned long long pk = __ldcg(p.packed + s);

@@ -381,6 +381,15 @@ class SharedBasis:
         out["producers_share_slab"] &= 1
         return out
 
+    def two_pass_items(self):
+        """(items the full-precision pass of the last argmax covered, items in all), or None if it ran as a single pass.
+        Large argmax calls run a hi*hi-only pass over everything and the full contraction only where the maximum can be
+        (csrc/rff.cu: launch_argmax); the results are the same bits either way.  Synchronises the device."""
+        self._torch.cuda.synchronize(self.device)
+        a, b = ctypes.c_int(-1), ctypes.c_int(-1)
+        nat.check(nat.lib().tkbo_two_pass_items(self._h, ctypes.byref(a), ctypes.byref(b)), "tkbo_two_pass_items")
+        return None if a.value < 0 else (a.value, b.value)
+
     def _candidates(self, X):
         X = _f32(X, self.device)
         assert X.dim() == 2 and X.shape[1] == self.d, "candidates must be (N, d)"
