@@ -663,7 +663,12 @@ static int launch_argmax(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, i
   const size_t o_list = o_lb + align256(sizeof(float) * bs->Salloc);
   const size_t o_cnt = o_list + align256(sizeof(int) * static_cast<size_t>(n_items));
   unsigned char* scratch = nullptr;
-  TKBO_CUDA_CHECK(cudaMallocAsync(&scratch, o_cnt + 256, stream));
+  if (cudaMallocAsync(&scratch, o_cnt + 256, stream) != cudaSuccess) {
+    // no room for the row-group maxima (N / 32 x S floats): the single pass needs no scratch and gives the same result
+    cudaGetLastError();
+    if (h->two_pass_host) { h->two_pass_host[0] = -1; h->two_pass_host[1] = -1; }
+    return dispatch_fused<0>(h, bs, p, grid, stream);
+  }
   cudaError_t e = cudaMemsetAsync(scratch + o_cnt, 0, 256, stream);
   int rc = TKBO_OK;
   if (e != cudaSuccess) { set_error(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); rc = TKBO_ERR_CUDA; }
