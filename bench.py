@@ -3,7 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c4|c4d] [--no-blocks] [--no-cpu]
 
-A step = one fused RFF-sample + per-sample argmax pass over the synthetic candidate set.  Default workload c3
+A step = one fused RFF-sample + per-sample argmax call over the synthetic candidate set (tkbo_rff_argmax; at the tensor-bound
+shapes the library runs it as two passes of the same kernel - the hi*hi MMAs over every work item, then the full contraction
+over the items that can hold a maximum - with the result bits of a single pass; roofline.two_pass says how many items the
+second pass covered).  Default workload c3
 (BASELINE.json configs[2], the largest single-GPU configuration): N = 2^24 Hartmann-6 candidates, d = 6, D = 4096
 features, S = 256 posterior samples -- STRONG scaling: the 2^24 candidates are split into contiguous 128-row-aligned
 shards over the N ranks (one process per GPU, torchrun), the basis is replicated, and each rank's S (value, index) keys
@@ -15,8 +18,8 @@ Printed JSON (rank 0, one line):
   e2e           the same through the C ABI with HOST buffers (tkbo_rff_argmax_host / _host_peer): every step copies the
                 rank's pinned candidates and the float64 basis to the device, runs the one fused launch (which merges the
                 ranks' keys itself) and reads the S global results back
-  roofline      fused kernel against the tensor pipe: algorithmic flops 2*N*D*S per launch, the executed figure (the
-                fp32-emulating split issues 3 fp16 MMAs per product + the projection), which contraction form ran
+  roofline      fused kernel against the tensor pipe: algorithmic flops 2*N*D*S per step, the executed figure (what the
+                passes issue in 16-bit-MMA equivalents + the projection), which contraction form ran
   parity        in-run check of the timed kernel against the fp64 oracle on a 2^16-candidate sample, in BOTH contraction
                 forms: max |dv| / max|f|, argmax mismatches, tie count (top-2 gap below 1e-4)
   cpu_baseline  the CPU oracle port timed on this host on a bounded sample
@@ -338,7 +341,7 @@ def k1_roofline(cfg, n_rows, D, S, ms, pk, form, facts_key, long_run, two_pass=N
             "tensor_pipe_active_pct_ncu": facts.get("tensor_pipe_active_pct"), "ncu_source": facts.get("source"),
             "algorithmic_bytes_per_launch": 4.0 * n_rows * cfg["d_template"],
             "mufu": {"cos_per_s": cos_rate, "peak_cos_per_s": cos_peak, "frac": cos_rate / cos_peak},
-            "note": f"achieved = algorithmic 2*N*D*S of ONE launch on one GPU ({n_rows} candidates) / its CUDA-event duration "
+            "note": f"achieved = algorithmic 2*N*D*S of ONE argmax call on one GPU ({n_rows} candidates) / its CUDA-event duration "
                     f"(median over the timed steps); executed = what the tensor pipe does in 16-bit-MMA equivalents: {mma_eq} per "
                     f"product ({'fp16 hi*hi + one e4m3 MMA for both corrections' if mma_eq == 2 else 'hi*hi + hi*lo + lo*hi, fp32-accurate'}) "
                     f"+ the bf16x3 projection X W^T + b (K = {proj_k}); the kernel issues fp16 / bf16 / e4m3 MMAs, never TF32, so the "
