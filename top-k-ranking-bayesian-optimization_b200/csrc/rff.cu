@@ -125,7 +125,8 @@ prep_basis_kernel(const double* __restrict__ Theta, int transposed, const double
   // eps2[s] (stored behind the Salloc unscale factors) = 2 eps_s in accumulator units, eps_s >= |full - hi*hi-only value|:
   // the two correction terms are at most (2^-11 + 2^-12) amp sum|v| (fp16 half-ulps of both operands, |Phi operand| <= amp
   // = 4096 in the fast form, 1 otherwise; the e4m3 corrections of the fast form approximate the same two terms), rounded
-  // up to 1.25 x 2^-10 (the fast form's e4m3-rounded corrections reach 2^-10.3); every accumulator update truncates by < 2^-23 of a partial sum that is <= amp sum|v|, and the two passes
+  // up to 2^-9 (the fast form's e4m3-rounded corrections reach 2^-10.3: a margin of 2.4, which costs a handful of extra items
+// in pass 2); every accumulator update truncates by < 2^-23 of a partial sum that is <= amp sum|v|, and the two passes
   // make Dpad / 16 and at most 3 Dpad / 16 updates.
   __syncthreads();
   red[threadIdx.x] = l1;
@@ -136,7 +137,7 @@ prep_basis_kernel(const double* __restrict__ Theta, int transposed, const double
   }
   if (threadIdx.x == 0) {
     const double amp = corr8 ? 4096.0 : 1.0;
-    const double eps = amp * red[0] * (1.25 * ldexp(1.0, -10) + (Dpad / 4.0) * ldexp(1.0, -23));
+    const double eps = amp * red[0] * (ldexp(1.0, -9) + (Dpad / 4.0) * ldexp(1.0, -23));
     unscale[Salloc + s] = static_cast<float>(2.02 * eps);
   }
 }
