@@ -793,7 +793,8 @@ def run_gpu(args):
                 blocks["c4d"] = bd
         if ctx.world == 1:
             if name != "c2":
-                blocks["c2"] = k1_block(ctx, "c2", args, "auto", 20, 5, with_e2e=True, long_run=False,
+                # (0.4 ms steps right after the power-capped c3 blocks: 200 warm-up steps let the SM clock settle first)
+                blocks["c2"] = k1_block(ctx, "c2", args, "auto", 50, 200, with_e2e=True, long_run=False,
                                         parity_rows=0 if args.no_cpu else (1 << 16))
             blocks["c5_mpes"] = mpes_block(ctx, args)
             blocks["c1"] = c1_block(ctx, args)
