@@ -543,7 +543,7 @@ def test_singular_regression_retries_then_fails(pbo):
 
 
 @pytest.mark.parametrize("N,d,D,S,form", [(40000, 3, 192, 256, "fp32"), (40000, 3, 192, 256, "fast"), (30001, 6, 320, 300, "fast"),
-                                          (9000, 4, 128, 64, "fp32")])
+                                          (9000, 4, 128, 160, "fp32")])
 def test_two_pass_argmax_equals_single_pass(pbo, monkeypatch, N, d, D, S, form):
     """Large argmax calls run a hi*hi-only pass over everything and the full contraction only over the items that can hold a
     maximum (csrc/rff.cu: launch_argmax).  Forced on here (TKBO_PRUNE=2) against the single pass (TKBO_PRUNE=0): the same

@@ -655,7 +655,7 @@ static int launch_argmax(tkbo_handle_t h, tkbo_basis_t bs, const RffParams& p, i
   const int64_t n_items = (bs->pair ? (mt + 1) / 2 : mt) * bs->n_chunks;
   // automatic: only the tensor-bound forms (sample chunks >= 128) with enough items per CTA to pay for the extra launches;
   // at c2 (chunk 64, bound by the feature map, which pass 1 evaluates in full) two passes cost 0.43 against 0.37 ms
-  if (bs->prune == 0 || (bs->prune == 1 && (n_items < 8ll * grid || bs->SC < 128))) {
+  if (bs->prune == 0 || bs->npg == 4 || (bs->prune == 1 && (n_items < 8ll * grid || bs->SC < 128))) {
     if (h->two_pass_host) { h->two_pass_host[0] = -1; h->two_pass_host[1] = -1; }
     return dispatch_fused<0>(h, bs, p, grid, stream);
   }

@@ -350,7 +350,12 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);      // item stream of this CTA / pair
   const int n_units = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int n_items_all = (PAIR ? (p.n_mtiles + 1) / 2 : p.n_mtiles) * n_chunks;
-  const bool listed = (p.item_list != nullptr) && !p.approx;          // pass 2 of the two-pass argmax: items come from the list
+  // The two-pass argmax exists for the tensor-bound forms only (the host never asks the four-group form for it): compiled out
+  // of the NPG = 4 instances, whose timing is sensitive to every instruction around their producers (c2: 0.365 -> 0.43 ms
+  // with the run-time branches in place)
+  constexpr bool kTwoPass = (MODE == 0) && (NPG != 4);
+  const bool approx_pass = kTwoPass && p.approx != 0;
+  const bool listed = kTwoPass && (p.item_list != nullptr) && !approx_pass;   // pass 2: items come from the list
   const int n_items = listed ? __ldcg(p.list_count) : n_items_all;
   auto item_of = [&](int i) { return listed ? __ldcg(p.item_list + i) : i; };
   const int my_items = (n_items - unit + n_units - 1) / n_units;
@@ -585,7 +590,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t desc_lo0 = smem_desc_lo(smem0 + (whole ? 0 : h * NH * 128));
     const uint32_t desc_stage = static_cast<uint32_t>(sbytes) >> 4;
     const uint32_t desc_lopart = static_cast<uint32_t>(th_rows * 128) >> 4;     // Theta-lo tile follows the hi tile
-    const bool hi_only = (p.debug & 1) != 0 || p.approx != 0;
+    const bool hi_only = (p.debug & 1) != 0 || approx_pass;
     const bool pairing = ring >= 5 && !(p.debug & 8);  // a pair holds two ring slots while its MMAs run
     const bool halves = PAIR && p.halves;
     const int total_main = ((PAIR && (h != 0 || !leader || halves)) || (!PAIR && whole && h != 0)) ? 0 : total;
@@ -785,7 +790,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int q = warp & 3;                          // TMEM lane quarter of this warp
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const bool skip = (p.debug & 2) != 0;
-    const bool approx = p.approx != 0;               // pass 1 of the two-pass argmax reads the hi operand only
+    const bool approx = approx_pass;                 // pass 1 of the two-pass argmax reads the hi operand only
     auto split16 = [approx](const uint32_t* a, uint32_t (&o)[16], bool sk) {
       // four producer groups = the shapes bound by the feature map (XU pipe): part of the cos goes to the FMA pipe
       if (approx) cos_hi16<C8>(a, o, sk);
@@ -1033,7 +1038,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 #pragma unroll
               for (int c = 0; c < 32; ++c) v[c] = row_ok ? v[c] : 0xFF800000u;     // -inf
             }
-            if (p.approx) {
+            if (approx_pass) {
               // approximate maximum of this warp's 32 rows in each of the block's 32 columns (NaN rows drop out of the
               // max; an all-NaN group yields NaN, which the marking kernel treats as "cannot be excluded")
               float gm = -INFINITY;
@@ -1066,7 +1071,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
               // lane c holds (max, rows attaining it) of column c; record it if it may beat (or tie) the bound
               const int cs = j * 32 + lane;
               if (minehit != 0u && mine > -INFINITY && !(mine < thr_s[cs]) && s_base + cs < p.S) {
-                if (p.approx) {
+                if (approx_pass) {
                   // pass 1: the recorded bound is 2 eps below the largest approximate value: a value that reaches it may,
                   // in full precision, reach the largest value seen
                   const float lb = mine - __ldg(p.eps2 + s_base + cs);
@@ -1173,7 +1178,7 @@ rff_fused_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       peer_timed_out = 0;
     }
     __syncthreads();
-    if (is_last_cta && p.approx) {
+    if (is_last_cta && approx_pass) {
       // pass 1: nothing to report yet.  Hand the final bounds to the marking kernel and clear the keys (pass 2 starts from
       // scratch with exact values)
       __threadfence();
