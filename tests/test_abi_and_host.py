@@ -359,3 +359,42 @@ def test_bench_reference_arm_contract():
     cb = j["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_two_pass_bound_covers_the_correction_terms_in_simulation():
+    """The two-pass argmax (csrc/rff.cu: launch_argmax) excludes rows whose hi*hi-only value lies more than 2 eps_s below the
+    largest one, with eps_s = A * sum_j |hi(theta'_sj)| * (2^-9 + Dpad/4 * 2^-23) (prep_basis_kernel).  NumPy / torch restatement
+    of both operand splits - fp16 hi/lo (fp32 form) and fp16 hi + e4m3 corrections on u = 4096 cos (fast form) - on random
+    data: the dropped terms never exceed eps_s, with the margin DESIGN section 3 states."""
+    import torch
+    rng = np.random.default_rng(5)
+    D, S, R = 512, 8, 400
+    theta = rng.standard_normal((D, S)) * rng.uniform(0.2, 5.0, size=(1, S)) * np.sqrt(2.0 / D)
+    phi = np.cos(rng.uniform(-40.0, 40.0, size=(R, D)))
+
+    def f16(a):
+        return a.astype(np.float16).astype(np.float64)
+
+    def e4m3(a):
+        return torch.from_numpy(np.asarray(a, dtype=np.float32)).to(torch.float8_e4m3fn).to(torch.float64).numpy()
+
+    worst = {"fp32": 0.0, "fast": 0.0}
+    for s in range(S):
+        amax = np.abs(theta[:, s]).max()
+        # fp32 form: max |v| in [2^9, 2^10); fast form: [2^7, 2^8)
+        for form, top, amp in (("fp32", 9, 1.0), ("fast", 7, 4096.0)):
+            v = theta[:, s] * 2.0 ** (top - np.floor(np.log2(amax)))
+            vh = f16(v)
+            eps = amp * np.abs(vh).sum() * (2.0 ** -9 + (D / 4.0) * 2.0 ** -23)
+            if form == "fp32":
+                vl = f16(v - vh)
+                ph = f16(phi)
+                pl = f16(phi - ph)
+                dropped = ph @ vl + pl @ vh
+            else:
+                u = phi * 4096.0
+                uh = f16(u)
+                dropped = e4m3(phi) @ e4m3(4096.0 * (v - vh)) + e4m3(u - uh) @ e4m3(v)
+            assert np.all(np.abs(dropped) <= eps), (form, s)
+            worst[form] = max(worst[form], float(np.abs(dropped).max() / eps))
+    assert worst["fp32"] < 0.5 and worst["fast"] < 0.5       # random signs: far inside the worst-case bound
