@@ -24,7 +24,8 @@ Printed JSON (rank 0, one line):
                 forms: max |dv| / max|f|, argmax mismatches, tie count (top-2 gap below 1e-4)
   cpu_baseline  the CPU oracle port timed on this host on a bounded sample
   blocks        c2 (configs[1]), c5 = K2 MPES kernel + the device acquisition pipeline, c1 (ascent at the MPES_Forr sizes),
-                the fast contraction form at the headline shape, and at 8 GPUs c4 (argmax and duel mode)
+                the fast contraction form at the headline shape, the headline call as a single full-precision pass
+                (TKBO_PRUNE=0), and at 8 GPUs c4 (argmax and duel mode)
   run           tiling, L2 note, merge: everything descriptive that is not part of `config` (both arms share `config`)
 
 `--impl reference` times the CPU implementation of the same path (the fp64 NumPy oracle port of the reference's
@@ -782,6 +783,20 @@ def run_gpu(args):
         fast = k1_block(ctx, name, args, "fast", sub_steps, 3, with_e2e=False, long_run=(name != "c2"))
         if ctx.rank == 0:
             blocks[f"{name}_fast_form"] = fast
+        if name != "c2":
+            # the same call as ONE pass over everything in full precision (TKBO_PRUNE=0): what the headline would be without the
+            # two-pass argmax, and the launch whose tensor-pipe figure profiles/r02_prof_k1_c3_*_summary.txt shows
+            prev = os.environ.get("TKBO_PRUNE")
+            os.environ["TKBO_PRUNE"] = "0"
+            try:
+                single = k1_block(ctx, name, args, "auto", sub_steps, 3, with_e2e=False, long_run=True)
+            finally:
+                if prev is None:
+                    os.environ.pop("TKBO_PRUNE", None)
+                else:
+                    os.environ["TKBO_PRUNE"] = prev
+            if ctx.rank == 0:
+                blocks[f"{name}_single_pass"] = single
         if ctx.world == 8:
             for other in ("c4",):
                 if other != name:
